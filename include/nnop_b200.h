@@ -1,0 +1,162 @@
+/*
+ * nnop_b200.h -- C ABI of libnnop_b200.so, the B200 (sm_100a) implementation of the
+ * NNop.jl hot path.  Every entry point is what a Julia `ccall` in the NNop shim binds in
+ * place of a KernelAbstractions launch of the reference (file:line cited per function,
+ * relative to pxl-th/NNop.jl v0.2.0).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers (CuArray / torch.cuda storage) unless named host_*.
+ *    The library never allocates, frees or retains user-visible memory; outputs,
+ *    residuals and workspaces are supplied by the caller.
+ *  - Arrays are in the reference's column-major layout.  A Julia (E, L, H, B) array is the
+ *    same bytes as a row-major (B, H, L, E) array; the comments below give the Julia shape.
+ *  - `stream` is a cudaStream_t / CUstream passed as void*.  Calls only enqueue work; they
+ *    never synchronise the device.
+ *  - Return value: 0 (NNOP_OK) on success, otherwise an nnop_status_t; a human-readable
+ *    message for the calling thread is available from nnop_last_error_string().
+ *  - dtype: element type T of q/k/v/x...; softmax statistics, lse, rstd, mean are float.
+ */
+#ifndef NNOP_B200_H
+#define NNOP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNOP_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  NNOP_F32 = 0,  /* Float32  */
+  NNOP_F16 = 1,  /* Float16  */
+  NNOP_BF16 = 2  /* BFloat16 */
+} nnop_dtype_t;
+
+typedef enum {
+  NNOP_OK = 0,
+  NNOP_ERR_SHAPE = 1,         /* shape violation; message mirrors src/attention.jl:141-144 */
+  NNOP_ERR_DTYPE = 2,
+  NNOP_ERR_UNSUPPORTED_E = 3, /* embedding dim not a power of two / out of range */
+  NNOP_ERR_WORKSPACE = 4,     /* workspace NULL or too small */
+  NNOP_ERR_CUDA = 5,          /* a CUDA runtime / driver call failed */
+  NNOP_ERR_ARG = 6            /* NULL pointer or otherwise invalid argument */
+} nnop_status_t;
+
+typedef struct {
+  int sm_count;
+  int cc_major, cc_minor;
+  size_t shared_mem_per_block_optin; /* replaces NNop._shared_memory, ext/NNopCUDAExt.jl:6-9 */
+  size_t l2_bytes;
+  size_t hbm_bytes;
+} nnop_device_info_t;
+
+int nnop_version(void);
+const char* nnop_last_error_string(void);
+/* Replaces NNop.shared_memory / _shared_memory (src/NNop.jl:27-30, ext/NNopCUDAExt.jl:6-9). */
+int nnop_device_info(int device, nnop_device_info_t* out);
+
+/* Attention kernel selection (diagnostics / tests).  0 = auto (tcgen05 path whenever the
+ * problem qualifies), 1 = force the generic SIMT path, 2 = require the tcgen05 path (returns
+ * NNOP_ERR_ARG if the problem does not qualify).  Process-wide. */
+int nnop_set_attention_path(int mode);
+/* 1 if the last flash-attention call on this thread ran the tcgen05 path, else 0. */
+int nnop_last_attention_path(void);
+
+/* ---------------------------------------------------------------------------------------
+ * flash attention forward.  Replaces `_flash_attention` + kernel `_flash_attention_fwd!`
+ * (src/attention.jl:133-177, :1-131).
+ *   o    (E, QL, QH, B)  T      out
+ *   lse  (QL, QH, B)     float  out: m + log(l), natural log, of the scaled+biased+masked
+ *                               logits.  Replaces the reference residual pair (ms, ls)
+ *                               (src/attention.jl:166-168).  -inf for a fully masked row,
+ *                               whose output row is 0 (the reference yields NaN there).
+ *   q    (E, QL, QH, B)  T ;  k, v (E, KL, KH, B) T ; QH % KH == 0 (GQA; q-head j reads
+ *                               kv-head j / (QH/KH), src/attention.jl:28)
+ *   pair       (QH, QL, KL, B) T  or NULL : additive logit bias   (src/attention.jl:59-64)
+ *   kpad_mask  (KL, B) uint8 0/1  or NULL : 1 = attend            (src/attention.jl:73-79)
+ *   causal     keep k_idx <= q_idx (top-left aligned)             (src/attention.jl:67-72)
+ *   scale      logit scale; the reference always passes 1/sqrt(E) (src/attention.jl:154)
+ */
+int nnop_flash_attn_fwd(void* o, float* lse, const void* q, const void* k, const void* v,
+                        const void* pair, const uint8_t* kpad_mask, int dtype, int E, int QL,
+                        int KL, int QH, int KH, int B, int causal, float scale, void* stream);
+
+/* Workspace needed by nnop_flash_attn_bwd for these dims (delta, fp32 dQ accumulator). */
+size_t nnop_flash_attn_bwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH,
+                                           int B);
+
+/* flash attention backward.  Replaces `∇flash_attention` + kernels
+ * `_flash_attention_bwd_preprocess!` and `_flash_attention_bwd!`
+ * (src/attention_bwd.jl:199-275, :163-197, :1-161).
+ *   dq (E,QL,QH,B), dk, dv (E,KL,KH,B)  T out -- fully overwritten (no pre-zeroing needed)
+ *   dpair (QH,QL,KL,B) T out or NULL (required iff pair != NULL)
+ *   dO, o (E,QL,QH,B) T ; lse from the forward; remaining arguments as in the forward.
+ */
+int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, const void* dO,
+                        const void* o, const float* lse, const void* q, const void* k,
+                        const void* v, const void* pair, const uint8_t* kpad_mask, int dtype,
+                        int E, int QL, int KL, int QH, int KH, int B, int causal, float scale,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * online softmax over dim 1 of x (N, cols).  Replaces `online_softmax` / `online_softmax!`
+ * (src/softmax.jl:60-68, :19-58) and `∇online_softmax` (src/softmax.jl:70-80).
+ */
+int nnop_softmax_fwd(void* y, const void* x, int dtype, int64_t N, int64_t cols, void* stream);
+int nnop_softmax_bwd(void* dx, const void* dy, const void* y, int dtype, int64_t N,
+                     int64_t cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * RMS norm over dim 1 of x (emb, n).  Replaces `_rms_norm` / `_rms_norm!`
+ * (src/rms_norm.jl:117-137, :3-38) and `∇rms_norm` / `_∇rms_norm!` (:139-169, :43-115).
+ *   y (emb,n) T out ; rstd (n) float out (the reference's `rms` residual, :27)
+ *   dw_f32 (emb) float out -- Float32 for every T, as the reference (:146)
+ */
+int nnop_rms_norm_fwd(void* y, float* rstd, const void* x, const void* w, int dtype,
+                      int64_t emb, int64_t n, float eps, float offset, void* stream);
+size_t nnop_norm_bwd_workspace_bytes(int64_t emb, int64_t n);
+int nnop_rms_norm_bwd(void* dx, float* dw_f32, const void* dy, const float* rstd, const void* x,
+                      const void* w, int dtype, int64_t emb, int64_t n, float offset,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * layer norm over dim 1 of x (emb, n).  Replaces `_layer_norm` / `_layer_norm!`
+ * (src/layer_norm.jl:150-170, :8-63) and `∇layer_norm` / `_∇layer_norm!` (:172-204, :65-148).
+ *   mean, rstd (n) float out (reference residuals μ, Σ; Σ holds rstd, :50)
+ *   dw, db (emb) T out (eltype(w), eltype(b) in the reference, :179-180)
+ */
+int nnop_layer_norm_fwd(void* y, float* mean, float* rstd, const void* x, const void* w,
+                        const void* b, int dtype, int64_t emb, int64_t n, float eps,
+                        void* stream);
+int nnop_layer_norm_bwd(void* dx, void* dw, void* db, const void* dy, const float* mean,
+                        const float* rstd, const void* x, const void* w, int dtype,
+                        int64_t emb, int64_t n, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Llama RoPE.  Replaces `_llama_rope` / `llama_rope!` (src/rope/llama_rope.jl:69-89, :24-65)
+ * out-of-place (fuses the reference's `copy(q)`, `copy(k)` at :75-76).
+ *   q_out,q_in (E,L,QH,B) T ; k_out,k_in (E,L,KH,B) T ; cos, sin (E,L,B) float, only rows
+ *   1..E/2 are read (:43-44).  sin_sign = +1 forward, -1 backward (:86).
+ *   In-place use (q_out == q_in) is allowed.
+ */
+int nnop_llama_rope(void* q_out, void* k_out, const void* q_in, const void* k_in,
+                    const float* cos, const float* sin, int dtype, int E, int64_t L, int QH,
+                    int KH, int B, float sin_sign, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Hardware self-test of the tcgen05/TMA building blocks (diagnostics; used by tests).
+ * Runs one 128x128x128 bf16 GEMM through an operand form the attention kernels use and
+ * writes the 128x128 fp32 result to d_out; a, b are 128x128 bf16 row-major device buffers.
+ *   which 0: A B^T, TMA + K-major smem operands        which 1: A B, A in TMEM, B MN-major
+ *   which 2: A B^T, thread-written swizzled smem       which 3: A^T B, both MN-major
+ *   which 4: A B, A K-major, B MN-major
+ */
+int nnop_selftest_umma(float* d_out, const void* a, const void* b, int which, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNOP_B200_H */

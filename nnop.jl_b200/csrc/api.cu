@@ -1,0 +1,203 @@
+// api.cu -- C-ABI entry points of libnnop_b200.so for flash attention, plus error / device
+// plumbing.  Validation mirrors the reference launcher (`_flash_attention`,
+// src/attention.jl:141-144; `∇flash_attention`, src/attention_bwd.jl:210-213), including the
+// wording of its error strings.
+#include <cuda.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "internal.h"
+
+namespace nnop {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_last_path = 0;
+static std::atomic<int> g_path_mode{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void clear_error() { g_err[0] = '\0'; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_3d(void* tmap_out, const void* base, int dtype, uint64_t inner, uint64_t rows,
+                 uint64_t outer, uint32_t box_inner, uint32_t box_rows) {
+  const uint64_t elem_bytes = dtype == NNOP_F32 ? 4 : 2;
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(NNOP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[3] = {inner, rows, outer};
+  const cuuint64_t strides[2] = {inner * elem_bytes, inner * rows * elem_bytes};
+  const cuuint32_t box[3] = {box_inner, box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = dtype == NNOP_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == NNOP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                     : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(static_cast<CUtensorMap*>(tmap_out), dt, 3, const_cast<void*>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(NNOP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return NNOP_OK;
+}
+
+static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+static int validate(int dtype, int E, int QL, int KL, int QH, int KH, int B) {
+  if (dtype != NNOP_F32 && dtype != NNOP_F16 && dtype != NNOP_BF16)
+    return fail(NNOP_ERR_DTYPE, "unknown dtype code %d", dtype);
+  if (E <= 0 || QL < 0 || KL < 0 || QH <= 0 || KH <= 0 || B < 0)
+    return fail(NNOP_ERR_SHAPE, "Invalid attention shape E=%d QL=%d KL=%d QH=%d KH=%d B=%d.", E, QL,
+                KL, QH, KH, B);
+  if (!is_pow2(E)) return fail(NNOP_ERR_UNSUPPORTED_E, "Only power-of-2 embedding dims are supported.");
+  if (E < 16 || E > 256)
+    return fail(NNOP_ERR_UNSUPPORTED_E,
+                "Embedding dim `%d` is not supported (power of 2 in [16, 256]).", E);
+  if (QH % KH != 0)
+    return fail(NNOP_ERR_SHAPE,
+                "Number of query heads `%d` must be divisible by number of KV heads `%d`.", QH, KH);
+  return NNOP_OK;
+}
+
+}  // namespace nnop
+
+using namespace nnop;
+
+extern "C" int nnop_version(void) { return NNOP_B200_VERSION; }
+extern "C" const char* nnop_last_error_string(void) { return g_err; }
+
+extern "C" int nnop_device_info(int device, nnop_device_info_t* out) {
+  clear_error();
+  if (!out) return fail(NNOP_ERR_ARG, "NULL pointer");
+  cudaDeviceProp prop;
+  NNOP_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  out->sm_count = prop.multiProcessorCount;
+  out->cc_major = prop.major;
+  out->cc_minor = prop.minor;
+  out->shared_mem_per_block_optin = prop.sharedMemPerBlockOptin;
+  out->l2_bytes = static_cast<size_t>(prop.l2CacheSize);
+  out->hbm_bytes = prop.totalGlobalMem;
+  return NNOP_OK;
+}
+
+extern "C" int nnop_set_attention_path(int mode) {
+  if (mode < 0 || mode > 2) return fail(NNOP_ERR_ARG, "attention path mode must be 0, 1 or 2");
+  g_path_mode.store(mode);
+  return NNOP_OK;
+}
+extern "C" int nnop_last_attention_path(void) { return g_last_path; }
+
+extern "C" int nnop_flash_attn_fwd(void* o, float* lse, const void* q, const void* k, const void* v,
+                                   const void* pair, const uint8_t* kpad_mask, int dtype, int E,
+                                   int QL, int KL, int QH, int KH, int B, int causal, float scale,
+                                   void* stream) {
+  clear_error();
+  if (int rc = validate(dtype, E, QL, KL, QH, KH, B)) return rc;
+  if (static_cast<int64_t>(B) * QL == 0) return NNOP_OK;
+  if (!o || !lse || !q || (KL > 0 && (!k || !v))) return fail(NNOP_ERR_ARG, "NULL pointer");
+  AttnParams p{};
+  p.o = o; p.lse = lse; p.q = q; p.k = k; p.v = v; p.pair = pair; p.kpad = kpad_mask;
+  p.dtype = dtype; p.E = E; p.QL = QL; p.KL = KL; p.QH = QH; p.KH = KH; p.B = B;
+  p.causal = causal ? 1 : 0; p.scale = scale;
+  p.stream = static_cast<cudaStream_t>(stream);
+  const int mode = g_path_mode.load();
+  const bool fast_ok = attn_sm100_supported(p, false);
+  if (mode == 2 && !fast_ok)
+    return fail(NNOP_ERR_ARG, "tcgen05 attention path required but the problem does not qualify");
+  if (fast_ok && mode != 1) {
+    g_last_path = 1;
+    return attn_sm100_fwd(p);
+  }
+  g_last_path = 0;
+  return attn_generic_fwd(p);
+}
+
+extern "C" size_t nnop_flash_attn_bwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH,
+                                                      int KH, int B) {
+  (void)dtype; (void)KL; (void)KH;
+  if (E <= 0 || QL <= 0 || QH <= 0 || B <= 0) return 0;
+  // delta (B,QH,QL) fp32, 256-byte aligned, then the fp32 dQ accumulator of the tcgen05 path
+  size_t delta = (static_cast<size_t>(B) * QH * QL * sizeof(float) + 255) & ~static_cast<size_t>(255);
+  return delta + attn_sm100_bwd_workspace_bytes(E, QL, QH, B);
+}
+
+extern "C" int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, const void* dO,
+                                   const void* o, const float* lse, const void* q, const void* k,
+                                   const void* v, const void* pair, const uint8_t* kpad_mask,
+                                   int dtype, int E, int QL, int KL, int QH, int KH, int B,
+                                   int causal, float scale, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  clear_error();
+  if (int rc = validate(dtype, E, QL, KL, QH, KH, B)) return rc;
+  if (static_cast<int64_t>(B) * QL == 0 && static_cast<int64_t>(B) * KL == 0) return NNOP_OK;
+  if ((QL > 0 && (!dq || !dO || !o || !lse || !q)) || (KL > 0 && (!dk || !dv || !k || !v)))
+    return fail(NNOP_ERR_ARG, "NULL pointer");
+  if (pair && !dpair) return fail(NNOP_ERR_ARG, "dpair must be given when pair is given");
+  const size_t need = nnop_flash_attn_bwd_workspace_bytes(dtype, E, QL, KL, QH, KH, B);
+  if (need > 0 && (!workspace || workspace_bytes < need))
+    return fail(NNOP_ERR_WORKSPACE, "flash attention backward needs a %zu-byte workspace, got %zu",
+                need, workspace_bytes);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+    return fail(NNOP_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  AttnParams p{};
+  p.o = const_cast<void*>(o); p.lse = const_cast<float*>(lse);
+  p.q = q; p.k = k; p.v = v; p.pair = pair; p.kpad = kpad_mask;
+  p.dq = dq; p.dk = dk; p.dv = dv; p.dpair = pair ? dpair : nullptr; p.dO = dO;
+  p.delta = static_cast<float*>(workspace);
+  const size_t delta_bytes =
+      (static_cast<size_t>(B) * QH * QL * sizeof(float) + 255) & ~static_cast<size_t>(255);
+  p.dq_accum = reinterpret_cast<float*>(static_cast<char*>(workspace) + delta_bytes);
+  p.dtype = dtype; p.E = E; p.QL = QL; p.KL = KL; p.QH = QH; p.KH = KH; p.B = B;
+  p.causal = causal ? 1 : 0; p.scale = scale;
+  p.stream = static_cast<cudaStream_t>(stream);
+  const int mode = g_path_mode.load();
+  const bool fast_ok = attn_sm100_supported(p, true);
+  if (mode == 2 && !fast_ok)
+    return fail(NNOP_ERR_ARG, "tcgen05 attention path required but the problem does not qualify");
+  if (QL > 0) {
+    if (int rc = attn_bwd_preprocess(p)) return rc;
+  }
+  if (fast_ok && mode != 1) {
+    g_last_path = 1;
+    return attn_sm100_bwd(p);
+  }
+  g_last_path = 0;
+  if (QL == 0 || KL == 0) {
+    // degenerate: gradients are all zero
+    if (KL > 0) {
+      const size_t kvb = static_cast<size_t>(B) * KH * KL * E * dtype_size(dtype);
+      NNOP_CUDA_CHECK(cudaMemsetAsync(dk, 0, kvb, p.stream));
+      NNOP_CUDA_CHECK(cudaMemsetAsync(dv, 0, kvb, p.stream));
+    }
+    if (QL > 0)
+      NNOP_CUDA_CHECK(cudaMemsetAsync(dq, 0, static_cast<size_t>(B) * QH * QL * E * dtype_size(dtype),
+                                      p.stream));
+    return NNOP_OK;
+  }
+  return attn_generic_bwd(p);
+}

@@ -1,0 +1,83 @@
+// internal.h -- host-side glue shared by the translation units of libnnop_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/nnop_b200.h"
+
+namespace nnop {
+
+// thread-local error message; returns `code` so call sites can `return fail(...)`.
+int fail(int code, const char* fmt, ...);
+void clear_error();
+
+#define NNOP_CUDA_CHECK(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::nnop::fail(NNOP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                   \
+                          cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+  } while (0)
+
+#define NNOP_LAUNCH_CHECK()                                                                \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess)                                                                 \
+      return ::nnop::fail(NNOP_ERR_CUDA, "kernel launch failed: %s (%s:%d)",               \
+                          cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+  } while (0)
+
+inline size_t dtype_size(int dtype) { return dtype == NNOP_F32 ? 4 : 2; }
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+struct AttnParams {
+  void* o;
+  float* lse;
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* pair;
+  const uint8_t* kpad;
+  // backward only
+  void* dq;
+  void* dk;
+  void* dv;
+  void* dpair;
+  const void* dO;
+  float* delta;     // workspace (B, QH, QL) fp32
+  float* dq_accum;  // workspace (B, QH, QL, E) fp32 (tcgen05 path)
+  int dtype, E, QL, KL, QH, KH, B, causal;
+  float scale;
+  cudaStream_t stream;
+};
+
+// attn_generic.cu -- SIMT path: any dtype, any power-of-two E <= 256, pair, kpad, ragged
+int attn_generic_fwd(const AttnParams& p);
+int attn_generic_bwd(const AttnParams& p);
+// delta[b,h,q] = sum_e dO*O  (shared by both backward paths)
+int attn_bwd_preprocess(const AttnParams& p);
+
+// attn_fwd_sm100.cu / attn_bwd_sm100.cu -- tcgen05 + TMA path (bf16/f16, E in {64,128})
+bool attn_sm100_supported(const AttnParams& p, bool backward);
+int attn_sm100_fwd(const AttnParams& p);
+int attn_sm100_bwd(const AttnParams& p);
+bool attn_sm100_bwd_available();
+size_t attn_sm100_bwd_workspace_bytes(int E, int QL, int QH, int B);
+
+// TMA descriptor helper (api.cu): 3-D map over a row-major (outer, rows, inner) tensor of
+// nnop_dtype_t elements, box (box_inner, box_rows, 1), 128-byte swizzle, zero OOB fill.
+int make_tmap_3d(void* tmap_out, const void* base, int dtype, uint64_t inner, uint64_t rows,
+                 uint64_t outer, uint32_t box_inner, uint32_t box_rows);
+
+}  // namespace nnop

@@ -1,0 +1,31 @@
+"""nnop_b200 -- host-side mirror of NNop.jl's public API over libnnop_b200.so.
+
+Same operator names, argument meaning and error behaviour as the reference
+(`NNop.flash_attention`, `online_softmax`, `rms_norm`, `layer_norm`, `llama_rope`,
+`LlamaRotaryEmbedding`; src/NNop.jl:15-25), with torch CUDA tensors standing in for CuArrays
+and `torch.autograd.Function`s standing in for the ChainRules rrules.  A Julia `(E, L, H, B)`
+array is passed as the row-major tensor `(B, H, L, E)` holding the same bytes.
+"""
+from ._lib import NNopError, LIB_PATH, lib  # noqa: F401
+from .ops import (  # noqa: F401
+    flash_attention, _flash_attention, grad_flash_attention,
+    online_softmax, grad_online_softmax,
+    rms_norm, _rms_norm, grad_rms_norm,
+    layer_norm, _layer_norm, grad_layer_norm,
+    llama_rope, grad_llama_rope, LlamaRotaryEmbedding,
+    device_info, set_attention_path, last_attention_path, selftest_umma,
+)
+from .sharding import shard_slices, shard_attention_inputs  # noqa: F401
+
+__all__ = [
+    "flash_attention", "_flash_attention", "grad_flash_attention", "online_softmax",
+    "grad_online_softmax", "rms_norm", "_rms_norm", "grad_rms_norm", "layer_norm",
+    "_layer_norm", "grad_layer_norm", "llama_rope", "grad_llama_rope", "LlamaRotaryEmbedding",
+    "device_info", "set_attention_path", "last_attention_path", "selftest_umma",
+    "shard_slices", "shard_attention_inputs", "NNopError",
+]
+# the reference spells its pullbacks with a nabla; reachable via getattr(nnop_b200, "∇flash_attention")
+globals().update({
+    "∇flash_attention": grad_flash_attention, "∇online_softmax": grad_online_softmax,
+    "∇rms_norm": grad_rms_norm, "∇layer_norm": grad_layer_norm, "∇llama_rope": grad_llama_rope,
+})

@@ -1,0 +1,369 @@
+"""Host launchers mirroring NNop.jl's L2/L3 layers over the C ABI.
+
+Reference functions mirrored (file:line in pxl-th/NNop.jl):
+  flash_attention / _flash_attention / ∇flash_attention  src/attention_crc.jl:4-31,
+                                                          src/attention.jl:133-177,
+                                                          src/attention_bwd.jl:199-275
+  online_softmax / ∇online_softmax                        src/softmax.jl:60-86
+  rms_norm / _rms_norm / ∇rms_norm                        src/rms_norm.jl:117-185
+  layer_norm / _layer_norm / ∇layer_norm                  src/layer_norm.jl:150-220
+  LlamaRotaryEmbedding / llama_rope / ∇llama_rope         src/rope/llama_rope.jl:1-98
+
+Shapes are the row-major view of the reference's column-major arrays (same bytes):
+q (B,QH,QL,E), k/v (B,KH,KL,E), pair (B,KL,QL,QH), kpad_mask (B,KL) bool, lse (B,QH,QL),
+x (n,emb), softmax x (cols,N), cos/sin (B,L,E).  Residual contents differ from the reference
+where SURVEY.md Appendix C says so (one fp32 `lse` instead of `ms`,`ls`).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+from ._lib import NNopError, check, lib
+
+_DT = {torch.float32: _lib.NNOP_F32, torch.float16: _lib.NNOP_F16, torch.bfloat16: _lib.NNOP_BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise NNopError(2, f"unsupported element type {t.dtype}; Float32, Float16, BFloat16 only")
+
+
+def _req(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise NNopError(6, "nnop_b200 operates on CUDA tensors only (there is no CPU path)")
+        if not t.is_contiguous():
+            raise NNopError(6, "nnop_b200 requires contiguous (dense column-major) arrays")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_info(device: int | None = None) -> dict:
+    """Replaces NNop.shared_memory (src/NNop.jl:27-30, ext/NNopCUDAExt.jl:6-9)."""
+    info = _lib.DeviceInfo()
+    check(lib.nnop_device_info(torch.cuda.current_device() if device is None else device, info))
+    return {f: getattr(info, f) for f, _ in info._fields_}
+
+
+def set_attention_path(mode: int) -> None:
+    check(lib.nnop_set_attention_path(mode))
+
+
+def last_attention_path() -> int:
+    return lib.nnop_last_attention_path()
+
+
+def selftest_umma(a: torch.Tensor, b: torch.Tensor, which: int) -> torch.Tensor:
+    _req(a, b)
+    out = torch.empty(128, 128, dtype=torch.float32, device=a.device)
+    check(lib.nnop_selftest_umma(out.data_ptr(), a.data_ptr(), b.data_ptr(), which, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# flash attention
+# ------------------------------------------------------------------------------------------
+def _attn_dims(q, k, v, pair, kpad_mask):
+    if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
+        raise NNopError(1, "q, k, v must be 4-dimensional (E, L, H, B) arrays")
+    B, QH, QL, QE = q.shape
+    KB, KH, KL, KE = k.shape
+    # same checks and wording as src/attention.jl:141-144
+    if QE != KE:
+        raise NNopError(1, f"Embedding dim of Q `{QE}` must be the same as of K `{KE}`.")
+    if tuple(k.shape) != tuple(v.shape):
+        raise NNopError(1, f"Shapes of K `{tuple(k.shape)}` and V `{tuple(v.shape)}` must be the same.")
+    if KB != B:
+        raise NNopError(1, f"Batch size of Q `{B}` must be the same as of K `{KB}`.")
+    if k.dtype != q.dtype or v.dtype != q.dtype:
+        raise NNopError(2, "q, k, v must share one element type")
+    if pair is not None:
+        if tuple(pair.shape) != (B, KL, QL, QH) or pair.dtype != q.dtype:
+            raise NNopError(1, f"pair must be a (QH, QL, KL, B) array of {q.dtype}")
+    if kpad_mask is not None:
+        if tuple(kpad_mask.shape) != (B, KL) or kpad_mask.dtype != torch.bool:
+            raise NNopError(1, "kpad_mask must be a (KL, B) Bool matrix")
+    return B, QH, QL, QE, KH, KL
+
+
+def _flash_attention(q, k, v, pair=None, *, causal: bool, kpad_mask=None):
+    """`_flash_attention` (src/attention.jl:133-177).  Returns ``(o, lse)``."""
+    _req(q, k, v, pair, kpad_mask)
+    B, QH, QL, E, KH, KL = _attn_dims(q, k, v, pair, kpad_mask)
+    o = torch.empty_like(q)
+    lse = torch.empty((B, QH, QL), dtype=torch.float32, device=q.device)
+    scale = 1.0 / math.sqrt(E)
+    check(lib.nnop_flash_attn_fwd(_p(o), _p(lse), _p(q), _p(k), _p(v), _p(pair), _p(kpad_mask),
+                                  _dt(q), E, QL, KL, QH, KH, B, int(bool(causal)), scale,
+                                  _stream()))
+    return o, lse
+
+
+def grad_flash_attention(dO, o, lse, q, k, v, pair=None, *, causal: bool, kpad_mask=None):
+    """`∇flash_attention` (src/attention_bwd.jl:199-275).  Returns ``(dq, dk, dv, dpair|None)``."""
+    _req(dO, o, lse, q, k, v, pair, kpad_mask)
+    B, QH, QL, E, KH, KL = _attn_dims(q, k, v, pair, kpad_mask)
+    if tuple(dO.shape) != tuple(q.shape) or dO.dtype != q.dtype:
+        raise NNopError(1, "Δ must have the shape and element type of q")
+    dq = torch.empty_like(q)
+    dk = torch.empty_like(k)
+    dv = torch.empty_like(v)
+    dpair = torch.empty_like(pair) if pair is not None else None
+    ws_bytes = lib.nnop_flash_attn_bwd_workspace_bytes(_dt(q), E, QL, KL, QH, KH, B)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=q.device)
+    scale = 1.0 / math.sqrt(E)
+    check(lib.nnop_flash_attn_bwd(_p(dq), _p(dk), _p(dv), _p(dpair), _p(dO), _p(o), _p(lse), _p(q),
+                                  _p(k), _p(v), _p(pair), _p(kpad_mask), _dt(q), E, QL, KL, QH, KH,
+                                  B, int(bool(causal)), scale, _p(ws), ws_bytes, _stream()))
+    return dq, dk, dv, dpair
+
+
+class _FlashAttentionFn(torch.autograd.Function):
+    """rrule(_flash_attention) (src/attention_crc.jl:16-31): primal is `o`; residuals o, lse, q, k, v, pair."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, pair, causal, kpad_mask):
+        o, lse = _flash_attention(q, k, v, pair, causal=causal, kpad_mask=kpad_mask)
+        ctx.save_for_backward(o, lse, q, k, v, pair, kpad_mask)
+        ctx.causal = causal
+        return o
+
+    @staticmethod
+    def backward(ctx, dO):
+        o, lse, q, k, v, pair, kpad_mask = ctx.saved_tensors
+        dq, dk, dv, dpair = grad_flash_attention(dO.contiguous(), o, lse, q, k, v, pair,
+                                                 causal=ctx.causal, kpad_mask=kpad_mask)
+        return dq, dk, dv, dpair, None, None
+
+
+def flash_attention(q, k, v, pair=None, *, causal: bool, kpad_mask=None):
+    """`NNop.flash_attention(q, k, v, pair=nothing; causal, kpad_mask=nothing)` (src/attention_crc.jl:4-14)."""
+    return _FlashAttentionFn.apply(q, k, v, pair, bool(causal), kpad_mask)
+
+
+# ------------------------------------------------------------------------------------------
+# online softmax
+# ------------------------------------------------------------------------------------------
+def _softmax_fwd(x):
+    _req(x)
+    if x.dim() != 2:
+        raise NNopError(1, "online_softmax expects a matrix (src/softmax.jl:60)")
+    y = torch.empty_like(x)
+    cols, N = x.shape
+    check(lib.nnop_softmax_fwd(_p(y), _p(x), _dt(x), N, cols, _stream()))
+    return y
+
+
+def grad_online_softmax(dy, y):
+    """`∇online_softmax(Δ, y)` (src/softmax.jl:70-80), fused into one kernel."""
+    _req(dy, y)
+    if dy.shape != y.shape or dy.dtype != y.dtype:
+        raise NNopError(1, "Δ must have the shape and element type of y")
+    dx = torch.empty_like(y)
+    cols, N = y.shape
+    check(lib.nnop_softmax_bwd(_p(dx), _p(dy), _p(y), _dt(y), N, cols, _stream()))
+    return dx
+
+
+class _SoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = _softmax_fwd(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return grad_online_softmax(dy.contiguous(), y)
+
+
+def online_softmax(x):
+    """`NNop.online_softmax(x)`: softmax over dim 1 of the (N, cols) matrix (src/softmax.jl:60-68)."""
+    return _SoftmaxFn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------
+# RMS norm
+# ------------------------------------------------------------------------------------------
+def _norm_ws(emb, n, device):
+    nbytes = lib.nnop_norm_bwd_workspace_bytes(emb, n)
+    return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device), nbytes
+
+
+def _rms_norm(x, w, *, eps: float = 1e-6, offset: float = 0.0):
+    """`_rms_norm` (src/rms_norm.jl:117-137).  Returns ``(y, rstd)``."""
+    _req(x, w)
+    if x.dim() != 2 or w.dim() != 1 or w.shape[0] != x.shape[1]:
+        raise NNopError(1, "rms_norm: x must be (emb, n) and w (emb) (src/rms_norm.jl:119)")
+    if w.dtype != x.dtype:
+        raise NNopError(2, "x and w must share one element type")
+    n, emb = x.shape
+    y = torch.empty_like(x)
+    rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+    check(lib.nnop_rms_norm_fwd(_p(y), _p(rstd), _p(x), _p(w), _dt(x), emb, n, eps, offset, _stream()))
+    return y, rstd
+
+
+def grad_rms_norm(dy, rstd, x, w, *, offset: float = 0.0):
+    """`∇rms_norm(Δ, rms, x, w; offset)` (src/rms_norm.jl:139-169).  ``dw`` is Float32 (:146)."""
+    _req(dy, rstd, x, w)
+    n, emb = x.shape
+    dx = torch.empty_like(x)
+    dw = torch.empty(emb, dtype=torch.float32, device=x.device)
+    ws, nbytes = _norm_ws(emb, n, x.device)
+    check(lib.nnop_rms_norm_bwd(_p(dx), _p(dw), _p(dy), _p(rstd), _p(x), _p(w), _dt(x), emb, n,
+                                offset, _p(ws), nbytes, _stream()))
+    return dx, dw
+
+
+class _RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, eps, offset):
+        y, rstd = _rms_norm(x, w, eps=eps, offset=offset)
+        ctx.save_for_backward(rstd, x, w)
+        ctx.offset = offset
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        rstd, x, w = ctx.saved_tensors
+        dx, dw = grad_rms_norm(dy.contiguous(), rstd, x, w, offset=ctx.offset)
+        return dx, dw.to(w.dtype), None, None
+
+
+def rms_norm(x, w, *, eps: float = 1e-6, offset: float = 0.0):
+    """`NNop.rms_norm(x, w; ϵ=1f-6, offset=0f0)` (src/rms_norm.jl:171-176)."""
+    return _RMSNormFn.apply(x, w, float(eps), float(offset))
+
+
+# ------------------------------------------------------------------------------------------
+# layer norm
+# ------------------------------------------------------------------------------------------
+def _layer_norm(x, w, b, *, eps: float = 1e-6):
+    """`_layer_norm` (src/layer_norm.jl:150-170).  Returns ``(y, mean, rstd)``."""
+    _req(x, w, b)
+    if x.dim() != 2 or w.dim() != 1 or b.dim() != 1 or w.shape[0] != x.shape[1] or b.shape != w.shape:
+        raise NNopError(1, "layer_norm: x must be (emb, n) and w, b (emb)")
+    if w.dtype != x.dtype or b.dtype != x.dtype:
+        raise NNopError(2, "x, w and b must share one element type")
+    n, emb = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(n, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+    check(lib.nnop_layer_norm_fwd(_p(y), _p(mean), _p(rstd), _p(x), _p(w), _p(b), _dt(x), emb, n,
+                                  eps, _stream()))
+    return y, mean, rstd
+
+
+def grad_layer_norm(dy, mean, rstd, x, w, b=None):
+    """`∇layer_norm(Δ, μ, Σ, x, w, b)` (src/layer_norm.jl:172-204).  Returns ``(dx, dw, db)``."""
+    _req(dy, mean, rstd, x, w)
+    n, emb = x.shape
+    dx = torch.empty_like(x)
+    dw = torch.empty_like(w)
+    db = torch.empty_like(w)
+    ws, nbytes = _norm_ws(emb, n, x.device)
+    check(lib.nnop_layer_norm_bwd(_p(dx), _p(dw), _p(db), _p(dy), _p(mean), _p(rstd), _p(x), _p(w),
+                                  _dt(x), emb, n, _p(ws), nbytes, _stream()))
+    return dx, dw, db
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        y, mean, rstd = _layer_norm(x, w, b, eps=eps)
+        ctx.save_for_backward(mean, rstd, x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        mean, rstd, x, w = ctx.saved_tensors
+        dx, dw, db = grad_layer_norm(dy.contiguous(), mean, rstd, x, w)
+        return dx, dw, db, None
+
+
+def layer_norm(x, w, b, *, eps: float = 1e-6):
+    """`NNop.layer_norm(x, w, b; ϵ=1f-6)` (src/layer_norm.jl:206-211)."""
+    return _LayerNormFn.apply(x, w, b, float(eps))
+
+
+# ------------------------------------------------------------------------------------------
+# Llama RoPE
+# ------------------------------------------------------------------------------------------
+class LlamaRotaryEmbedding:
+    """`LlamaRotaryEmbedding(dim; base=10000)` and its functor (src/rope/llama_rope.jl:1-22).
+
+    Host-side table construction, Float32 like the reference: ``inv_freq = 1 / base^((0:2:dim-1)/dim)``;
+    calling it on ``position_ids`` (B, L) float32 returns ``cos, sin`` of shape (B, L, dim) with
+    the half-frequencies duplicated (``vcat(freqs, freqs)``, :20)."""
+
+    def __init__(self, dim: int, *, base: int = 10000):
+        self.dim = int(dim)
+        self.base = int(base)
+        ids = torch.arange(0, dim, 2, dtype=torch.float32) / float(dim)
+        self.inv_freq = 1.0 / (torch.tensor(float(base), dtype=torch.float32) ** ids)
+
+    def __call__(self, position_ids: torch.Tensor):
+        pos = position_ids.to(torch.float32)
+        freqs = pos.unsqueeze(-1) * self.inv_freq.to(pos.device)
+        freqs = torch.cat([freqs, freqs], dim=-1)
+        return torch.cos(freqs), torch.sin(freqs)
+
+
+def _llama_rope(q, k, cos, sin, *, bwd: bool):
+    """`_llama_rope(q, k, cos, sin; bwd)` (src/rope/llama_rope.jl:69-89), out-of-place."""
+    _req(q, k, cos, sin)
+    if q.dim() != 4 or k.dim() != 4:
+        raise NNopError(1, "q, k must be (E, L, H, B) arrays")
+    # the reference's three @asserts (:70-72)
+    if q.shape[3] != k.shape[3] or q.shape[2] != k.shape[2] or q.shape[0] != k.shape[0]:
+        raise NNopError(1, "llama_rope: q and k must agree in head dim, sequence length and batch")
+    if q.dtype != k.dtype:
+        raise NNopError(2, "q and k must share one element type")
+    B, QH, L, E = q.shape
+    KH = k.shape[1]
+    if tuple(cos.shape) != (B, L, E) or tuple(sin.shape) != (B, L, E) or \
+            cos.dtype != torch.float32 or sin.dtype != torch.float32:
+        raise NNopError(1, "cos, sin must be Float32 (dim, seq, batch) arrays")
+    qo = torch.empty_like(q)
+    ko = torch.empty_like(k)
+    check(lib.nnop_llama_rope(_p(qo), _p(ko), _p(q), _p(k), _p(cos), _p(sin), _dt(q), E, L, QH, KH,
+                              B, -1.0 if bwd else 1.0, _stream()))
+    return qo, ko
+
+
+def grad_llama_rope(dq, dk, *, cos, sin):
+    """`∇llama_rope(dq, dk; cos, sin)` (src/rope/llama_rope.jl:92)."""
+    return _llama_rope(dq, dk, cos, sin, bwd=True)
+
+
+class _RopeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, cos, sin):
+        ctx.save_for_backward(cos, sin)
+        return _llama_rope(q, k, cos, sin, bwd=False)
+
+    @staticmethod
+    def backward(ctx, dq, dk):
+        cos, sin = ctx.saved_tensors
+        gq, gk = _llama_rope(dq.contiguous(), dk.contiguous(), cos, sin, bwd=True)
+        return gq, gk, None, None
+
+
+def llama_rope(q, k, *, cos, sin):
+    """`NNop.llama_rope(q, k; cos, sin)` -> ``(q′, k′)`` (src/rope/llama_rope.jl:91)."""
+    return _RopeFn.apply(q, k, cos, sin)
