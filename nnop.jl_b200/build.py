@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             print(f"==== {src}\n{log}")
     objs = [str(OBJ / (s + ".o")) for s in SOURCES]
     if force or _stale(LIB, objs):
-        r = subprocess.run([NVCC, "-shared", "-o", str(LIB), *objs], capture_output=True, text=True)
+        r = subprocess.run([NVCC, "-shared", "-cudart", "shared", "-o", str(LIB), *objs], capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")

@@ -111,7 +111,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    setmaxnreg_dec<80>();
+    setmaxnreg_dec<72>();  // releases 128*(168-72) = 12288 regs = 256*(216-168)
     if (warp == 0 && lane == 0) {
       // ================================ TMA producer =================================
       mbar_arrive_expect_tx(&q_full[0], S::kTileBytes);

@@ -49,10 +49,12 @@ def _check(nnop, q, k, v, dO, pr, m, causal, tol, expect_path=None):
     dq, dk, dv, dpair = nnop.grad_flash_attention(dev(dO), o, lse, dev(q), dev(k), dev(v), dev(pr),
                                                   causal=causal, kpad_mask=dev(m))
     rq, rk, rv, rp = O.naive_attention_bwd(D(dO), D(q), D(k), D(v), D(pr), causal=causal, kpad_mask=m)
-    g = q.shape[1] // k.shape[1]
-    assert max_abs(dq, rq) < tol, "dq"
-    assert max_abs(dk, rk) < tol * max(1.0, math.sqrt(g)), "dk"
-    assert max_abs(dv, rv) < tol * max(1.0, math.sqrt(g)), "dv"
+    # 16-bit outputs: the bound is absolute for O(1) values and follows the output rounding
+    # (2^-8 relative for bf16) once a gradient's magnitude exceeds 2
+    mag = (lambda r: max(1.0, r.abs().max().item() / 2)) if tol > 1e-3 else (lambda r: 1.0)
+    assert max_abs(dq, rq) < tol * mag(rq), "dq"
+    assert max_abs(dk, rk) < tol * mag(rk), "dk"
+    assert max_abs(dv, rv) < tol * mag(rv), "dv"
     if pr is not None:
         assert max_abs(dpair, rp) < tol, "dpair"
     return o, lse
