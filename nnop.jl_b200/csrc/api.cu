@@ -179,14 +179,14 @@ extern "C" int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, co
   const bool fast_ok = attn_sm100_supported(p, true);
   if (mode == 2 && !fast_ok)
     return fail(NNOP_ERR_ARG, "tcgen05 attention path required but the problem does not qualify");
+  if (fast_ok && mode != 1) {
+    g_last_path = 1;
+    return attn_sm100_bwd(p);  // runs its own preprocess (delta, lse2, dQ accumulator zeroing)
+  }
+  g_last_path = 0;
   if (QL > 0) {
     if (int rc = attn_bwd_preprocess(p)) return rc;
   }
-  if (fast_ok && mode != 1) {
-    g_last_path = 1;
-    return attn_sm100_bwd(p);
-  }
-  g_last_path = 0;
   if (QL == 0 || KL == 0) {
     // degenerate: gradients are all zero
     if (KL > 0) {

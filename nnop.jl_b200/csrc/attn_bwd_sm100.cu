@@ -1,11 +1,533 @@
-// attn_bwd_sm100.cu -- placeholder until the tcgen05 backward lands (next commit).
+// attn_bwd_sm100.cu -- flash attention backward on tcgen05 / TMEM / TMA (bf16 / fp16, E in
+// {64,128}, causal or not, GQA, ragged QL/KL).  Replaces `_flash_attention_bwd_preprocess!`
+// and `_flash_attention_bwd!` (src/attention_bwd.jl:163-197, :1-161), whose grid is only
+// (QH, B) workgroups of SIMT 32x32 tiles with global read-modify-write of dQ/dK/dV.
+//
+// Three launches:
+//   1. prep:  delta = rowsum(dO o O), lse2 = lse*log2(e) (padded to 128-row blocks; padding rows
+//             get lse2 = +inf so their P is exactly 0), and zeroes the fp32 dQ accumulator.
+//   2. main:  one CTA per (128-key block j, kv head, batch); loops over the q heads of the GQA
+//             group (dK/dV are summed inside the CTA -- no atomics, unlike :100,139) and over the
+//             128-row q blocks i (causal: i >= j only).  Per step, five 128x128x128 MMAs:
+//                S^T  = K_j Q_i^T          (smem x smem)            -> TMEM [0,128)
+//                dP^T = V_j dO_i^T         (smem x smem)            -> TMEM [128,256)
+//                dV  += P^T dO_i           (A = P^T bf16 in TMEM, aliasing S^T)
+//                dQ_i = dS K_j             (A = dS^T smem read MN-major) -> TMEM [128,128+E), aliasing dP^T
+//                dK  += dS^T Q_i           (A = dS^T smem read K-major)
+//             P^T = exp2(S^T*scale*log2e - lse2[q]) and dS^T = P^T o (dP^T - delta[q]) are computed
+//             by two warpgroups (thread <-> key row, half of the q columns each).  A fourth
+//             warpgroup drains dQ_i from TMEM and adds it into the fp32 accumulator with TMA
+//             reduce-add (cp.reduce.async.bulk.tensor), 32 columns at a time.
+//             Issue order per step: dV(i), S^T(i+1), dQ(i), dK(i), dP^T(i+1) so the tensor pipe
+//             works on step i's products while the warpgroups exponentiate step i+1.
+//   3. post:  dQ = T(scale * dQ_accum).
 #include "common.cuh"
 #include "internal.h"
 
 namespace nnop {
-bool attn_sm100_bwd_available() { return false; }
-size_t attn_sm100_bwd_workspace_bytes(int, int, int, int) { return 0; }
-int attn_sm100_bwd(const AttnParams&) {
-  return fail(NNOP_ERR_ARG, "tcgen05 backward not built");
+namespace {
+
+constexpr int kBwdThreads = 512;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct BwdParams {
+  const float* lse2p;   // (B*QH, QLp) lse * log2e, +inf padded
+  const float* deltap;  // (B*QH, QLp)
+  int QL, KL, QH, KH, QLp, causal;
+  float scale, scale_log2;
+};
+
+template <int D>
+struct BwdSmem {
+  static constexpr int kTile = 128 * D * 2;  // K_j, V_j, Q_i, dO_i tiles
+  static constexpr int kBox = 128 * 64 * 2;  // 64-column box
+  static constexpr int kNBox = D / 64;
+  static constexpr int kK = 0;
+  static constexpr int kV = kK + kTile;
+  static constexpr int kQ = kV + kTile;         // 2 stages
+  static constexpr int kdO = kQ + 2 * kTile;    // 1 stage
+  static constexpr int kdS = kdO + kTile;       // 128 x 128 16-bit, two boxes
+  static constexpr int kdQs = kdS + 2 * kBox;   // 2 x (128 rows x 32 fp32)
+  static constexpr int kStat = kdQs + 2 * 16384;  // lse2[2][128], delta[2][128]
+  static constexpr int kBar = kStat + 2048;
+  static constexpr int kNumBars = 14;
+  static constexpr int kTotal = kBar + kNumBars * 8 + 16;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
+                      const __grid_constant__ CUtensorMap tm_k,
+                      const __grid_constant__ CUtensorMap tm_v,
+                      const __grid_constant__ CUtensorMap tm_do,
+                      const __grid_constant__ CUtensorMap tm_dk,
+                      const __grid_constant__ CUtensorMap tm_dv,
+                      const __grid_constant__ CUtensorMap tm_dqa, const BwdParams p) {
+  using S = BwdSmem<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem + S::kK;
+  uint8_t* sV = smem + S::kV;
+  uint8_t* sQ = smem + S::kQ;
+  uint8_t* sdO = smem + S::kdO;
+  uint8_t* sdS = smem + S::kdS;
+  uint8_t* sdQ = smem + S::kdQs;
+  float* s_lse = reinterpret_cast<float*>(smem + S::kStat);        // [2][128]
+  float* s_del = reinterpret_cast<float*>(smem + S::kStat + 1024);  // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;    // [2]
+  uint64_t* q_empty = bars + 3;   // [2]
+  uint64_t* do_full = bars + 5;
+  uint64_t* do_empty = bars + 6;
+  uint64_t* s_full = bars + 7;
+  uint64_t* p_full = bars + 8;
+  uint64_t* dp_full = bars + 9;
+  uint64_t* ds_full = bars + 10;
+  uint64_t* dq_full = bars + 11;
+  uint64_t* dq_empty = bars + 12;
+  uint64_t* dkdv_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S::kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- work assignment ----------------------------------------------------------------
+  const int j = blockIdx.x;  // kv block
+  const int k0 = j * 128;
+  const int hk = blockIdx.y, b = blockIdx.z;
+  const int g = p.QH / p.KH;
+  const int bh_kv = b * p.KH + hk;
+  const int nq = (p.QL + 127) >> 7;
+  const int i0 = p.causal ? j : 0;
+  const int nqi = nq > i0 ? nq - i0 : 0;
+  const int n_it = nqi * g;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("nnop: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dqa);
+    mbar_init(kv_full, 1);
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    mbar_init(&q_empty[0], 1);
+    mbar_init(&q_empty[1], 1);
+    mbar_init(do_full, 1);
+    mbar_init(do_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 256);
+    mbar_init(dp_full, 1);
+    mbar_init(ds_full, 256);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 128);
+    mbar_init(dkdv_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 256 + D;
+
+  if (warp < 4) {
+    setmaxnreg_dec<64>();
+    if (warp == 0 && lane == 0 && n_it > 0) {
+      // ================================ TMA producer =================================
+      mbar_arrive_expect_tx(kv_full, 2 * S::kTile);
+#pragma unroll
+      for (int bx = 0; bx < S::kNBox; ++bx) {
+        tma_load_3d(sK + bx * S::kBox, &tm_k, kv_full, bx * 64, k0, bh_kv);
+        tma_load_3d(sV + bx * S::kBox, &tm_v, kv_full, bx * 64, k0, bh_kv);
+      }
+      auto load_q = [&](int it) {
+        const int s = it & 1;
+        const int bh_q = b * p.QH + hk * g + it / nqi;
+        const int q0 = (i0 + it % nqi) * 128;
+        mbar_wait(&q_empty[s], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[s], S::kTile + 1024);
+#pragma unroll
+        for (int bx = 0; bx < S::kNBox; ++bx)
+          tma_load_3d(sQ + s * S::kTile + bx * S::kBox, &tm_q, &q_full[s], bx * 64, q0, bh_q);
+        const int64_t soff = static_cast<int64_t>(bh_q) * p.QLp + q0;
+        bulk_load_1d(s_lse + s * 128, p.lse2p + soff, 512, &q_full[s]);
+        bulk_load_1d(s_del + s * 128, p.deltap + soff, 512, &q_full[s]);
+      };
+      auto load_do = [&](int it) {
+        const int bh_q = b * p.QH + hk * g + it / nqi;
+        const int q0 = (i0 + it % nqi) * 128;
+        mbar_wait(do_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(do_full, S::kTile);
+#pragma unroll
+        for (int bx = 0; bx < S::kNBox; ++bx)
+          tma_load_3d(sdO + bx * S::kBox, &tm_do, do_full, bx * 64, q0, bh_q);
+      };
+      load_q(0);
+      load_do(0);
+      if (n_it > 1) load_q(1);
+      for (int it = 1; it < n_it; ++it) {
+        load_do(it);
+        if (it + 1 < n_it) load_q(it + 1);
+      }
+    } else if (warp == 1 && lane == 0 && n_it > 0) {
+      // ================================ MMA issuer ===================================
+      constexpr bool BF = is_bf16<T>::value;
+      constexpr uint32_t id_kk = make_idesc_f16(128, 128, BF, false, false);  // S^T, dP^T
+      constexpr uint32_t id_tv = make_idesc_f16(128, D, BF, false, true);     // dV (A in TMEM), dK
+      constexpr uint32_t id_mm = make_idesc_f16(128, D, BF, true, true);      // dQ
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO),
+                     adS = smem_u32(sdS);
+      // D[128 x 128] = A[128 x D] B[128 x D]^T, both K-major tiles
+      auto mma_kk = [&](uint32_t dcol, uint32_t a0, uint32_t b0) {
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * S::kBox + (ks & 3) * 32;
+          umma_ss(tmem_base + dcol, make_smem_desc_sw128(a0 + off, 16, 1024),
+                  make_smem_desc_sw128(b0 + off, 16, 1024), id_kk, ks > 0 ? 1u : 0u);
+        }
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&q_full[0], 0);
+      tc_fence_after();
+      mma_kk(kColS, aK, aQ);
+      tc_commit(s_full);
+      mbar_wait(do_full, 0);
+      tc_fence_after();
+      mma_kk(kColDP, aV, adO);
+      tc_commit(dp_full);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        const uint32_t acc = it > 0 ? 1u : 0u;
+        // dV += P^T dO_i
+        mbar_wait(p_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_ts(tmem_base + kColDV, tmem_base + kColS + ks * 8,
+                  make_smem_desc_sw128(adO + ks * 2048, S::kBox, 1024), id_tv, (acc | (ks > 0)) ? 1u : 0u);
+        tc_commit(do_empty);
+        // S^T(i+1)
+        if (it + 1 < n_it) {
+          mbar_wait(&q_full[s ^ 1], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          mma_kk(kColS, aK, aQ + (s ^ 1) * S::kTile);
+          tc_commit(s_full);
+        }
+        // dQ_i = dS K_j   (A: dS^T smem viewed MN-major; B: K_j MN-major)
+        mbar_wait(ds_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_ss(tmem_base + kColDP, make_smem_desc_sw128(adS + ks * 2048, S::kBox, 1024),
+                  make_smem_desc_sw128(aK + ks * 2048, S::kBox, 1024), id_mm, ks > 0 ? 1u : 0u);
+        tc_commit(dq_full);
+        // dK += dS^T Q_i  (A: dS^T K-major; B: Q_i MN-major)
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t off = (ks >> 2) * S::kBox + (ks & 3) * 32;
+          umma_ss(tmem_base + kColDK, make_smem_desc_sw128(adS + off, 16, 1024),
+                  make_smem_desc_sw128(aQ + s * S::kTile + ks * 2048, S::kBox, 1024), id_tv,
+                  (acc | (ks > 0)) ? 1u : 0u);
+        }
+        tc_commit(&q_empty[s]);
+        // dP^T(i+1) -- its TMEM columns hold dQ_i until the drain warpgroup has read them
+        if (it + 1 < n_it) {
+          mbar_wait(do_full, (it + 1) & 1);
+          mbar_wait(dq_empty, it & 1);
+          tc_fence_after();
+          mma_kk(kColDP, aV, adO);
+          tc_commit(dp_full);
+        }
+      }
+      tc_commit(dkdv_full);
+    }
+  } else if (warp < 12) {
+    // ================================ compute warpgroups ===============================
+    setmaxnreg_inc<184>();
+    const int half = (warp - 4) >> 2;  // which 64 q columns
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;    // key row within the block
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const int c0 = half * 64;
+    const float sl2 = p.scale_log2;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1;
+      const int i = i0 + it % nqi;
+      // ---- P^T ----
+      mbar_wait(&q_full[s], (it >> 1) & 1);  // lse2 / delta of this stage have landed
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      uint32_t sr[2][32];
+      tmem_ld_x32(tmem_base + lane_off + kColS + c0, sr[0]);
+      tmem_ld_x32(tmem_base + lane_off + kColS + c0 + 32, sr[1]);
+      tmem_ld_wait();
+      float pf[64];
+      const float4* l4 = reinterpret_cast<const float4*>(s_lse + s * 128 + c0);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const float4 l = l4[u];
+        pf[4 * u + 0] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 0) & 31]), sl2, -l.x));
+        pf[4 * u + 1] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 1) & 31]), sl2, -l.y));
+        pf[4 * u + 2] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 2) & 31]), sl2, -l.z));
+        pf[4 * u + 3] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 3) & 31]), sl2, -l.w));
+      }
+      if (p.causal && i == j) {  // diagonal block: key k0+row is visible to query q0+c iff row <= c
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (row > c0 + c) pf[c] = 0.f;
+      }
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) pk[c] = pack2<T>(pf[2 * c], pf[2 * c + 1]);
+        tmem_st_x32(tmem_base + lane_off + kColS + half * 32, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      // ---- dS^T ----
+      mbar_wait(dp_full, it & 1);
+      tc_fence_after();
+      tmem_ld_x32(tmem_base + lane_off + kColDP + c0, sr[0]);
+      tmem_ld_x32(tmem_base + lane_off + kColDP + c0 + 32, sr[1]);
+      tmem_ld_wait();
+      const float4* d4 = reinterpret_cast<const float4*>(s_del + s * 128 + c0);
+      uint8_t* drow = sdS + half * S::kBox + row * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {  // 8 columns = one 16-byte chunk
+        const float4 da = d4[2 * ch], db = d4[2 * ch + 1];
+        const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        float ds[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = 8 * ch + e;
+          ds[e] = pf[c] * (__uint_as_float(sr[c >> 5][c & 31]) - dl[e]);
+        }
+        uint4 v;
+        v.x = pack2<T>(ds[0], ds[1]);
+        v.y = pack2<T>(ds[2], ds[3]);
+        v.z = pack2<T>(ds[4], ds[5]);
+        v.w = pack2<T>(ds[6], ds[7]);
+        *reinterpret_cast<uint4*>(drow + ((ch ^ (row & 7)) << 4)) = v;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_full);
+    }
+    // ---- epilogue: dV (half 0) / dK (half 1) -> 16-bit -> swizzled smem -> TMA store ------
+    if (n_it > 0) {
+      mbar_wait(dkdv_full, 0);
+      tc_fence_after();
+    }
+    {
+      const uint32_t tsrc = tmem_base + lane_off + (half ? kColDK : kColDV);
+      const float mul = half ? p.scale : 1.f;
+      uint8_t* stage = sQ + half * S::kTile;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t r[32];
+        if (n_it > 0) {
+          tmem_ld_x32(tsrc + c * 32, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) r[x] = 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 v;
+          v.x = pack2<T>(__uint_as_float(r[8 * u + 0]) * mul, __uint_as_float(r[8 * u + 1]) * mul);
+          v.y = pack2<T>(__uint_as_float(r[8 * u + 2]) * mul, __uint_as_float(r[8 * u + 3]) * mul);
+          v.z = pack2<T>(__uint_as_float(r[8 * u + 4]) * mul, __uint_as_float(r[8 * u + 5]) * mul);
+          v.w = pack2<T>(__uint_as_float(r[8 * u + 6]) * mul, __uint_as_float(r[8 * u + 7]) * mul);
+          const int chunk = c * 4 + u;
+          const int bx = chunk >> 3, cin = chunk & 7;
+          *reinterpret_cast<uint4*>(stage + bx * S::kBox + row * 128 + ((cin ^ (row & 7)) << 4)) = v;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + half, 128);
+      if (wq == 0 && lane == 0) {
+#pragma unroll
+        for (int bx = 0; bx < S::kNBox; ++bx)
+          tma_store_3d(half ? &tm_dk : &tm_dv, stage + bx * S::kBox, bx * 64, k0, bh_kv);
+        bulk_commit();
+        bulk_wait_read<0>();
+      }
+    }
+  } else {
+    // ================================ dQ drain warpgroup ===============================
+    setmaxnreg_dec<80>();
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;  // query row within the block
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const bool issuer = (warp == 12 && lane == 0);
+    int nred = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int bh_q = b * p.QH + hk * g + it / nqi;
+      const int q0 = (i0 + it % nqi) * 128;
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(tmem_base + lane_off + kColDP + c * 32, r);
+        tmem_ld_wait();
+        if (c == D / 32 - 1) {  // TMEM columns are free for dP^T(i+1)
+          tc_fence_before();
+          mbar_arrive(dq_empty);
+        }
+        uint8_t* stage = sdQ + (nred & 1) * 16384;
+        if (issuer) bulk_wait_read<1>();  // the reduce that last read this buffer has finished
+        named_bar_sync(3, 128);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint4 v = make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+          *reinterpret_cast<uint4*>(stage + row * 128 + ((u ^ (row & 7)) << 4)) = v;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (issuer) {
+          tma_reduce_add_3d(&tm_dqa, stage, c * 32, q0, bh_q);
+          bulk_commit();
+        }
+        ++nred;
+      }
+    }
+    if (issuer) bulk_wait<0>();
+  }
+
+  // ---- teardown -------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
 }
+
+// ---------------------------------------------------------------------------------------
+// prep: delta, lse2 (padded), zero dQ accumulator.  LPR lanes per row, one 16-byte vector each.
+// ---------------------------------------------------------------------------------------
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(float* __restrict__ deltap, float* __restrict__ lse2p,
+                     float* __restrict__ dq_accum, const T* __restrict__ dO,
+                     const T* __restrict__ o, const float* __restrict__ lse, int QL, int QLp,
+                     int64_t n_rows_p) {
+  constexpr int LPR = D / 8;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t rowp = gid / LPR;  // padded row index: bh * QLp + q
+  const int li = static_cast<int>(gid % LPR);
+  if (rowp >= n_rows_p) return;  // LPR divides 32 and 256: whole row groups exit together
+  const int64_t bh = rowp / QLp;
+  const int q = static_cast<int>(rowp % QLp);
+  float acc = 0.f;
+  if (q < QL) {
+    const int64_t off = (bh * QL + q) * D + li * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(dO + off);
+    const uint4 c = *reinterpret_cast<const uint4*>(o + off);
+    const T* ah = reinterpret_cast<const T*>(&a);
+    const T* ch = reinterpret_cast<const T*>(&c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc = fmaf(to_f32<T>(ah[e]), to_f32<T>(ch[e]), acc);
+    float4* z = reinterpret_cast<float4*>(dq_accum + off);
+    z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int sft = 1; sft < LPR; sft <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+  if (li == 0) {
+    deltap[rowp] = q < QL ? acc : 0.f;
+    lse2p[rowp] = q < QL ? lse[bh * QL + q] * kLog2e : INFINITY;
+  }
+}
+
+// post: dQ = T(scale * dQ_accum), 8 elements per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_bwd_post_kernel(T* __restrict__ dq, const float* __restrict__ dq_accum, int64_t n8,
+                     float scale) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = reinterpret_cast<const float4*>(dq_accum)[2 * i];
+  const float4 c = reinterpret_cast<const float4*>(dq_accum)[2 * i + 1];
+  uint4 v;
+  v.x = pack2<T>(a.x * scale, a.y * scale);
+  v.y = pack2<T>(a.z * scale, a.w * scale);
+  v.z = pack2<T>(c.x * scale, c.y * scale);
+  v.w = pack2<T>(c.z * scale, c.w * scale);
+  reinterpret_cast<uint4*>(dq)[i] = v;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+template <typename T, int D>
+int launch_bwd(const AttnParams& a) {
+  using S = BwdSmem<D>;
+  const int QLp = ((a.QL + 127) / 128) * 128;
+  const int64_t BH = static_cast<int64_t>(a.B) * a.QH;
+  // workspace carve-up (a.delta is the workspace base)
+  char* ws = reinterpret_cast<char*>(a.delta);
+  const size_t stat_bytes = align256(static_cast<size_t>(BH) * QLp * sizeof(float));
+  float* deltap = reinterpret_cast<float*>(ws);
+  float* lse2p = reinterpret_cast<float*>(ws + stat_bytes);
+  float* dqa = reinterpret_cast<float*>(ws + 2 * stat_bytes);
+
+  {
+    const int64_t n_rows_p = BH * QLp;
+    const int64_t threads = n_rows_p * (D / 8);
+    attn_bwd_prep_kernel<T, D><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, a.stream>>>(
+        deltap, lse2p, dqa, static_cast<const T*>(a.dO), static_cast<const T*>(a.o), a.lse, a.QL,
+        QLp, n_rows_p);
+    NNOP_LAUNCH_CHECK();
+  }
+  alignas(64) CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdqa;
+  const uint64_t bhq = static_cast<uint64_t>(BH), bhk = static_cast<uint64_t>(a.B) * a.KH;
+  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, D, a.QL, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdo, a.dO, a.dtype, D, a.QL, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdk, a.dk, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdv, a.dv, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdqa, dqa, NNOP_F32, D, a.QL, bhq, 32, 128)) return rc;
+  auto kern = attn_bwd_sm100_kernel<T, D>;
+  NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  BwdParams bp;
+  bp.lse2p = lse2p; bp.deltap = deltap;
+  bp.QL = a.QL; bp.KL = a.KL; bp.QH = a.QH; bp.KH = a.KH; bp.QLp = QLp; bp.causal = a.causal;
+  bp.scale = a.scale; bp.scale_log2 = a.scale * kLog2e;
+  dim3 grid((a.KL + 127) / 128, a.KH, a.B);
+  kern<<<grid, kBwdThreads, S::kTotal, a.stream>>>(tq, tk, tv, tdo, tdk, tdv, tdqa, bp);
+  NNOP_LAUNCH_CHECK();
+  {
+    const int64_t n8 = BH * a.QL * D / 8;
+    attn_bwd_post_kernel<T><<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, a.stream>>>(
+        static_cast<T*>(a.dq), dqa, n8, a.scale);
+    NNOP_LAUNCH_CHECK();
+  }
+  return NNOP_OK;
+}
+
+}  // namespace
+
+bool attn_sm100_bwd_available() { return true; }
+
+size_t attn_sm100_bwd_workspace_bytes(int E, int QL, int QH, int B) {
+  const size_t QLp = static_cast<size_t>((QL + 127) / 128) * 128;
+  const size_t BH = static_cast<size_t>(B) * QH;
+  return 2 * align256(BH * QLp * sizeof(float)) + BH * static_cast<size_t>(QL) * E * sizeof(float);
+}
+
+int attn_sm100_bwd(const AttnParams& a) {
+  if (a.dtype == NNOP_BF16)
+    return a.E == 128 ? launch_bwd<__nv_bfloat16, 128>(a) : launch_bwd<__nv_bfloat16, 64>(a);
+  return a.E == 128 ? launch_bwd<__half, 128>(a) : launch_bwd<__half, 64>(a);
+}
+
 }  // namespace nnop

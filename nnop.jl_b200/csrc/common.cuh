@@ -131,7 +131,25 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
       "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// fp32 add-reduction of a contiguous smem span into global memory (dQ accumulation)
+// 1-D bulk copy global -> shared, completing on an mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// element-wise add-reduction of a smem box into a global tensor (fp32 dQ accumulation)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* smem_src,
+                                                  int c0, int c1, int c2) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], "
+      "[%1];" ::"l"(map),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// fp32 add-reduction of a contiguous smem span into global memory
 __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* smem_src,
                                                     uint32_t bytes) {
   asm volatile(

@@ -181,8 +181,8 @@ def test_tcgen05_matches_generic_path(nnop, causal):
         nnop.set_attention_path(0)
     assert max_abs(o_f, o_g) < H16_TOL and max_abs(lse_f, lse_g) < 1e-3
     g_f = nnop.grad_flash_attention(dOd, o_f, lse_f, qd, kd, vd, causal=causal)
-    for a, b in zip(g_f[:3], g_g[:3]):
-        assert max_abs(a, b) < H16_TOL
+    for a, b in zip(g_f[:3], g_g[:3]):  # two bf16 results: allow one output ulp at the gradient's magnitude
+        assert max_abs(a, b) < H16_TOL * max(1.0, b.abs().max().item() / 2)
 
 
 def test_16bit_pair_and_mask_fall_to_generic(nnop):
