@@ -147,6 +147,14 @@ int nnop_llama_rope(void* q_out, void* k_out, const void* q_in, const void* k_in
                     int KH, int B, float sin_sign, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Measurement hook (bench.py): the next tcgen05 attention launch of kind `which` (0 = forward
+ * kernel, 1 = backward main kernel) made by the calling thread records `start_event` right
+ * before and `stop_event` right after that one kernel, on the launch stream.  Events are
+ * cudaEvent_t handles passed as void*; the hook is one-shot (cleared once used); NULLs clear it.
+ */
+int nnop_set_timing_events(int which, void* start_event, void* stop_event);
+
+/* ---------------------------------------------------------------------------------------
  * Hardware self-test of the tcgen05/TMA building blocks (diagnostics; used by tests).
  * Runs one 128x128x128 bf16 GEMM through an operand form the attention kernels use and
  * writes the 128x128 fp32 result to d_out; a, b are 128x128 bf16 row-major device buffers.

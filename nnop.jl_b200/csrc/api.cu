@@ -66,6 +66,15 @@ int make_tmap_3d(void* tmap_out, const void* base, int dtype, uint64_t inner, ui
   return NNOP_OK;
 }
 
+static thread_local cudaEvent_t g_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+void timing_begin(int which, cudaStream_t st) {
+  if (g_ev[which][0]) cudaEventRecord(g_ev[which][0], st);
+}
+void timing_end(int which, cudaStream_t st) {
+  if (g_ev[which][1]) cudaEventRecord(g_ev[which][1], st);
+  g_ev[which][0] = g_ev[which][1] = nullptr;
+}
+
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 static int validate(int dtype, int E, int QL, int KL, int QH, int KH, int B) {
@@ -102,6 +111,13 @@ extern "C" int nnop_device_info(int device, nnop_device_info_t* out) {
   out->shared_mem_per_block_optin = prop.sharedMemPerBlockOptin;
   out->l2_bytes = static_cast<size_t>(prop.l2CacheSize);
   out->hbm_bytes = prop.totalGlobalMem;
+  return NNOP_OK;
+}
+
+extern "C" int nnop_set_timing_events(int which, void* start_event, void* stop_event) {
+  if (which < 0 || which > 1) return fail(NNOP_ERR_ARG, "which must be 0 (forward) or 1 (backward)");
+  g_ev[which][0] = static_cast<cudaEvent_t>(start_event);
+  g_ev[which][1] = static_cast<cudaEvent_t>(stop_event);
   return NNOP_OK;
 }
 

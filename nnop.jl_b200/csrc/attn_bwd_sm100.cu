@@ -503,7 +503,9 @@ int launch_bwd(const AttnParams& a) {
   bp.QL = a.QL; bp.KL = a.KL; bp.QH = a.QH; bp.KH = a.KH; bp.QLp = QLp; bp.causal = a.causal;
   bp.scale = a.scale; bp.scale_log2 = a.scale * kLog2e;
   dim3 grid((a.KL + 127) / 128, a.KH, a.B);
+  timing_begin(1, a.stream);
   kern<<<grid, kBwdThreads, S::kTotal, a.stream>>>(tq, tk, tv, tdo, tdk, tdv, tdqa, bp);
+  timing_end(1, a.stream);
   NNOP_LAUNCH_CHECK();
   {
     const int64_t n8 = BH * a.QL * D / 8;

@@ -360,7 +360,9 @@ int launch_fwd(const AttnParams& a) {
   fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
   fp.scale_log2 = a.scale * kLog2e;
   dim3 grid((a.QL + 255) / 256, a.QH, a.B);
+  timing_begin(0, a.stream);
   kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, fp);
+  timing_end(0, a.stream);
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
 }

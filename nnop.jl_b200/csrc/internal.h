@@ -62,6 +62,10 @@ struct AttnParams {
   cudaStream_t stream;
 };
 
+// one-shot timing hook (api.cu); which: 0 forward kernel, 1 backward main kernel
+void timing_begin(int which, cudaStream_t st);
+void timing_end(int which, cudaStream_t st);
+
 // attn_generic.cu -- SIMT path: any dtype, any power-of-two E <= 256, pair, kpad, ragged
 int attn_generic_fwd(const AttnParams& p);
 int attn_generic_bwd(const AttnParams& p);

@@ -14,6 +14,7 @@ from .ops import (  # noqa: F401
     layer_norm, _layer_norm, grad_layer_norm,
     llama_rope, grad_llama_rope, LlamaRotaryEmbedding,
     device_info, set_attention_path, last_attention_path, selftest_umma,
+    set_timing_events, HostAttentionPipeline,
 )
 from .sharding import shard_slices, shard_attention_inputs  # noqa: F401
 
@@ -22,7 +23,8 @@ __all__ = [
     "grad_online_softmax", "rms_norm", "_rms_norm", "grad_rms_norm", "layer_norm",
     "_layer_norm", "grad_layer_norm", "llama_rope", "grad_llama_rope", "LlamaRotaryEmbedding",
     "device_info", "set_attention_path", "last_attention_path", "selftest_umma",
-    "shard_slices", "shard_attention_inputs", "NNopError",
+    "shard_slices", "shard_attention_inputs", "NNopError", "set_timing_events",
+    "HostAttentionPipeline",
 ]
 # the reference spells its pullbacks with a nabla; reachable via getattr(nnop_b200, "∇flash_attention")
 globals().update({

@@ -56,6 +56,7 @@ SIGNATURES = {
     "nnop_layer_norm_fwd": (_i, [_vp] * 6 + [_i, _i64, _i64, _f, _vp]),
     "nnop_layer_norm_bwd": (_i, [_vp] * 8 + [_i, _i64, _i64, _vp, _sz, _vp]),
     "nnop_llama_rope": (_i, [_vp] * 6 + [_i, _i, _i64, _i, _i, _i, _f, _vp]),
+    "nnop_set_timing_events": (_i, [_i, _vp, _vp]),
     "nnop_selftest_umma": (_i, [_vp, _vp, _vp, _i, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
