@@ -136,7 +136,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 256 + D;
 
   if (warp < 4) {
-    setmaxnreg_dec<64>();
+    setmaxnreg_dec<88>();  // 512 thr x 128 regs at launch -> 88 / 136 / 152 (sum = 64K regs)
     if (warp == 0 && lane == 0 && n_it > 0) {
       // ================================ TMA producer =================================
       mbar_arrive_expect_tx(kv_full, 2 * S::kTile);
@@ -248,7 +248,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     }
   } else if (warp < 12) {
     // ================================ compute warpgroups ===============================
-    setmaxnreg_inc<184>();
+    setmaxnreg_inc<136>();
     const int half = (warp - 4) >> 2;  // which 64 q columns
     const int wq = warp & 3;
     const int row = wq * 32 + lane;    // key row within the block
@@ -362,7 +362,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     }
   } else {
     // ================================ dQ drain warpgroup ===============================
-    setmaxnreg_dec<80>();
+    setmaxnreg_inc<152>();
     const int wq = warp & 3;
     const int row = wq * 32 + lane;  // query row within the block
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
@@ -373,21 +373,22 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       const int q0 = (i0 + it % nqi) * 128;
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
+      // pull the whole dQ_i tile into registers first so its TMEM columns (shared with dP^T)
+      // are released as early as possible -- this read sits on the dS -> dQ -> dP^T(i+1) chain
+      uint32_t r[D / 32][32];
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) tmem_ld_x32(tmem_base + lane_off + kColDP + c * 32, r[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_empty);
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_x32(tmem_base + lane_off + kColDP + c * 32, r);
-        tmem_ld_wait();
-        if (c == D / 32 - 1) {  // TMEM columns are free for dP^T(i+1)
-          tc_fence_before();
-          mbar_arrive(dq_empty);
-        }
         uint8_t* stage = sdQ + (nred & 1) * 16384;
         if (issuer) bulk_wait_read<1>();  // the reduce that last read this buffer has finished
         named_bar_sync(3, 128);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const uint4 v = make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+          const uint4 v = make_uint4(r[c][4 * u], r[c][4 * u + 1], r[c][4 * u + 2], r[c][4 * u + 3]);
           *reinterpret_cast<uint4*>(stage + row * 128 + ((u ^ (row & 7)) << 4)) = v;
         }
         fence_proxy_async_smem();
