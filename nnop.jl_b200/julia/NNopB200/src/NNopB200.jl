@@ -1,0 +1,260 @@
+# NNopB200.jl -- drop-in for NNop.jl's public API on NVIDIA B200 (sm_100a).
+#
+# Same function names, signatures, column-major (E, L, H, B) layout and ChainRules rrules as
+# pxl-th/NNop.jl v0.2.0; every body is: validate -> allocate outputs with `similar` -> one
+# `ccall` into libnnop_b200.so (C ABI: include/nnop_b200.h) on the task-local CUDA stream.
+# It replaces ext/NNopCUDAExt.jl and the KernelAbstractions kernels of src/*.jl; there is no
+# AMDGPU dispatch and no CPU fallback.  (Written without a Julia toolchain at hand -- the image
+# this repo is built in has none -- so it is kept deliberately thin; the same ABI is exercised
+# end to end by the Python twin in nnop.jl_b200/nnop_b200/.)
+module NNopB200
+
+using CUDA
+import ChainRulesCore as CRC
+
+const libnnop_b200 = get(ENV, "NNOP_B200_LIB", joinpath(@__DIR__, "..", "..", "..", "lib", "libnnop_b200.so"))
+const Maybe{T} = Union{Nothing, T}                                   # src/NNop.jl:13
+const FloatT = Union{Float32, Float16, CUDA.BFloat16}
+
+dtype_code(::Type{Float32}) = Cint(0)
+dtype_code(::Type{Float16}) = Cint(1)
+dtype_code(::Type{CUDA.BFloat16}) = Cint(2)
+
+function check(status::Cint)
+    status == 0 && return
+    msg = unsafe_string(ccall((:nnop_last_error_string, libnnop_b200), Cstring, ()))
+    error(msg)                                   # reference: error("...") (src/attention.jl:141-144)
+end
+
+ptr(x::CuArray) = Base.unsafe_convert(CuPtr{Cvoid}, x)
+ptr(::Nothing) = CuPtr{Cvoid}(0)
+stream() = CUDA.stream().handle
+
+within_gradient(x) = false                                                     # src/attention_crc.jl:1-2
+CRC.rrule(::typeof(within_gradient), x) = true, _ -> (CRC.NoTangent(), CRC.NoTangent())
+
+# ------------------------------------------------------------------ flash attention
+# _flash_attention: src/attention.jl:133-177.  Residuals: (o, lse, nothing) -- one Float32
+# log-sum-exp replaces the reference's (ms, ls); they are private to the rrule closure.
+function _flash_attention(
+    q::CuArray{T,4}, k::CuArray{T,4}, v::CuArray{T,4},
+    pair::Maybe{CuArray{T,4}} = nothing;
+    causal::Bool, kpad_mask::Maybe{CuMatrix{Bool}} = nothing,
+) where T <: FloatT
+    QE, QL, QH, B = size(q)
+    KE, KL, KH, KB = size(k)
+    QE == KE || error("Embedding dim of Q `$QE` must be the same as of K `$KE`.")
+    size(k) == size(v) || error("Shapes of K `$(size(k))` and V `$(size(v))` must be the same.")
+    ispow2(QE) || error("Only power-of-2 embedding dims are supported.")
+    QH % KH == 0 || error("Number of query heads `$QH` must be divisible by number of KV heads `$KH`.")
+
+    o = similar(q)
+    lse = CUDA.zeros(Float32, QL, QH, B)
+    check(ccall((:nnop_flash_attn_fwd, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
+         Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cfloat, Ptr{Cvoid}),
+        ptr(o), ptr(lse), ptr(q), ptr(k), ptr(v), ptr(pair), ptr(kpad_mask),
+        dtype_code(T), QE, QL, KL, QH, KH, B, causal, Float32(inv(sqrt(QE))), stream()))
+    return o, lse, nothing
+end
+
+# ∇flash_attention: src/attention_bwd.jl:199-275 (`ms` carries lse, `ls` is unused)
+function ∇flash_attention(
+    Δ::CuArray{T,4}, o::CuArray{T,4}, ms, ls,
+    q::CuArray{T,4}, k::CuArray{T,4}, v::CuArray{T,4},
+    pair::Maybe{CuArray{T,4}} = nothing;
+    causal::Bool, kpad_mask::Maybe{CuMatrix{Bool}} = nothing,
+) where T <: FloatT
+    QE, QL, QH, B = size(q)
+    _, KL, KH, _ = size(k)
+    dq, dk, dv = similar(q), similar(k), similar(v)          # fully overwritten by the library
+    dpair = isnothing(pair) ? nothing : similar(pair)
+    nbytes = ccall((:nnop_flash_attn_bwd_workspace_bytes, libnnop_b200), Csize_t,
+        (Cint, Cint, Cint, Cint, Cint, Cint, Cint), dtype_code(T), QE, QL, KL, QH, KH, B)
+    ws = CuArray{UInt8}(undef, max(nbytes, 1))
+    check(ccall((:nnop_flash_attn_bwd, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
+         CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
+         Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cfloat, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        ptr(dq), ptr(dk), ptr(dv), ptr(dpair), ptr(Δ), ptr(o), ptr(ms), ptr(q), ptr(k), ptr(v),
+        ptr(pair), ptr(kpad_mask), dtype_code(T), QE, QL, KL, QH, KH, B, causal,
+        Float32(inv(sqrt(QE))), ptr(ws), nbytes, stream()))
+    CUDA.unsafe_free!(ws)
+    return dq, dk, dv, dpair
+end
+
+function flash_attention(q, k, v, pair::Maybe{AbstractArray{<:Real,4}} = nothing;
+                         causal::Bool, kpad_mask::Maybe{AbstractMatrix{Bool}} = nothing)   # src/attention_crc.jl:4-14
+    o = _flash_attention(q, k, v, pair; causal, kpad_mask)
+    within_gradient(q) && return o
+    return o[1]
+end
+
+function CRC.rrule(::typeof(_flash_attention), q, k, v, pair::Maybe{AbstractArray{<:Real,4}} = nothing;
+                   causal::Bool, kpad_mask::Maybe{AbstractMatrix{Bool}} = nothing)         # src/attention_crc.jl:16-31
+    o, lse, _ = _flash_attention(q, k, v, pair; causal, kpad_mask)
+    function _pullback(Δ)
+        Δd = convert(typeof(o), CRC.unthunk(Δ))      # Zygote may hand a Fill / thunk: materialise
+        dq, dk, dv, dpair = ∇flash_attention(Δd, o, lse, nothing, q, k, v, pair; causal, kpad_mask)
+        return CRC.NoTangent(), dq, dk, dv, (isnothing(dpair) ? CRC.NoTangent() : dpair)
+    end
+    return o, _pullback
+end
+
+# ------------------------------------------------------------------ online softmax (src/softmax.jl:60-86)
+function online_softmax(x::CuMatrix{T}) where T <: FloatT
+    y = similar(x)
+    check(ccall((:nnop_softmax_fwd, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}),
+        ptr(y), ptr(x), dtype_code(T), size(x, 1), size(x, 2), stream()))
+    return y
+end
+
+function ∇online_softmax(Δ::CuMatrix{T}, y::CuMatrix{T}) where T <: FloatT
+    dx = similar(y)
+    check(ccall((:nnop_softmax_bwd, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}),
+        ptr(dx), ptr(Δ), ptr(y), dtype_code(T), size(y, 1), size(y, 2), stream()))
+    return dx
+end
+
+function CRC.rrule(::typeof(online_softmax), x)
+    y = online_softmax(x)
+    _pullback(Δ) = (CRC.NoTangent(), ∇online_softmax(convert(typeof(y), CRC.unthunk(Δ)), y))
+    return y, _pullback
+end
+
+# ------------------------------------------------------------------ RMS norm (src/rms_norm.jl:117-185)
+function norm_workspace(emb, n)
+    nbytes = ccall((:nnop_norm_bwd_workspace_bytes, libnnop_b200), Csize_t, (Int64, Int64), emb, n)
+    return CuArray{UInt8}(undef, max(nbytes, 1)), nbytes
+end
+
+function _rms_norm(x::CuMatrix{T}, w::CuVector{T}; ϵ::Float32, offset::Float32 = 0f0) where T <: FloatT
+    emb, n = size(x)
+    @assert emb == length(w)
+    y = similar(x)
+    rms = CUDA.zeros(Float32, n)
+    check(ccall((:nnop_rms_norm_fwd, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Int64, Int64, Cfloat, Cfloat, Ptr{Cvoid}),
+        ptr(y), ptr(rms), ptr(x), ptr(w), dtype_code(T), emb, n, ϵ, offset, stream()))
+    return y, rms
+end
+
+function ∇rms_norm(Δ::CuMatrix{T}, rms, x::CuMatrix{T}, w::CuVector{T}; offset::Float32) where T <: FloatT
+    emb, n = size(x)
+    dx = similar(x)
+    dw = CUDA.zeros(Float32, emb)                               # Float32 for every T (src/rms_norm.jl:146)
+    ws, nbytes = norm_workspace(emb, n)
+    check(ccall((:nnop_rms_norm_bwd, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
+         Cint, Int64, Int64, Cfloat, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        ptr(dx), ptr(dw), ptr(Δ), ptr(rms), ptr(x), ptr(w), dtype_code(T), emb, n, offset,
+        ptr(ws), nbytes, stream()))
+    CUDA.unsafe_free!(ws)
+    return dx, dw
+end
+
+function rms_norm(x, w; ϵ::Float32 = 1f-6, offset::Float32 = 0f0)      # src/rms_norm.jl:171-176
+    y = _rms_norm(x, w; ϵ, offset)
+    within_gradient(x) && return y
+    return y[1]
+end
+
+function CRC.rrule(::typeof(_rms_norm), x, w; ϵ::Float32 = 1f-6, offset::Float32 = 0f0)
+    y, rms = _rms_norm(x, w; ϵ, offset)
+    function _pullback(Δ)
+        dx, dw = ∇rms_norm(convert(typeof(y), CRC.unthunk(Δ)), rms, x, w; offset)
+        return CRC.NoTangent(), dx, dw
+    end
+    return y, _pullback
+end
+
+# ------------------------------------------------------------------ layer norm (src/layer_norm.jl:150-220)
+function _layer_norm(x::CuMatrix{T}, w::CuVector{T}, b::CuVector{T}; ϵ::Float32) where T <: FloatT
+    emb, n = size(x)
+    @assert emb == length(w) == length(b)
+    y = similar(x)
+    μ = CUDA.zeros(Float32, n)
+    Σ = CUDA.zeros(Float32, n)                                   # holds rstd (src/layer_norm.jl:50)
+    check(ccall((:nnop_layer_norm_fwd, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
+         Cint, Int64, Int64, Cfloat, Ptr{Cvoid}),
+        ptr(y), ptr(μ), ptr(Σ), ptr(x), ptr(w), ptr(b), dtype_code(T), emb, n, ϵ, stream()))
+    return y, μ, Σ
+end
+
+function ∇layer_norm(Δ::CuMatrix{T}, μ, Σ, x::CuMatrix{T}, w::CuVector{T}, b::CuVector{T}) where T <: FloatT
+    emb, n = size(x)
+    dx, dw, db = similar(x), similar(w), similar(b)
+    ws, nbytes = norm_workspace(emb, n)
+    check(ccall((:nnop_layer_norm_bwd, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
+         CuPtr{Cvoid}, Cint, Int64, Int64, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        ptr(dx), ptr(dw), ptr(db), ptr(Δ), ptr(μ), ptr(Σ), ptr(x), ptr(w), dtype_code(T), emb, n,
+        ptr(ws), nbytes, stream()))
+    CUDA.unsafe_free!(ws)
+    return dx, dw, db
+end
+
+function layer_norm(x, w, b; ϵ::Float32 = 1f-6)                       # src/layer_norm.jl:206-211
+    y = _layer_norm(x, w, b; ϵ)
+    within_gradient(x) && return y
+    return y[1]
+end
+
+function CRC.rrule(::typeof(_layer_norm), x, w, b; ϵ::Float32 = 1f-6)
+    y, μ, Σ = _layer_norm(x, w, b; ϵ)
+    function _pullback(Δ)
+        dx, dw, db = ∇layer_norm(convert(typeof(y), CRC.unthunk(Δ)), μ, Σ, x, w, b)
+        return CRC.NoTangent(), dx, dw, db
+    end
+    return y, _pullback
+end
+
+# ------------------------------------------------------------------ Llama RoPE (src/rope/llama_rope.jl)
+struct LlamaRotaryEmbedding{F <: AbstractVector{Float32}}
+    inv_freq::F
+    dim::Int
+    base::Int
+end
+
+function LlamaRotaryEmbedding(dim::Int; base::Int = 10000)            # :7-11, host side, Float32
+    ids = (0f0:2f0:Float32(dim - 1)) ./ Float32(dim)
+    LlamaRotaryEmbedding(inv.(base .^ ids), dim, base)
+end
+
+function (emb::LlamaRotaryEmbedding)(position_ids::AbstractMatrix{Float32})   # :15-22
+    position_ids = reshape(position_ids, 1, size(position_ids)...)
+    freqs = emb.inv_freq .* position_ids
+    freqs = vcat(freqs, freqs)
+    return cos.(freqs), sin.(freqs)
+end
+
+function _llama_rope(q::CuArray{T,4}, k::CuArray{T,4}, cos::CuArray{Float32,3}, sin::CuArray{Float32,3};
+                     bwd::Bool) where T <: FloatT
+    @assert size(q, 1) == size(k, 1)
+    @assert size(q, 2) == size(k, 2)
+    @assert size(q, 4) == size(k, 4)
+    qo, ko = similar(q), similar(k)            # out-of-place: fuses the reference's copy (:75-76)
+    check(ccall((:nnop_llama_rope, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
+         Cint, Cint, Int64, Cint, Cint, Cint, Cfloat, Ptr{Cvoid}),
+        ptr(qo), ptr(ko), ptr(q), ptr(k), ptr(cos), ptr(sin), dtype_code(T),
+        size(q, 1), size(q, 2), size(q, 3), size(k, 3), size(q, 4), bwd ? -1f0 : 1f0, stream()))
+    return qo, ko
+end
+
+llama_rope(q, k; cos, sin) = _llama_rope(q, k, cos, sin; bwd=false)      # :91
+∇llama_rope(dq, dk; cos, sin) = _llama_rope(dq, dk, cos, sin; bwd=true)  # :92
+
+function CRC.rrule(::typeof(llama_rope), q, k; cos, sin)                   # :94-98
+    qr, kr = llama_rope(q, k; cos, sin)
+    function _pullback(Δ)
+        dq, dk = CRC.unthunk.(Δ)
+        return (CRC.NoTangent(), ∇llama_rope(convert(typeof(q), dq), convert(typeof(k), dk); cos, sin)...)
+    end
+    return (qr, kr), _pullback
+end
+
+end # module
