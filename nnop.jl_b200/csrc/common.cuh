@@ -170,6 +170,21 @@ __device__ __forceinline__ void bulk_wait() {
 }
 
 // -------------------------------------------------------------------------------------
+// cp.async (LDGSTS): 16-byte global -> shared copies that bypass registers
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// -------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, fences, commit
 // -------------------------------------------------------------------------------------
 template <int NCOLS>

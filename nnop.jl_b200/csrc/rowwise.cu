@@ -53,6 +53,36 @@ __device__ __forceinline__ void load_vec<__nv_bfloat16>(const __nv_bfloat16* p, 
     out[2 * i] = f.x; out[2 * i + 1] = f.y;
   }
 }
+// raw 16-byte load (kept packed while a prefetched row waits in registers) + unpack
+template <typename T>
+__device__ __forceinline__ uint4 load_raw(const T* p) {
+  return *reinterpret_cast<const uint4*>(p);
+}
+template <typename T>
+__device__ __forceinline__ void unpack_raw(const uint4& v, float (&out)[VecIO<T>::N]);
+template <>
+__device__ __forceinline__ void unpack_raw<float>(const uint4& v, float (&out)[4]) {
+  out[0] = __uint_as_float(v.x); out[1] = __uint_as_float(v.y);
+  out[2] = __uint_as_float(v.z); out[3] = __uint_as_float(v.w);
+}
+template <>
+__device__ __forceinline__ void unpack_raw<__half>(const uint4& v, float (&out)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    out[2 * i] = f.x; out[2 * i + 1] = f.y;
+  }
+}
+template <>
+__device__ __forceinline__ void unpack_raw<__nv_bfloat16>(const uint4& v, float (&out)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    out[2 * i] = f.x; out[2 * i + 1] = f.y;
+  }
+}
 template <typename T>
 __device__ __forceinline__ void store_vec(T* p, const float (&in)[VecIO<T>::N]);
 template <>
@@ -317,25 +347,50 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
     }
   }
 
+  // Row groups are streamed through a 3-stage cp.async ring in shared memory.  Every thread
+  // copies exactly the vectors it later reads itself, so the ring needs no block barrier, and a
+  // CTA keeps two row groups of x and dy in flight while it reduces the current one.
+  extern __shared__ __align__(16) uint8_t ring[];  // [3 stages][x|dy][MAXV][256 threads] x 16 B
+  auto slot = [&](int st, int which, int i) {
+    return ring + ((static_cast<size_t>((st * 2 + which) * MAXV + i) * kThreads + threadIdx.x) << 4);
+  };
+  auto fetch = [&](int64_t g, int st) {
+    const int64_t row = g * RPB + sub;
+    if (g < n_groups && row < n) {
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int vi = t + i * TPR;
+        if (vi < nvec) {
+          cp_async16(slot(st, 0, i), x_or_y + row * emb + static_cast<int64_t>(vi) * VE);
+          cp_async16(slot(st, 1, i), dy + row * emb + static_cast<int64_t>(vi) * VE);
+        }
+      }
+    }
+    cp_async_commit();  // always commit so the group count is uniform
+  };
+  fetch(blockIdx.x, 0);
+  fetch(static_cast<int64_t>(blockIdx.x) + gridDim.x, 1);
+  int stage = 0;
   for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
     const int64_t row = g * RPB + sub;
     const bool live = row < n;  // TPR==256: uniform per CTA; TPR==32: uniform per warp
-    if (!live) continue;        // (no block barrier is used when TPR == 32)
-    const T* ar = x_or_y + row * emb;
-    const T* dr = dy + row * emb;
-    T* dxr = dx + row * emb;
+    fetch(g + 2 * static_cast<int64_t>(gridDim.x), stage == 0 ? 2 : stage - 1);
+    cp_async_wait<2>();  // everything but the two newest groups has landed
     float av[MAXV][VE], dv[MAXV][VE];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int vi = t + i * TPR;
-      if (vi < nvec) {
-        load_vec<T>(ar + static_cast<int64_t>(vi) * VE, av[i]);
-        load_vec<T>(dr + static_cast<int64_t>(vi) * VE, dv[i]);
+      if (live && vi < nvec) {
+        unpack_raw<T>(*reinterpret_cast<const uint4*>(slot(stage, 0, i)), av[i]);
+        unpack_raw<T>(*reinterpret_cast<const uint4*>(slot(stage, 1, i)), dv[i]);
       } else {
 #pragma unroll
         for (int j = 0; j < VE; ++j) av[i][j] = dv[i][j] = 0.f;
       }
     }
+    stage = stage == 2 ? 0 : stage + 1;
+    if (!live) continue;        // (no block barrier is used when TPR == 32)
+    T* dxr = dx + row * emb;
     if constexpr (OP == 0) {
       // dx = y*dy - y*sum(y*dy)              (src/softmax.jl:70-80)
       float s = 0.f;
@@ -522,18 +577,18 @@ struct BwdPlan {
   int64_t n_part;
 };
 template <typename T>
-BwdPlan bwd_plan(int64_t emb, int64_t n, bool all_aligned) {
+BwdPlan bwd_plan(int64_t emb, int64_t n, bool all_aligned, bool softmax) {
   constexpr int VE = 16 / sizeof(T);
   BwdPlan p;
   const int64_t nvec = emb / VE;
   const int max_ctas = sm_count() * 4;
-  constexpr int MAXV = 16 / VE;
+  constexpr int MAXV = 4;
   if (all_aligned && emb % VE == 0 && nvec <= 32 * MAXV) {
     p.mode = 1;
     const int64_t groups = (n + 7) / 8;
     p.grid = static_cast<int>(groups < max_ctas ? groups : max_ctas);
     p.n_part = static_cast<int64_t>(p.grid) * 8;
-  } else if (all_aligned && emb % VE == 0 && nvec <= 256 * MAXV) {
+  } else if (all_aligned && emb % VE == 0 && nvec <= 256 * (softmax ? 8 : MAXV)) {
     p.mode = 2;
     p.grid = static_cast<int>(n < max_ctas ? n : max_ctas);
     p.n_part = p.grid;
@@ -558,17 +613,26 @@ int launch_fwd(void* y, float* s0, float* s1, const void* x, const void* w, cons
   const T* xx = static_cast<const T*>(x);
   const T* ww = static_cast<const T*>(w);
   const T* bb = static_cast<const T*>(b);
+  // smallest register cache (MAXV vectors per thread) that holds the row: fewer registers ->
+  // more resident CTAs -> more bytes in flight
+#define NNOP_FWD_LAUNCH(TPR_, MAXV_, GRID_)                                                    \
+  rowwise_fwd_vec<T, TPR_, MAXV_, OP><<<static_cast<unsigned>(GRID_), kThreads, 0, st>>>(      \
+      yy, s0, s1, xx, ww, bb, emb, n, eps, offset)
   if (al && nvec <= 32 * 8) {
     const int64_t grid = (n + 7) / 8;
-    rowwise_fwd_vec<T, 32, 8, OP><<<static_cast<unsigned>(grid), kThreads, 0, st>>>(
-        yy, s0, s1, xx, ww, bb, emb, n, eps, offset);
+    if (nvec <= 32) NNOP_FWD_LAUNCH(32, 1, grid);
+    else if (nvec <= 64) NNOP_FWD_LAUNCH(32, 2, grid);
+    else if (nvec <= 128) NNOP_FWD_LAUNCH(32, 4, grid);
+    else NNOP_FWD_LAUNCH(32, 8, grid);
   } else if (al && nvec <= 256 * 8) {
-    rowwise_fwd_vec<T, 256, 8, OP><<<static_cast<unsigned>(n), kThreads, 0, st>>>(
-        yy, s0, s1, xx, ww, bb, emb, n, eps, offset);
+    if (nvec <= 512) NNOP_FWD_LAUNCH(256, 2, n);
+    else if (nvec <= 1024) NNOP_FWD_LAUNCH(256, 4, n);
+    else NNOP_FWD_LAUNCH(256, 8, n);
   } else {
     rowwise_fwd_generic<T, OP><<<static_cast<unsigned>(n), kThreads, 0, st>>>(
         yy, s0, s1, xx, ww, bb, emb, n, eps, offset);
   }
+#undef NNOP_FWD_LAUNCH
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
 }
@@ -581,7 +645,7 @@ int launch_bwd(void* dx, TW* dw, TW* db, const void* dy, const void* a, const fl
   if (n == 0 || emb == 0) return NNOP_OK;
   const bool al = aligned16(dx) && aligned16(dy) && aligned16(a) && (OP == 0 || aligned16(w)) &&
                   (OP == 0 || aligned16(ws));
-  const BwdPlan plan = bwd_plan<T>(emb, n, al);
+  const BwdPlan plan = bwd_plan<T>(emb, n, al, OP == 0);
   float* p0 = nullptr;
   float* p1 = nullptr;
   if (OP != 0) {
@@ -596,20 +660,41 @@ int launch_bwd(void* dx, TW* dw, TW* db, const void* dy, const void* a, const fl
   const T* dyy = static_cast<const T*>(dy);
   const T* aa = static_cast<const T*>(a);
   const T* ww = static_cast<const T*>(w);
+  const int64_t nvec = emb / VE;
+  // persistent grid = what is actually resident (occupancy x SMs, at most 4 per SM), so every
+  // CTA streams rows back to back with its prefetch pipeline full
+  int grid = plan.grid;
+  int64_t n_part = plan.n_part;
+  auto run = [&](auto kern, int rows_per_cta, int maxv) {
+    const int smem = maxv > 0 ? 3 * 2 * maxv * kThreads * 16 : 0;
+    if (smem > 32 * 1024)  // static smem (reduction scratch) counts against the 48 KB default too
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1)
+      occ = 1;
+    if (occ > 4) occ = 4;
+    const int64_t groups = (n + rows_per_cta - 1) / rows_per_cta;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * occ;
+    grid = static_cast<int>(groups < cap ? groups : cap);
+    n_part = static_cast<int64_t>(grid) * rows_per_cta;
+    kern<<<grid, kThreads, smem, st>>>(dxx, p0, p1, dyy, aa, s0, s1, ww, emb, n, offset);
+  };
   if (plan.mode == 1) {
-    rowwise_bwd_vec<T, 32, 16 / VE, OP><<<plan.grid, kThreads, 0, st>>>(dxx, p0, p1, dyy, aa, s0, s1, ww,
-                                                                  emb, n, offset);
+    if (nvec <= 32) run(rowwise_bwd_vec<T, 32, 1, OP>, 8, 1);
+    else if (nvec <= 64) run(rowwise_bwd_vec<T, 32, 2, OP>, 8, 2);
+    else run(rowwise_bwd_vec<T, 32, 4, OP>, 8, 4);
   } else if (plan.mode == 2) {
-    rowwise_bwd_vec<T, 256, 16 / VE, OP><<<plan.grid, kThreads, 0, st>>>(dxx, p0, p1, dyy, aa, s0, s1,
-                                                                   ww, emb, n, offset);
+    if (nvec <= 256) run(rowwise_bwd_vec<T, 256, 1, OP>, 1, 1);
+    else if (nvec <= 512) run(rowwise_bwd_vec<T, 256, 2, OP>, 1, 2);
+    else if (nvec <= 1024) run(rowwise_bwd_vec<T, 256, 4, OP>, 1, 4);
+    else if constexpr (OP == 0) run(rowwise_bwd_vec<T, 256, 8, OP>, 1, 8);
   } else {
-    rowwise_bwd_generic<T, OP><<<plan.grid, kThreads, 0, st>>>(dxx, p0, p1, dyy, aa, s0, s1, ww,
-                                                               emb, n, offset);
+    run(rowwise_bwd_generic<T, OP>, 1, 0);
   }
   NNOP_LAUNCH_CHECK();
   if (OP != 0) {
     // every (CTA, sub-row) writes its partial row (zeros if it never saw a live row)
-    const int64_t live_part = plan.n_part;
+    const int64_t live_part = n_part;
     const dim3 blk(32, 8);
     const unsigned grid = static_cast<unsigned>((emb + 31) / 32);
     reduce_partials<TW><<<grid, blk, 0, st>>>(dw, p0, live_part, emb);
