@@ -120,11 +120,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     mbar_init(do_full, 1);
     mbar_init(do_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
+    mbar_init(p_full, 8);    // one arrival per compute warp
     mbar_init(dp_full, 1);
-    mbar_init(ds_full, 256);
+    mbar_init(ds_full, 8);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 128);
+    mbar_init(dq_empty, 4);  // one arrival per drain warp
     mbar_init(dkdv_full, 1);
     fence_mbar_init();
   }
@@ -289,7 +289,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
       // ---- dS^T ----
       mbar_wait(dp_full, it & 1);
       tc_fence_after();
@@ -317,7 +318,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(ds_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
     }
     // ---- epilogue: dV (half 0) / dK (half 1) -> 16-bit -> swizzled smem -> TMA store ------
     if (n_it > 0) {
@@ -380,7 +382,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       for (int c = 0; c < D / 32; ++c) tmem_ld_x32(tmem_base + lane_off + kColDP + c * 32, r[c]);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(dq_empty);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
         uint8_t* stage = sdQ + (nred & 1) * 16384;
