@@ -30,6 +30,14 @@ namespace {
 constexpr int kBwdThreads = 512;
 constexpr float kLog2e = 1.4426950408889634f;
 
+#ifdef NNOP_BWD_TRACE
+// development aid: pipeline timeline of CTA (0,0,0), 16 clock64 stamps per q-block step
+__device__ long long g_bwd_trace[256 * 16];
+#define BWD_STAMP(i, k) do { if (tr) g_bwd_trace[(i) * 16 + (k)] = clock64(); } while (0)
+#else
+#define BWD_STAMP(i, k) do { } while (0)
+#endif
+
 struct BwdParams {
   const float* lse2p;   // (B*QH, QLp) lse * log2e, +inf padded
   const float* deltap;  // (B*QH, QLp)
@@ -90,6 +98,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef NNOP_BWD_TRACE
+  const bool tr = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#endif
 
   // ---- work assignment ----------------------------------------------------------------
   const int j = blockIdx.x;  // kv block
@@ -174,77 +185,100 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         load_do(it);
         if (it + 1 < n_it) load_q(it + 1);
       }
-    } else if (warp == 1 && lane == 0 && n_it > 0) {
+    } else if (warp == 1 && n_it > 0) {
       // ================================ MMA issuer ===================================
+      // Whole warp runs the uniform control flow and the waits; one elected lane issues.  All
+      // operands are warp-uniform so descriptors stay in uniform registers (see attn_fwd_sm100.cu).
       constexpr bool BF = is_bf16<T>::value;
       constexpr uint32_t id_kk = make_idesc_f16(128, 128, BF, false, false);  // S^T, dP^T
       constexpr uint32_t id_tv = make_idesc_f16(128, D, BF, false, true);     // dV (A in TMEM), dK
       constexpr uint32_t id_mm = make_idesc_f16(128, D, BF, true, true);      // dQ
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO),
-                     adS = smem_u32(sdS);
-      // D[128 x 128] = A[128 x D] B[128 x D]^T, both K-major tiles
+      const uint32_t tm = uniform_u32(tmem_base);
+      const uint32_t sbase = uniform_u32(smem_u32(smem));
+      // K-major views (LBO unused, SBO 1024) and MN-major views (LBO = next 64-element box)
+      // descriptor templates: operand = template low word + (byte offset >> 4), constant high word
+      const uint64_t kmaj = make_smem_desc_sw128(sbase, 16, 1024);        // K-major (SBO 1024)
+      const uint64_t mnmaj = make_smem_desc_sw128(sbase, S::kBox, 1024);  // MN-major (LBO = next box)
+      const uint32_t k_lo = desc_lo(kmaj), k_hi = desc_hi(kmaj);
+      const uint32_t m_lo = desc_lo(mnmaj), m_hi = desc_hi(mnmaj);
+      // D[128 x 128] = A[128 x D] B[128 x D]^T, both K-major tiles at byte offsets a0 / b0
       auto mma_kk = [&](uint32_t dcol, uint32_t a0, uint32_t b0) {
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t off = (ks >> 2) * S::kBox + (ks & 3) * 32;
-          umma_ss(tmem_base + dcol, make_smem_desc_sw128(a0 + off, 16, 1024),
-                  make_smem_desc_sw128(b0 + off, 16, 1024), id_kk, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t off = (ks >> 2) * S::kBox + (ks & 3) * 32;
+            umma_ss_lo(tm + dcol, k_lo, (a0 + off) >> 4, k_hi, k_lo, (b0 + off) >> 4, k_hi, id_kk,
+                       ks > 0 ? 1u : 0u);
+          }
         }
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) tc_commit(bar);
       };
       mbar_wait(kv_full, 0);
       mbar_wait(&q_full[0], 0);
       tc_fence_after();
-      mma_kk(kColS, aK, aQ);
-      tc_commit(s_full);
+      mma_kk(kColS, S::kK, S::kQ);
+      commit(s_full);
       mbar_wait(do_full, 0);
       tc_fence_after();
-      mma_kk(kColDP, aV, adO);
-      tc_commit(dp_full);
+      mma_kk(kColDP, S::kV, S::kdO);
+      commit(dp_full);
       for (int it = 0; it < n_it; ++it) {
         const int s = it & 1;
         const uint32_t acc = it > 0 ? 1u : 0u;
+        const uint32_t qoff = static_cast<uint32_t>(s * S::kTile);
         // dV += P^T dO_i
         mbar_wait(p_full, it & 1);
         tc_fence_after();
+        BWD_STAMP(it, 0);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_ts(tmem_base + kColDV, tmem_base + kColS + ks * 8,
-                  make_smem_desc_sw128(adO + ks * 2048, S::kBox, 1024), id_tv, (acc | (ks > 0)) ? 1u : 0u);
-        tc_commit(do_empty);
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ts_lo(tm + kColDV, tm + kColS + ks * 8, m_lo, (S::kdO + ks * 2048) >> 4, m_hi, id_tv,
+                       (acc | (ks > 0)) ? 1u : 0u);
+        }
+        commit(do_empty);
         // S^T(i+1)
         if (it + 1 < n_it) {
           mbar_wait(&q_full[s ^ 1], ((it + 1) >> 1) & 1);
           tc_fence_after();
-          mma_kk(kColS, aK, aQ + (s ^ 1) * S::kTile);
-          tc_commit(s_full);
+          mma_kk(kColS, S::kK, S::kQ + static_cast<uint32_t>((s ^ 1) * S::kTile));
+          commit(s_full);
         }
         // dQ_i = dS K_j   (A: dS^T smem viewed MN-major; B: K_j MN-major)
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
+        BWD_STAMP(it, 1);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_ss(tmem_base + kColDP, make_smem_desc_sw128(adS + ks * 2048, S::kBox, 1024),
-                  make_smem_desc_sw128(aK + ks * 2048, S::kBox, 1024), id_mm, ks > 0 ? 1u : 0u);
-        tc_commit(dq_full);
-        // dK += dS^T Q_i  (A: dS^T K-major; B: Q_i MN-major)
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t off = (ks >> 2) * S::kBox + (ks & 3) * 32;
-          umma_ss(tmem_base + kColDK, make_smem_desc_sw128(adS + off, 16, 1024),
-                  make_smem_desc_sw128(aQ + s * S::kTile + ks * 2048, S::kBox, 1024), id_tv,
-                  (acc | (ks > 0)) ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ss_lo(tm + kColDP, m_lo, (S::kdS + ks * 2048) >> 4, m_hi, m_lo, (S::kK + ks * 2048) >> 4,
+                       m_hi, id_mm, ks > 0 ? 1u : 0u);
         }
-        tc_commit(&q_empty[s]);
+        commit(dq_full);
+        // dK += dS^T Q_i  (A: dS^T K-major; B: Q_i MN-major)
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t off = (ks >> 2) * S::kBox + (ks & 3) * 32;
+            umma_ss_lo(tm + kColDK, k_lo, (S::kdS + off) >> 4, k_hi, m_lo, (S::kQ + qoff + ks * 2048) >> 4,
+                       m_hi, id_tv, (acc | (ks > 0)) ? 1u : 0u);
+          }
+        }
+        commit(&q_empty[s]);
         // dP^T(i+1) -- its TMEM columns hold dQ_i until the drain warpgroup has read them
         if (it + 1 < n_it) {
           mbar_wait(do_full, (it + 1) & 1);
+          BWD_STAMP(it, 2);
           mbar_wait(dq_empty, it & 1);
           tc_fence_after();
-          mma_kk(kColDP, aV, adO);
-          tc_commit(dp_full);
+          BWD_STAMP(it, 3);
+          mma_kk(kColDP, S::kV, S::kdO);
+          commit(dp_full);
         }
       }
-      tc_commit(dkdv_full);
+      commit(dkdv_full);
     }
   } else if (warp < 12) {
     // ================================ compute warpgroups ===============================
@@ -262,6 +296,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       mbar_wait(&q_full[s], (it >> 1) & 1);  // lse2 / delta of this stage have landed
       mbar_wait(s_full, it & 1);
       tc_fence_after();
+      if (wq == 0) BWD_STAMP(it, 4 + 4 * half);
       uint32_t sr[2][32];
       tmem_ld_x32(tmem_base + lane_off + kColS + c0, sr[0]);
       tmem_ld_x32(tmem_base + lane_off + kColS + c0 + 32, sr[1]);
@@ -291,9 +326,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (wq == 0) BWD_STAMP(it, 5 + 4 * half);
       // ---- dS^T ----
       mbar_wait(dp_full, it & 1);
       tc_fence_after();
+      if (wq == 0) BWD_STAMP(it, 6 + 4 * half);
       tmem_ld_x32(tmem_base + lane_off + kColDP + c0, sr[0]);
       tmem_ld_x32(tmem_base + lane_off + kColDP + c0 + 32, sr[1]);
       tmem_ld_wait();
@@ -320,6 +357,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
+      if (wq == 0) BWD_STAMP(it, 7 + 4 * half);
     }
     // ---- epilogue: dV (half 0) / dK (half 1) -> 16-bit -> swizzled smem -> TMA store ------
     if (n_it > 0) {
@@ -375,6 +413,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       const int q0 = (i0 + it % nqi) * 128;
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
+      if (wq == 0) BWD_STAMP(it, 12);
       // pull the whole dQ_i tile into registers first so its TMEM columns (shared with dP^T)
       // are released as early as possible -- this read sits on the dS -> dQ -> dP^T(i+1) chain
       uint32_t r[D / 32][32];
@@ -384,6 +423,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);
+      if (wq == 0) BWD_STAMP(it, 13);
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
         uint8_t* stage = sdQ + (nred & 1) * 16384;
@@ -521,6 +561,12 @@ int launch_bwd(const AttnParams& a) {
 }
 
 }  // namespace
+
+#ifdef NNOP_BWD_TRACE
+extern "C" int nnop_debug_bwd_trace(long long* host_out, int n) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, g_bwd_trace, sizeof(long long) * n));
+}
+#endif
 
 bool attn_sm100_bwd_available() { return true; }
 

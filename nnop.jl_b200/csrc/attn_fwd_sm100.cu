@@ -30,6 +30,27 @@ constexpr int kNStage = 4;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+#ifndef NNOP_FWD_POLY_EVERY
+#define NNOP_FWD_POLY_EVERY 0
+#endif
+// every kPolyEvery-th pair of exponentials runs on the FMA pipe instead of the MUFU (0 = none)
+constexpr int kPolyEvery = NNOP_FWD_POLY_EVERY;
+#ifndef NNOP_FWD_SPLIT_QK
+#define NNOP_FWD_SPLIT_QK 0
+#endif
+#ifndef NNOP_FWD_SPLIT_PV
+#define NNOP_FWD_SPLIT_PV 1
+#endif
+constexpr bool kSplitQK = NNOP_FWD_SPLIT_QK != 0;  // issue S columns 64.. of step i+1 before PV(i)
+constexpr bool kSplitPV = NNOP_FWD_SPLIT_PV != 0;  // start PV on keys 0..63 while 64..127 exponentiate
+
+#ifdef NNOP_FWD_TRACE
+// development aid: pipeline timeline of CTA (0,0,0), 16 clock64 stamps per kv step
+__device__ long long g_fwd_trace[256 * 16];
+#define FWD_STAMP(i, k) do { if (tr) g_fwd_trace[(i) * 16 + (k)] = clock64(); } while (0)
+#else
+#define FWD_STAMP(i, k) do { } while (0)
+#endif
 
 struct FwdParams {
   float* lse;
@@ -45,7 +66,7 @@ struct FwdSmem {
   static constexpr int kQOff = 0;
   static constexpr int kKVOff = 2 * kTileBytes;
   static constexpr int kBarOff = kKVOff + kNStage * kTileBytes;
-  static constexpr int kNumBars = 2 + 2 * kNStage + 6;
+  static constexpr int kNumBars = 2 + 2 * kNStage + 10;
   static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
   static constexpr int kDynBytes = kTotal + 1024;  // slack for manual 1024-byte alignment
 };
@@ -66,13 +87,17 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   uint64_t* q_full = bars;                     // [2]
   uint64_t* kv_full = bars + 2;                // [kNStage]
   uint64_t* kv_empty = bars + 2 + kNStage;     // [kNStage]
-  uint64_t* s_full = bars + 2 + 2 * kNStage;   // [2]
-  uint64_t* p_full = s_full + 2;               // [2]
-  uint64_t* o_full = s_full + 4;               // [2]
+  uint64_t* s_full = bars + 2 + 2 * kNStage;   // [2]  S_t complete in TMEM
+  uint64_t* s_read = s_full + 2;               // [2]  S_t now lives in registers (columns 64.. reusable)
+  uint64_t* p_half = s_full + 4;               // [2][2]  P_t keys 0..63 / 64..127 written
+  uint64_t* o_full = s_full + 8;               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S::kNumBars);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef NNOP_FWD_TRACE
+  const bool tr = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#endif
 
   // ---- work assignment ----------------------------------------------------------------
   const int qt = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heaviest first
@@ -99,7 +124,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&s_read[t], 4);  // one arrival per softmax warp
+      mbar_init(&p_half[2 * t], 4);
+      mbar_init(&p_half[2 * t + 1], 4);
       mbar_init(&o_full[t], 1);
     }
     fence_mbar_init();
@@ -111,7 +138,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    setmaxnreg_dec<72>();  // releases 128*(168-72) = 12288 regs = 256*(216-168)
+    setmaxnreg_dec<80>();  // 128*80 + 256*208 = 63488 <= 64K registers
     if (warp == 0 && lane == 0) {
       // ================================ TMA producer =================================
       mbar_arrive_expect_tx(&q_full[0], S::kTileBytes);
@@ -143,83 +170,123 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         load_kv(&tm_k, i);
         load_kv(&tm_v, i);
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ================================ MMA issuer ===================================
+      // The whole warp runs the (uniform) control flow and the barrier waits; one elected lane
+      // issues tcgen05.mma / commit.  Keeping every operand warp-uniform lets descriptors live in
+      // uniform registers (a lane-0-only branch costs a local-memory reload + R2UR waterfall per MMA).
       constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, is_bf16<T>::value, false, false);
+      constexpr uint32_t idesc_qk64 = make_idesc_f16(128, 64, is_bf16<T>::value, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, D, is_bf16<T>::value, false, true);
-      const uint32_t q_base = smem_u32(sQ);
-      const uint32_t kv_base = smem_u32(sKV);
+      const uint32_t tm = uniform_u32(tmem_base);
+      const uint32_t q_base = uniform_u32(smem_u32(sQ));
+      const uint32_t kv_base = uniform_u32(smem_u32(sKV));
+      const uint64_t dq0 = make_smem_desc_sw128(q_base, 16, 1024);               // K-major operands
+      const uint64_t dk0 = make_smem_desc_sw128(kv_base, 16, 1024);
+      const uint64_t dv0 = make_smem_desc_sw128(kv_base, S::kBoxBytes, 1024);    // V as MN-major B
       auto slot_wait = [&](int slot) {
         mbar_wait(&kv_full[slot % kNStage], (slot / kNStage) & 1);
       };
+      // descriptor address field is (byte address >> 4): advancing an operand = adding bytes/16.
+      // (Building descriptors inside the asm block, as the backward does, measured 5% slower here.)
       auto qk = [&](int t, int slot) {
-        const uint32_t a0 = q_base + t * S::kTileBytes;
-        const uint32_t b0 = kv_base + (slot % kNStage) * S::kTileBytes;
-        const uint32_t d = tmem_base + t * 128;
+        const uint64_t a0 = dq0 + static_cast<uint64_t>((t * S::kTileBytes) >> 4);
+        const uint64_t b0 = dk0 + static_cast<uint64_t>(((slot % kNStage) * S::kTileBytes) >> 4);
+        const uint32_t d = tm + t * 128;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t off = (ks >> 2) * S::kBoxBytes + (ks & 3) * 32;
-          umma_ss(d, make_smem_desc_sw128(a0 + off, 16, 1024),
-                  make_smem_desc_sw128(b0 + off, 16, 1024), idesc_qk, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t off = ((ks >> 2) * S::kBoxBytes + (ks & 3) * 32) >> 4;
+            umma_ss(d, a0 + off, b0 + off, idesc_qk, ks > 0 ? 1u : 0u);
+          }
         }
       };
-      auto pv = [&](int t, int slot, bool acc) {
-        const uint32_t b0 = kv_base + (slot % kNStage) * S::kTileBytes;
-        const uint32_t d = tmem_base + 256 + t * D;
-        const uint32_t a = tmem_base + t * 128;  // P aliases S
+      // keys [64*hf, 64*hf+64) of the block -> S columns [64*hf, 64*hf+64)
+      auto qk_half = [&](int t, int slot, int hf) {
+        const uint64_t a0 = dq0 + static_cast<uint64_t>((t * S::kTileBytes) >> 4);
+        const uint64_t b0 = dk0 + static_cast<uint64_t>(((slot % kNStage) * S::kTileBytes + hf * (64 * 128)) >> 4);
+        const uint32_t d = tm + t * 128 + hf * 64;
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_ts(d, a + j * 8, make_smem_desc_sw128(b0 + j * 2048, S::kBoxBytes, 1024), idesc_pv,
-                  (acc || j > 0) ? 1u : 0u);
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t off = ((ks >> 2) * S::kBoxBytes + (ks & 3) * 32) >> 4;
+            umma_ss(d, a0 + off, b0 + off, idesc_qk64, ks > 0 ? 1u : 0u);
+          }
+        }
+      };
+      // O_t += P_t[:, 64*hf .. 64*hf+64) V[64*hf .. 64*hf+64, :]
+      auto pv_half = [&](int t, int slot, int hf, bool acc) {
+        const uint64_t b0 = dv0 + static_cast<uint64_t>(((slot % kNStage) * S::kTileBytes) >> 4);
+        const uint32_t d = tm + 256 + t * D;
+        const uint32_t a = tm + t * 128;  // P aliases S columns [0, 64)
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 4 * hf; j < 4 * hf + 4; ++j)
+            umma_ts(d, a + j * 8, b0 + ((j * 2048) >> 4), idesc_pv, (acc || j > 0) ? 1u : 0u);
+        }
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) tc_commit(bar);
       };
       mbar_wait(&q_full[0], 0);
       slot_wait(0);
       tc_fence_after();
       qk(0, 0);
-      tc_commit(&s_full[0]);
+      commit(&s_full[0]);
       if (act1) {
         mbar_wait(&q_full[1], 0);
         tc_fence_after();
         qk(1, 0);
-        tc_commit(&s_full[1]);
+        commit(&s_full[1]);
       }
-      tc_commit(&kv_empty[0]);
+      commit(&kv_empty[0]);
+      // Per step and tile the tensor pipe sees PV_lo(i), PV_hi(i) (as each half of P lands) and
+      // QK(i+1) (its columns alias P, so it follows PV in the in-order pipe).  With kSplitQK the
+      // upper half of S(i+1) is issued as soon as the softmax warpgroup holds S(i) in registers.
       for (int i = 0; i < nblk; ++i) {
         const int vslot = 2 * i + 1, knext = 2 * i + 2;
-        slot_wait(vslot);
-        if (i < nb0) {
-          mbar_wait(&p_full[0], i & 1);
-          tc_fence_after();
-          pv(0, vslot, i > 0);
-          if (i + 1 < nb0) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int nbt = t ? nb1 : nb0;
+          if (i >= nbt) continue;
+          const bool has_next = i + 1 < nbt;
+          if (kSplitQK && has_next) {
+            mbar_wait(&s_read[t], i & 1);
             slot_wait(knext);
             tc_fence_after();
-            qk(0, knext);
-            tc_commit(&s_full[0]);
-          } else {
-            tc_commit(&o_full[0]);
+            qk_half(t, knext, 1);
           }
-        }
-        if (act1) {
-          mbar_wait(&p_full[1], i & 1);
+          mbar_wait(&p_half[2 * t], i & 1);
+          slot_wait(vslot);
           tc_fence_after();
-          pv(1, vslot, i > 0);
-          if (i + 1 < nblk) {
-            slot_wait(knext);
+          FWD_STAMP(i, 10 + 2 * t);
+          pv_half(t, vslot, 0, i > 0);
+          if (kSplitPV) {
+            mbar_wait(&p_half[2 * t + 1], i & 1);
             tc_fence_after();
-            qk(1, knext);
-            tc_commit(&s_full[1]);
-          } else {
-            tc_commit(&o_full[1]);
           }
+          pv_half(t, vslot, 1, true);
+          if (has_next) {
+            if (kSplitQK) {
+              qk_half(t, knext, 0);
+            } else {
+              slot_wait(knext);
+              tc_fence_after();
+              qk(t, knext);
+            }
+            commit(&s_full[t]);
+          } else {
+            commit(&o_full[t]);
+          }
+          FWD_STAMP(i, 11 + 2 * t);
         }
-        tc_commit(&kv_empty[vslot % kNStage]);
-        if (i + 1 < nblk) tc_commit(&kv_empty[knext % kNStage]);
+        commit(&kv_empty[vslot % kNStage]);
+        if (i + 1 < nblk) commit(&kv_empty[knext % kNStage]);
       }
     }
   } else {
     // ================================ softmax warpgroups ===============================
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<208>();
     const int t = (warp - 4) >> 2;
     const int nbt = t ? nb1 : nb0;
     if (nbt > 0) {
@@ -230,16 +297,24 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       const uint32_t tS = tmem_base + lane_off + t * 128;
       const uint32_t tO = tmem_base + lane_off + 256 + t * D;
       const float sl2 = p.scale_log2;
-      float m_used = -INFINITY;  // reference max in scaled log2 units
+      float m_used = -1e30f;  // reference max in scaled log2 units (finite: see the speculation note)
       float l = 0.f;
 
+      const uint64_t sl2x2 = pack_f2(sl2, sl2);
       for (int i = 0; i < nbt; ++i) {
         mbar_wait(&s_full[t], i & 1);
         tc_fence_after();
+        if (wq == 0) FWD_STAMP(i, 5 * t + 0);
         uint32_t sr[4][32];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, sr[c]);
         tmem_ld_wait();
+        if (wq == 0) FWD_STAMP(i, 5 * t + 1);
+        if (kSplitQK) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_read[t]);
+        }
 
         const int k0 = i * 128;
         const bool need_mask = (k0 + 128 > p.KL) || (p.causal && (k0 + 127 > q0 + t * 128));
@@ -251,22 +326,49 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
             for (int j = 0; j < 32; ++j)
               if (k0 + c * 32 + j > lim) sr[c][j] = 0xff800000u;  // -inf
         }
-        float mx = -INFINITY;
+        // exp2(S*scale*log2e - m_used) of one 32-key chunk; every kPolyEvery-th pair runs on the
+        // FMA pipe (exp2_poly2) instead of the MUFU
+        auto exp_chunk = [&](int c, float (&pf)[32]) {
+          const uint64_t negm2 = pack_f2(-m_used, -m_used);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint64_t x2 = ffma2(pack_f2(__uint_as_float(sr[c][2 * j]), __uint_as_float(sr[c][2 * j + 1])),
+                                      sl2x2, negm2);
+            float x0, x1;
+            unpack_f2(x2, x0, x1);
+            if (kPolyEvery > 0 && (j % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
+              exp2_poly2(x0, x1, pf[2 * j], pf[2 * j + 1]);
+            } else {
+              pf[2 * j] = fast_exp2(x0);
+              pf[2 * j + 1] = fast_exp2(x1);
+            }
+          }
+        };
+        float pf[32];
+        // Speculation: start exponentiating chunk 0 against the running reference max while the
+        // row max of this block is still being reduced (ALU pipe, off the critical path).  Any
+        // finite reference is exact as long as P, l and O share it; only if the block raises the
+        // max by more than 2^kRescaleThreshold is the reference moved (O, l rescaled) and chunk 0
+        // redone.  m_used starts at -1e30 so the first block always takes that path.
+        exp_chunk(0, pf);
+        float mx8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mx8[u] = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sr[c][j]));
+          for (int j = 0; j < 16; ++j)
+            mx8[j & 7] = fmax3(mx8[j & 7], __uint_as_float(sr[c][2 * j]), __uint_as_float(sr[c][2 * j + 1]));
+        const float mx = fmax3(fmax3(mx8[0], mx8[1], mx8[2]), fmax3(mx8[3], mx8[4], mx8[5]),
+                               fmaxf(mx8[6], mx8[7]));
         const float mx_s = mx * sl2;
-
-        if (i == 0) {
-          m_used = (mx_s == -INFINITY) ? 0.f : mx_s;
-        } else {
-          const bool grow = mx_s > m_used + kRescaleThreshold;
-          if (__any_sync(0xffffffffu, grow)) {
-            const float m_new = grow ? mx_s : m_used;
-            const float alpha = fast_exp2(m_used - m_new);
-            m_used = m_new;
-            l *= alpha;
+        const bool grow = mx_s > m_used + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = grow ? mx_s : m_used;
+          const float alpha = fast_exp2(m_used - m_new);
+          m_used = m_new;
+          l *= alpha;
+          if (i > 0) {
 #pragma unroll
             for (int c = 0; c < D / 32; ++c) {
               uint32_t orow[32];
@@ -277,25 +379,31 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
               tmem_st_x32(tO + c * 32, orow);
             }
           }
+          exp_chunk(0, pf);
         }
-
-        float sum = 0.f;
+        if (wq == 0) FWD_STAMP(i, 5 * t + 2);
+        uint64_t sum2 = pack_f2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          if (c > 0) exp_chunk(c, pf);
           uint32_t pr[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c][2 * j]), sl2, -m_used));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c][2 * j + 1]), sl2, -m_used));
-            sum += p0 + p1;
-            pr[j] = pack2<T>(p0, p1);
+            sum2 = fadd2(sum2, pack_f2(pf[2 * j], pf[2 * j + 1]));
+            pr[j] = pack2<T>(pf[2 * j], pf[2 * j + 1]);
           }
           tmem_st_x16(tS + c * 16, pr);
+          if (kSplitPV ? (c & 1) : (c == 3)) {  // (half of) the keys are in TMEM: release the tensor pipe
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_half[2 * t + (kSplitPV ? (c >> 1) : 0)]);
+            if (wq == 0) FWD_STAMP(i, 5 * t + 3 + (c >> 1));
+          }
         }
-        l += sum;
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[t]);
+        float s0, s1;
+        unpack_f2(sum2, s0, s1);
+        l += s0 + s1;
       }
 
       // ---- epilogue: O / l -> 16-bit -> swizzled smem (the Q_t buffer) -> TMA store -----
@@ -368,6 +476,12 @@ int launch_fwd(const AttnParams& a) {
 }
 
 }  // namespace
+
+#ifdef NNOP_FWD_TRACE
+extern "C" int nnop_debug_fwd_trace(long long* host_out, int n) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, g_fwd_trace, sizeof(long long) * n));
+}
+#endif
 
 bool attn_sm100_supported(const AttnParams& a, bool backward) {
   if (backward && !attn_sm100_bwd_available()) return false;

@@ -34,6 +34,21 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// one lane of a fully active warp (always the same lane for a given mask); the other lanes
+// keep running the warp-uniform control flow around it, so operands stay in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// tell the compiler a value is warp-uniform (lets it live in a uniform register)
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
@@ -57,6 +72,66 @@ __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+
+// -------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100: two lanes per issue slot) and a
+// software exp2 that runs on the FMA/ALU pipes, used to take load off the MUFU (XU) pipe
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack_f2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2_rm(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.ftz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// 2^x for a pair, x <= ~120, without the MUFU: x = n + f with n = floor(x) (round-to-minus-inf
+// add of 1.5*2^23 leaves n in the low mantissa bits), 2^f by a degree-3 minimax polynomial
+// (max relative error 8.8e-5, below the 16-bit rounding of P), exponent patched in by an
+// integer add.  Inputs below -127 are clamped (result ~ 2^-127, flushed to 0 by later .ftz math).
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& y0, float& y1) {
+  const uint64_t kRnd = pack_f2(12582912.f, 12582912.f);
+  const uint64_t kNegRnd = pack_f2(-12582912.f, -12582912.f);
+  const uint64_t kNegOne = pack_f2(-1.f, -1.f);
+  const uint64_t x = pack_f2(fmaxf(x0, -127.f), fmaxf(x1, -127.f));
+  const uint64_t xr = fadd2_rm(x, kRnd);
+  const uint64_t xrb = fadd2(xr, kNegRnd);
+  const uint64_t f = ffma2(xrb, kNegOne, x);
+  uint64_t p = ffma2(pack_f2(0.077119089663028717f, 0.077119089663028717f), f,
+                     pack_f2(0.227564394474029541f, 0.227564394474029541f));
+  p = ffma2(p, f, pack_f2(0.695146143436431885f, 0.695146143436431885f));
+  p = ffma2(p, f, pack_f2(1.f, 1.f));
+  float n0, n1, p0, p1;
+  unpack_f2(xr, n0, n1);
+  unpack_f2(p, p0, p1);
+  y0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(n0) << 23));
+  y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(n1) << 23));
 }
 
 // -------------------------------------------------------------------------------------
@@ -275,6 +350,48 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Variants that build the 64-bit descriptors inside the asm block from (template low word +
+// 16-byte-unit offset, constant high word).  The compiler then keeps one 32-bit template per
+// layout live instead of hoisting (and spilling) a 64-bit descriptor per K step, so the first
+// MMA after a barrier wait issues without a chain of local-memory reloads.
+__device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return static_cast<uint32_t>(d); }
+__device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return static_cast<uint32_t>(d >> 32); }
+__device__ __forceinline__ void umma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t a_off,
+                                           uint32_t a_hi, uint32_t b_lo, uint32_t b_off,
+                                           uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 la, lb;\n"
+      ".reg .b64 da, db;\n"
+      "add.u32 la, %1, %2;\n"
+      "add.u32 lb, %4, %5;\n"
+      "mov.b64 da, {la, %3};\n"
+      "mov.b64 db, {lb, %6};\n"
+      "setp.ne.b32 p, %8, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_off), "r"(a_hi), "r"(b_lo), "r"(b_off), "r"(b_hi), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
+                                           uint32_t b_off, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 lb;\n"
+      ".reg .b64 db;\n"
+      "add.u32 lb, %2, %3;\n"
+      "mov.b64 db, {lb, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_off), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
