@@ -101,6 +101,31 @@ int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, const void* d
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Packed variable-length flash attention (additive: the reference only has the dense Bool
+ * `kpad_mask`, src/attention.jl:73-79, which pays for every padded tile).  nseq sequences are
+ * concatenated along L:
+ *   q, o, dq, dO (E, total_q, QH) T ;  k, v, dk, dv (E, total_k, KH) T ;  lse (total_q, QH) float
+ *   cu_seqlens_q / cu_seqlens_k : nseq+1 int32 DEVICE arrays, cu[0] = 0, cu[nseq] = total;
+ *   sequence z owns rows [cu[z], cu[z+1]).  max_seqlen_* >= the longest sequence (sizes the grid).
+ *   causal is top-left aligned per sequence (k_idx <= q_idx), as in the dense call.
+ * Float16 / BFloat16, E in {64, 128} (tcgen05 path); same math as `_flash_attention` /
+ * `∇flash_attention` applied per sequence (src/attention.jl:133-177, src/attention_bwd.jl:199-275).
+ */
+int nnop_flash_attn_varlen_fwd(void* o, float* lse, const void* q, const void* k, const void* v,
+                               const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int nseq,
+                               int max_seqlen_q, int max_seqlen_k, int64_t total_q, int64_t total_k,
+                               int dtype, int E, int QH, int KH, int causal, float scale,
+                               void* stream);
+size_t nnop_flash_attn_varlen_bwd_workspace_bytes(int dtype, int E, int nseq, int64_t total_q,
+                                                  int QH);
+int nnop_flash_attn_varlen_bwd(void* dq, void* dk, void* dv, const void* dO, const void* o,
+                               const float* lse, const void* q, const void* k, const void* v,
+                               const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int nseq,
+                               int max_seqlen_q, int max_seqlen_k, int64_t total_q, int64_t total_k,
+                               int dtype, int E, int QH, int KH, int causal, float scale,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * online softmax over dim 1 of x (N, cols).  Replaces `online_softmax` / `online_softmax!`
  * (src/softmax.jl:60-68, :19-58) and `∇online_softmax` (src/softmax.jl:70-80).
  */

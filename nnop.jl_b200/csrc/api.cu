@@ -217,3 +217,97 @@ extern "C" int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, co
   }
   return attn_generic_bwd(p);
 }
+
+// ---------------------------------------------------------------------------------------
+// packed variable-length attention (additive API): tcgen05 path only
+// ---------------------------------------------------------------------------------------
+static int validate_varlen(int dtype, int E, int nseq, int max_q, int max_k, int64_t total_q,
+                           int64_t total_k, int QH, int KH) {
+  if (int rc = validate(dtype, E, max_q, max_k, QH, KH, 1)) return rc;
+  if (dtype == NNOP_F32)
+    return fail(NNOP_ERR_DTYPE, "packed variable-length attention supports Float16 / BFloat16 only");
+  if (E != 64 && E != 128)
+    return fail(NNOP_ERR_UNSUPPORTED_E,
+                "packed variable-length attention supports embedding dims 64 and 128, got `%d`.", E);
+  if (nseq < 0 || total_q < 0 || total_k < 0 || total_q > 0x7fffffff || total_k > 0x7fffffff)
+    return fail(NNOP_ERR_SHAPE, "Invalid packed shape nseq=%d total_q=%lld total_k=%lld.", nseq,
+                static_cast<long long>(total_q), static_cast<long long>(total_k));
+  return NNOP_OK;
+}
+
+extern "C" int nnop_flash_attn_varlen_fwd(void* o, float* lse, const void* q, const void* k,
+                                          const void* v, const int32_t* cu_seqlens_q,
+                                          const int32_t* cu_seqlens_k, int nseq, int max_seqlen_q,
+                                          int max_seqlen_k, int64_t total_q, int64_t total_k,
+                                          int dtype, int E, int QH, int KH, int causal, float scale,
+                                          void* stream) {
+  clear_error();
+  if (int rc = validate_varlen(dtype, E, nseq, max_seqlen_q, max_seqlen_k, total_q, total_k, QH, KH))
+    return rc;
+  if (nseq == 0 || total_q == 0 || max_seqlen_q == 0) return NNOP_OK;
+  if (!o || !lse || !q || !cu_seqlens_q || !cu_seqlens_k || (total_k > 0 && (!k || !v)))
+    return fail(NNOP_ERR_ARG, "NULL pointer");
+  AttnParams p{};
+  p.o = o; p.lse = lse; p.q = q; p.k = k; p.v = v;
+  p.dtype = dtype; p.E = E; p.QL = max_seqlen_q; p.KL = max_seqlen_k; p.QH = QH; p.KH = KH; p.B = 1;
+  p.causal = causal ? 1 : 0; p.scale = scale;
+  p.stream = static_cast<cudaStream_t>(stream);
+  p.cu_q = cu_seqlens_q; p.cu_k = cu_seqlens_k; p.nseq = nseq; p.total_q = total_q;
+  p.total_k = total_k > 0 ? total_k : 1;  // a TMA map needs a non-empty extent; no key is ever read
+  if (!attn_sm100_supported(p, false))
+    return fail(NNOP_ERR_ARG, "packed attention: pointers must be 16-byte aligned, heads <= 65535");
+  g_last_path = 1;
+  return attn_sm100_fwd(p);
+}
+
+extern "C" size_t nnop_flash_attn_varlen_bwd_workspace_bytes(int dtype, int E, int nseq,
+                                                             int64_t total_q, int QH) {
+  (void)dtype;
+  if (E <= 0 || nseq <= 0 || total_q <= 0 || QH <= 0) return 0;
+  return attn_sm100_bwd_packed_workspace_bytes(E, total_q, nseq, QH);
+}
+
+extern "C" int nnop_flash_attn_varlen_bwd(void* dq, void* dk, void* dv, const void* dO,
+                                          const void* o, const float* lse, const void* q,
+                                          const void* k, const void* v,
+                                          const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
+                                          int nseq, int max_seqlen_q, int max_seqlen_k,
+                                          int64_t total_q, int64_t total_k, int dtype, int E, int QH,
+                                          int KH, int causal, float scale, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  clear_error();
+  if (int rc = validate_varlen(dtype, E, nseq, max_seqlen_q, max_seqlen_k, total_q, total_k, QH, KH))
+    return rc;
+  if (nseq == 0 || (total_q == 0 && total_k == 0)) return NNOP_OK;
+  if (!cu_seqlens_q || !cu_seqlens_k || (total_q > 0 && (!dq || !dO || !o || !lse || !q)) ||
+      (total_k > 0 && (!dk || !dv || !k || !v)))
+    return fail(NNOP_ERR_ARG, "NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (total_q == 0 || max_seqlen_q == 0 || total_k == 0 || max_seqlen_k == 0) {  // all gradients are zero
+    if (total_k > 0) {
+      const size_t kvb = static_cast<size_t>(KH) * total_k * E * dtype_size(dtype);
+      NNOP_CUDA_CHECK(cudaMemsetAsync(dk, 0, kvb, st));
+      NNOP_CUDA_CHECK(cudaMemsetAsync(dv, 0, kvb, st));
+    }
+    if (total_q > 0)
+      NNOP_CUDA_CHECK(cudaMemsetAsync(dq, 0, static_cast<size_t>(QH) * total_q * E * dtype_size(dtype), st));
+    return NNOP_OK;
+  }
+  const size_t need = nnop_flash_attn_varlen_bwd_workspace_bytes(dtype, E, nseq, total_q, QH);
+  if (!workspace || workspace_bytes < need)
+    return fail(NNOP_ERR_WORKSPACE, "packed flash attention backward needs a %zu-byte workspace, got %zu",
+                need, workspace_bytes);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+    return fail(NNOP_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  AttnParams p{};
+  p.o = const_cast<void*>(o); p.lse = const_cast<float*>(lse);
+  p.q = q; p.k = k; p.v = v; p.dq = dq; p.dk = dk; p.dv = dv; p.dO = dO;
+  p.delta = static_cast<float*>(workspace);
+  p.dtype = dtype; p.E = E; p.QL = max_seqlen_q; p.KL = max_seqlen_k; p.QH = QH; p.KH = KH; p.B = 1;
+  p.causal = causal ? 1 : 0; p.scale = scale; p.stream = st;
+  p.cu_q = cu_seqlens_q; p.cu_k = cu_seqlens_k; p.nseq = nseq; p.total_q = total_q; p.total_k = total_k;
+  if (!attn_sm100_supported(p, true))
+    return fail(NNOP_ERR_ARG, "packed attention: pointers must be 16-byte aligned, heads <= 65535");
+  g_last_path = 1;
+  return attn_sm100_bwd(p);
+}

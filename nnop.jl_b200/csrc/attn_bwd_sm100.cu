@@ -43,7 +43,17 @@ struct BwdParams {
   const float* deltap;  // (B*QH, QLp)
   int QL, KL, QH, KH, QLp, causal;
   float scale, scale_log2;
+  // packed variable-length mode (cu_q != nullptr): sequence z = blockIdx.z; QL / KL are maxima;
+  // the padded statistics of sequence z start at row (cu_q[z] / 128 + z) * 128 of a QLp-long axis
+  const int* cu_q;
+  const int* cu_k;
+  void* dk_ptr;
+  void* dv_ptr;
+  int64_t total_k;
 };
+
+// first padded-statistics row of packed sequence z (each sequence is padded to whole 128-row blocks)
+__device__ __forceinline__ int packed_stat_row(int cu, int z) { return ((cu >> 7) + z) << 7; }
 
 template <int D>
 struct BwdSmem {
@@ -105,10 +115,21 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   // ---- work assignment ----------------------------------------------------------------
   const int j = blockIdx.x;  // kv block
   const int k0 = j * 128;
-  const int hk = blockIdx.y, b = blockIdx.z;
+  const int hk = blockIdx.y;
+  const bool packed = p.cu_q != nullptr;
+  int QL = p.QL, KL = p.KL, q_off = 0, k_off = 0, st_off = 0, b = blockIdx.z;
+  if (packed) {
+    q_off = p.cu_q[blockIdx.z];
+    QL = p.cu_q[blockIdx.z + 1] - q_off;
+    k_off = p.cu_k[blockIdx.z];
+    KL = p.cu_k[blockIdx.z + 1] - k_off;
+    st_off = packed_stat_row(q_off, blockIdx.z);
+    b = 0;
+    if (k0 >= KL) return;  // grid sized for the longest sequence
+  }
   const int g = p.QH / p.KH;
   const int bh_kv = b * p.KH + hk;
-  const int nq = (p.QL + 127) >> 7;
+  const int nq = (QL + 127) >> 7;
   const int i0 = p.causal ? j : 0;
   const int nqi = nq > i0 ? nq - i0 : 0;
   const int n_it = nqi * g;
@@ -153,8 +174,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       mbar_arrive_expect_tx(kv_full, 2 * S::kTile);
 #pragma unroll
       for (int bx = 0; bx < S::kNBox; ++bx) {
-        tma_load_3d(sK + bx * S::kBox, &tm_k, kv_full, bx * 64, k0, bh_kv);
-        tma_load_3d(sV + bx * S::kBox, &tm_v, kv_full, bx * 64, k0, bh_kv);
+        tma_load_3d(sK + bx * S::kBox, &tm_k, kv_full, bx * 64, k_off + k0, bh_kv);
+        tma_load_3d(sV + bx * S::kBox, &tm_v, kv_full, bx * 64, k_off + k0, bh_kv);
       }
       auto load_q = [&](int it) {
         const int s = it & 1;
@@ -164,8 +185,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         mbar_arrive_expect_tx(&q_full[s], S::kTile + 1024);
 #pragma unroll
         for (int bx = 0; bx < S::kNBox; ++bx)
-          tma_load_3d(sQ + s * S::kTile + bx * S::kBox, &tm_q, &q_full[s], bx * 64, q0, bh_q);
-        const int64_t soff = static_cast<int64_t>(bh_q) * p.QLp + q0;
+          tma_load_3d(sQ + s * S::kTile + bx * S::kBox, &tm_q, &q_full[s], bx * 64, q_off + q0, bh_q);
+        const int64_t soff = static_cast<int64_t>(bh_q) * p.QLp + st_off + q0;
         bulk_load_1d(s_lse + s * 128, p.lse2p + soff, 512, &q_full[s]);
         bulk_load_1d(s_del + s * 128, p.deltap + soff, 512, &q_full[s]);
       };
@@ -176,7 +197,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         mbar_arrive_expect_tx(do_full, S::kTile);
 #pragma unroll
         for (int bx = 0; bx < S::kNBox; ++bx)
-          tma_load_3d(sdO + bx * S::kBox, &tm_do, do_full, bx * 64, q0, bh_q);
+          tma_load_3d(sdO + bx * S::kBox, &tm_do, do_full, bx * 64, q_off + q0, bh_q);
       };
       load_q(0);
       load_do(0);
@@ -316,6 +337,10 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         for (int c = 0; c < 64; ++c)
           if (row > c0 + c) pf[c] = 0.f;
       }
+      if (packed && k0 + row >= KL) {  // this key row belongs to the next packed sequence
+#pragma unroll
+        for (int c = 0; c < 64; ++c) pf[c] = 0.f;
+      }
       {
         uint32_t pk[32];
 #pragma unroll
@@ -390,14 +415,31 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           *reinterpret_cast<uint4*>(stage + bx * S::kBox + row * 128 + ((cin ^ (row & 7)) << 4)) = v;
         }
       }
-      fence_proxy_async_smem();
-      named_bar_sync(1 + half, 128);
-      if (wq == 0 && lane == 0) {
+      const int rows_left = KL - k0;
+      if (packed && rows_left < 128) {
+        // partial last block of a packed sequence: copy only its own rows (coalesced 16-byte stores)
+        named_bar_sync(1 + half, 128);
+        constexpr int kCPR = D / 8;
+        T* obase = static_cast<T*>(half ? p.dk_ptr : p.dv_ptr) +
+                   (static_cast<int64_t>(hk) * p.total_k + k_off + k0) * D;
+        const int tid = wq * 32 + lane;
+        for (int idx = tid; idx < rows_left * kCPR; idx += 128) {
+          const int r = idx / kCPR, chunk = idx % kCPR;
+          const int bx = chunk >> 3, cin = chunk & 7;
+          const uint4 v = *reinterpret_cast<const uint4*>(stage + bx * S::kBox + r * 128 +
+                                                          ((cin ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(r) * D + chunk * 8) = v;
+        }
+      } else {
+        fence_proxy_async_smem();
+        named_bar_sync(1 + half, 128);
+        if (wq == 0 && lane == 0) {
 #pragma unroll
-        for (int bx = 0; bx < S::kNBox; ++bx)
-          tma_store_3d(half ? &tm_dk : &tm_dv, stage + bx * S::kBox, bx * 64, k0, bh_kv);
-        bulk_commit();
-        bulk_wait_read<0>();
+          for (int bx = 0; bx < S::kNBox; ++bx)
+            tma_store_3d(half ? &tm_dk : &tm_dv, stage + bx * S::kBox, bx * 64, k_off + k0, bh_kv);
+          bulk_commit();
+          bulk_wait_read<0>();
+        }
       }
     }
   } else {
@@ -437,7 +479,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         fence_proxy_async_smem();
         named_bar_sync(3, 128);
         if (issuer) {
-          tma_reduce_add_3d(&tm_dqa, stage, c * 32, q0, bh_q);
+          tma_reduce_add_3d(&tm_dqa, stage, c * 32, q_off + q0, bh_q);
           bulk_commit();
         }
         ++nred;
@@ -492,6 +534,42 @@ attn_bwd_prep_kernel(float* __restrict__ deltap, float* __restrict__ lse2p,
   }
 }
 
+// prep for packed sequences: grid (row groups of the longest padded sequence, QH, nseq)
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_packed_kernel(float* __restrict__ deltap, float* __restrict__ lse2p,
+                            float* __restrict__ dq_accum, const T* __restrict__ dO,
+                            const T* __restrict__ o, const float* __restrict__ lse,
+                            const int* __restrict__ cu_q, int64_t total_q, int64_t QLp) {
+  constexpr int LPR = D / 8;
+  const int z = blockIdx.z, h = blockIdx.y;
+  const int q_off = cu_q[z];
+  const int QL = cu_q[z + 1] - q_off;
+  const int r = blockIdx.x * (256 / LPR) + threadIdx.x / LPR;  // row within the padded sequence
+  const int li = threadIdx.x % LPR;
+  if (r >= ((QL + 127) & ~127)) return;  // whole row groups exit together
+  float acc = 0.f;
+  if (r < QL) {
+    const int64_t off = (static_cast<int64_t>(h) * total_q + q_off + r) * D + li * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(dO + off);
+    const uint4 c = *reinterpret_cast<const uint4*>(o + off);
+    const T* ah = reinterpret_cast<const T*>(&a);
+    const T* ch = reinterpret_cast<const T*>(&c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc = fmaf(to_f32<T>(ah[e]), to_f32<T>(ch[e]), acc);
+    float4* zp = reinterpret_cast<float4*>(dq_accum + off);
+    zp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    zp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int sft = 1; sft < LPR; sft <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+  if (li == 0) {
+    const int64_t pr = static_cast<int64_t>(h) * QLp + packed_stat_row(q_off, z) + r;
+    deltap[pr] = r < QL ? acc : 0.f;
+    lse2p[pr] = r < QL ? lse[static_cast<int64_t>(h) * total_q + q_off + r] * kLog2e : INFINITY;
+  }
+}
+
 // post: dQ = T(scale * dQ_accum), 8 elements per thread
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -511,11 +589,20 @@ attn_bwd_post_kernel(T* __restrict__ dq, const float* __restrict__ dq_accum, int
 
 inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
+// rows of the padded per-row statistics: dense (QL rounded up to 128) or packed (every sequence
+// padded to whole 128-row blocks: at most total_q / 128 + nseq blocks)
+inline int64_t stat_rows(int QL, int64_t total_q, int nseq, bool packed) {
+  return packed ? (total_q / 128 + nseq) * 128 : static_cast<int64_t>((QL + 127) / 128) * 128;
+}
+
 template <typename T, int D>
 int launch_bwd(const AttnParams& a) {
   using S = BwdSmem<D>;
-  const int QLp = ((a.QL + 127) / 128) * 128;
-  const int64_t BH = static_cast<int64_t>(a.B) * a.QH;
+  const bool packed = a.cu_q != nullptr;
+  const int64_t QLp = stat_rows(a.QL, a.total_q, a.nseq, packed);
+  const int64_t BH = packed ? a.QH : static_cast<int64_t>(a.B) * a.QH;
+  const int64_t rows_q = packed ? a.total_q : a.QL;
+  const int64_t rows_k = packed ? a.total_k : a.KL;
   // workspace carve-up (a.delta is the workspace base)
   char* ws = reinterpret_cast<char*>(a.delta);
   const size_t stat_bytes = align256(static_cast<size_t>(BH) * QLp * sizeof(float));
@@ -523,36 +610,46 @@ int launch_bwd(const AttnParams& a) {
   float* lse2p = reinterpret_cast<float*>(ws + stat_bytes);
   float* dqa = reinterpret_cast<float*>(ws + 2 * stat_bytes);
 
-  {
+  if (packed) {
+    constexpr int kRows = 256 / (D / 8);
+    dim3 pg((((a.QL + 127) & ~127) + kRows - 1) / kRows, a.QH, a.nseq);
+    attn_bwd_prep_packed_kernel<T, D><<<pg, 256, 0, a.stream>>>(
+        deltap, lse2p, dqa, static_cast<const T*>(a.dO), static_cast<const T*>(a.o), a.lse, a.cu_q,
+        a.total_q, QLp);
+    NNOP_LAUNCH_CHECK();
+  } else {
     const int64_t n_rows_p = BH * QLp;
     const int64_t threads = n_rows_p * (D / 8);
     attn_bwd_prep_kernel<T, D><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, a.stream>>>(
         deltap, lse2p, dqa, static_cast<const T*>(a.dO), static_cast<const T*>(a.o), a.lse, a.QL,
-        QLp, n_rows_p);
+        static_cast<int>(QLp), n_rows_p);
     NNOP_LAUNCH_CHECK();
   }
   alignas(64) CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdqa;
-  const uint64_t bhq = static_cast<uint64_t>(BH), bhk = static_cast<uint64_t>(a.B) * a.KH;
-  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, D, a.QL, bhq, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tdo, a.dO, a.dtype, D, a.QL, bhq, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tdk, a.dk, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tdv, a.dv, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tdqa, dqa, NNOP_F32, D, a.QL, bhq, 32, 128)) return rc;
+  const uint64_t bhq = static_cast<uint64_t>(BH);
+  const uint64_t bhk = packed ? a.KH : static_cast<uint64_t>(a.B) * a.KH;
+  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdo, a.dO, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdk, a.dk, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdv, a.dv, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdqa, dqa, NNOP_F32, D, rows_q, bhq, 32, 128)) return rc;
   auto kern = attn_bwd_sm100_kernel<T, D>;
   NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   BwdParams bp;
   bp.lse2p = lse2p; bp.deltap = deltap;
-  bp.QL = a.QL; bp.KL = a.KL; bp.QH = a.QH; bp.KH = a.KH; bp.QLp = QLp; bp.causal = a.causal;
+  bp.QL = a.QL; bp.KL = a.KL; bp.QH = a.QH; bp.KH = a.KH; bp.QLp = static_cast<int>(QLp);
+  bp.causal = a.causal;
   bp.scale = a.scale; bp.scale_log2 = a.scale * kLog2e;
-  dim3 grid((a.KL + 127) / 128, a.KH, a.B);
+  bp.cu_q = a.cu_q; bp.cu_k = a.cu_k; bp.dk_ptr = a.dk; bp.dv_ptr = a.dv; bp.total_k = a.total_k;
+  dim3 grid((a.KL + 127) / 128, a.KH, packed ? a.nseq : a.B);
   timing_begin(1, a.stream);
   kern<<<grid, kBwdThreads, S::kTotal, a.stream>>>(tq, tk, tv, tdo, tdk, tdv, tdqa, bp);
   timing_end(1, a.stream);
   NNOP_LAUNCH_CHECK();
   {
-    const int64_t n8 = BH * a.QL * D / 8;
+    const int64_t n8 = BH * rows_q * D / 8;
     attn_bwd_post_kernel<T><<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, a.stream>>>(
         static_cast<T*>(a.dq), dqa, n8, a.scale);
     NNOP_LAUNCH_CHECK();
@@ -574,6 +671,12 @@ size_t attn_sm100_bwd_workspace_bytes(int E, int QL, int QH, int B) {
   const size_t QLp = static_cast<size_t>((QL + 127) / 128) * 128;
   const size_t BH = static_cast<size_t>(B) * QH;
   return 2 * align256(BH * QLp * sizeof(float)) + BH * static_cast<size_t>(QL) * E * sizeof(float);
+}
+
+size_t attn_sm100_bwd_packed_workspace_bytes(int E, int64_t total_q, int nseq, int QH) {
+  const size_t QLp = static_cast<size_t>(stat_rows(0, total_q, nseq, true));
+  return 2 * align256(static_cast<size_t>(QH) * QLp * sizeof(float)) +
+         static_cast<size_t>(QH) * static_cast<size_t>(total_q) * E * sizeof(float);
 }
 
 int attn_sm100_bwd(const AttnParams& a) {

@@ -54,8 +54,14 @@ __device__ long long g_fwd_trace[256 * 16];
 
 struct FwdParams {
   float* lse;
-  int QL, KL, QH, KH, causal;
+  int QL, KL, QH, KH, causal;  // packed (varlen) mode: QL / KL are the maximum sequence lengths
   float scale_log2;
+  // packed variable-length mode (cu_q != nullptr): sequence z = blockIdx.z owns rows
+  // [cu_q[z], cu_q[z+1]) of the (QH, total_q, E) tensors and keys [cu_k[z], cu_k[z+1])
+  const int* cu_q;
+  const int* cu_k;
+  void* o_ptr;       // raw output pointer for partial tiles (a TMA store would spill into the next sequence)
+  int64_t total_q;
 };
 
 template <int D>
@@ -102,12 +108,22 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   // ---- work assignment ----------------------------------------------------------------
   const int qt = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heaviest first
   const int q0 = qt * 256;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.y;
+  const bool packed = p.cu_q != nullptr;
+  int QL = p.QL, KL = p.KL, q_off = 0, k_off = 0, b = blockIdx.z;
+  if (packed) {
+    q_off = p.cu_q[blockIdx.z];
+    QL = p.cu_q[blockIdx.z + 1] - q_off;
+    k_off = p.cu_k[blockIdx.z];
+    KL = p.cu_k[blockIdx.z + 1] - k_off;
+    b = 0;
+    if (q0 >= QL) return;  // the grid is sized for the longest sequence (whole CTA exits together)
+  }
   const int bh_q = b * p.QH + h;
   const int bh_kv = b * p.KH + h / (p.QH / p.KH);
-  const bool act1 = q0 + 128 < p.QL;
-  const int nb0 = ((p.causal ? min(p.KL, q0 + 128) : p.KL) + 127) >> 7;
-  const int nb1 = act1 ? (((p.causal ? min(p.KL, q0 + 256) : p.KL) + 127) >> 7) : 0;
+  const bool act1 = q0 + 128 < QL;
+  const int nb0 = ((p.causal ? min(KL, q0 + 128) : KL) + 127) >> 7;
+  const int nb1 = act1 ? (((p.causal ? min(KL, q0 + 256) : KL) + 127) >> 7) : 0;
   const int nblk = act1 ? nb1 : nb0;
 
   // ---- one-time setup -----------------------------------------------------------------
@@ -139,12 +155,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
 
   if (warp < 4) {
     setmaxnreg_dec<80>();  // 128*80 + 256*208 = 63488 <= 64K registers
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && lane == 0 && nblk > 0) {
       // ================================ TMA producer =================================
       mbar_arrive_expect_tx(&q_full[0], S::kTileBytes);
 #pragma unroll
       for (int bx = 0; bx < S::kNBox; ++bx)
-        tma_load_3d(sQ + bx * S::kBoxBytes, &tm_q, &q_full[0], bx * 64, q0, bh_q);
+        tma_load_3d(sQ + bx * S::kBoxBytes, &tm_q, &q_full[0], bx * 64, q_off + q0, bh_q);
       int n = 0;
       auto load_kv = [&](const CUtensorMap* tm, int blk) {
         const int st = n % kNStage;
@@ -154,7 +170,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
 #pragma unroll
         for (int bx = 0; bx < S::kNBox; ++bx)
           tma_load_3d(sKV + st * S::kTileBytes + bx * S::kBoxBytes, tm, &kv_full[st], bx * 64,
-                      blk * 128, bh_kv);
+                      k_off + blk * 128, bh_kv);
         ++n;
       };
       load_kv(&tm_k, 0);
@@ -162,15 +178,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         mbar_arrive_expect_tx(&q_full[1], S::kTileBytes);
 #pragma unroll
         for (int bx = 0; bx < S::kNBox; ++bx)
-          tma_load_3d(sQ + S::kTileBytes + bx * S::kBoxBytes, &tm_q, &q_full[1], bx * 64, q0 + 128,
-                      bh_q);
+          tma_load_3d(sQ + S::kTileBytes + bx * S::kBoxBytes, &tm_q, &q_full[1], bx * 64,
+                      q_off + q0 + 128, bh_q);
       }
       load_kv(&tm_v, 0);
       for (int i = 1; i < nblk; ++i) {
         load_kv(&tm_k, i);
         load_kv(&tm_v, i);
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 && nblk > 0) {
       // ================================ MMA issuer ===================================
       // The whole warp runs the (uniform) control flow and the barrier waits; one elected lane
       // issues tcgen05.mma / commit.  Keeping every operand warp-uniform lets descriptors live in
@@ -317,9 +333,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         }
 
         const int k0 = i * 128;
-        const bool need_mask = (k0 + 128 > p.KL) || (p.causal && (k0 + 127 > q0 + t * 128));
+        const bool need_mask = (k0 + 128 > KL) || (p.causal && (k0 + 127 > q0 + t * 128));
         if (need_mask) {
-          const int lim = p.causal ? min(p.KL - 1, q_row) : (p.KL - 1);  // last visible key
+          const int lim = p.causal ? min(KL - 1, q_row) : (KL - 1);  // last visible key
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -428,17 +444,48 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           *reinterpret_cast<uint4*>(stage + bx * S::kBoxBytes + row * 128 + ((cin ^ (row & 7)) << 4)) = v;
         }
       }
-      if (q_row < p.QL)
-        p.lse[static_cast<int64_t>(bh_q) * p.QL + q_row] =
-            l > 0.f ? (m_used + fast_log2(l)) * kLn2 : -INFINITY;
-      fence_proxy_async_smem();
-      named_bar_sync(1 + t, 128);
-      if (wq == 0 && lane == 0) {
+      if (q_row < QL) {
+        const int64_t li = packed ? static_cast<int64_t>(h) * p.total_q + q_off + q_row
+                                  : static_cast<int64_t>(bh_q) * QL + q_row;
+        p.lse[li] = l > 0.f ? (m_used + fast_log2(l)) * kLn2 : -INFINITY;
+      }
+      const int rows_left = QL - (q0 + t * 128);  // > 0 here
+      if (packed && rows_left < 128) {
+        // last, partial tile of a packed sequence: rows past its end belong to the next sequence,
+        // so copy the valid rows out of the staging buffer with coalesced 16-byte stores
+        named_bar_sync(1 + t, 128);
+        constexpr int kCPR = D / 8;  // 16-byte chunks per row
+        T* obase = static_cast<T*>(p.o_ptr) +
+                   (static_cast<int64_t>(h) * p.total_q + q_off + q0 + t * 128) * D;
+        const int tid = wq * 32 + lane;
+        for (int idx = tid; idx < rows_left * kCPR; idx += 128) {
+          const int r = idx / kCPR, chunk = idx % kCPR;
+          const int bx = chunk >> 3, cin = chunk & 7;
+          const uint4 v = *reinterpret_cast<const uint4*>(stage + bx * S::kBoxBytes + r * 128 +
+                                                          ((cin ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(r) * D + chunk * 8) = v;
+        }
+      } else {
+        fence_proxy_async_smem();
+        named_bar_sync(1 + t, 128);
+        if (wq == 0 && lane == 0) {
 #pragma unroll
-        for (int bx = 0; bx < S::kNBox; ++bx)
-          tma_store_3d(&tm_o, stage + bx * S::kBoxBytes, bx * 64, q0 + t * 128, bh_q);
-        bulk_commit();
-        bulk_wait_read<0>();
+          for (int bx = 0; bx < S::kNBox; ++bx)
+            tma_store_3d(&tm_o, stage + bx * S::kBoxBytes, bx * 64, q_off + q0 + t * 128, bh_q);
+          bulk_commit();
+          bulk_wait_read<0>();
+        }
+      }
+    } else if (t == 0 || act1) {
+      // no visible keys at all (KL == 0): the output rows are 0 and lse = -inf
+      const int q_row = q0 + t * 128 + (warp & 3) * 32 + lane;
+      if (q_row < QL) {
+        const int64_t ri = packed ? static_cast<int64_t>(h) * p.total_q + q_off + q_row
+                                  : static_cast<int64_t>(bh_q) * QL + q_row;
+        uint4* orow = reinterpret_cast<uint4*>(static_cast<T*>(p.o_ptr) + ri * D);
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) orow[c] = make_uint4(0u, 0u, 0u, 0u);
+        p.lse[ri] = -INFINITY;
       }
     }
   }
@@ -456,18 +503,24 @@ template <typename T, int D>
 int launch_fwd(const AttnParams& a) {
   using S = FwdSmem<D>;
   alignas(64) CUtensorMap tq, tk, tv, to;
-  const uint64_t bhq = static_cast<uint64_t>(a.B) * a.QH, bhk = static_cast<uint64_t>(a.B) * a.KH;
-  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, D, a.QL, bhq, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&to, a.o, a.dtype, D, a.QL, bhq, 64, 128)) return rc;
+  const bool packed = a.cu_q != nullptr;
+  // packed mode: the tensors are (QH, total_q, E) / (KH, total_k, E); a.QL / a.KL hold the maxima
+  const uint64_t bhq = packed ? a.QH : static_cast<uint64_t>(a.B) * a.QH;
+  const uint64_t bhk = packed ? a.KH : static_cast<uint64_t>(a.B) * a.KH;
+  const uint64_t rows_q = packed ? static_cast<uint64_t>(a.total_q) : a.QL;
+  const uint64_t rows_k = packed ? static_cast<uint64_t>(a.total_k) : a.KL;
+  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&to, a.o, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
   auto kern = attn_fwd_sm100_kernel<T, D>;
   NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynBytes));
   FwdParams fp;
   fp.lse = a.lse;
   fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
   fp.scale_log2 = a.scale * kLog2e;
-  dim3 grid((a.QL + 255) / 256, a.QH, a.B);
+  fp.cu_q = a.cu_q; fp.cu_k = a.cu_k; fp.o_ptr = a.o; fp.total_q = a.total_q;
+  dim3 grid((a.QL + 255) / 256, a.QH, packed ? a.nseq : a.B);
   timing_begin(0, a.stream);
   kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, fp);
   timing_end(0, a.stream);
@@ -489,7 +542,7 @@ bool attn_sm100_supported(const AttnParams& a, bool backward) {
   if (a.E != 64 && a.E != 128) return false;
   if (a.pair || a.kpad) return false;
   if (a.QL < 1 || a.KL < 1) return false;
-  if (a.QH > 65535 || a.B > 65535) return false;
+  if (a.QH > 65535 || a.B > 65535 || a.nseq > 65535) return false;
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.o)) return false;
   if (backward && (!al(a.dq) || !al(a.dk) || !al(a.dv) || !al(a.dO))) return false;

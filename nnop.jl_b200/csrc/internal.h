@@ -60,6 +60,12 @@ struct AttnParams {
   int dtype, E, QL, KL, QH, KH, B, causal;
   float scale;
   cudaStream_t stream;
+  // packed variable-length mode (tcgen05 path only): cu_q / cu_k are device arrays of nseq+1
+  // int32 row offsets into (QH, total_q, E) / (KH, total_k, E) tensors; QL / KL = max lengths
+  const int* cu_q;
+  const int* cu_k;
+  int nseq;
+  int64_t total_q, total_k;
 };
 
 // one-shot timing hook (api.cu); which: 0 forward kernel, 1 backward main kernel
@@ -78,6 +84,7 @@ int attn_sm100_fwd(const AttnParams& p);
 int attn_sm100_bwd(const AttnParams& p);
 bool attn_sm100_bwd_available();
 size_t attn_sm100_bwd_workspace_bytes(int E, int QL, int QH, int B);
+size_t attn_sm100_bwd_packed_workspace_bytes(int E, int64_t total_q, int nseq, int QH);
 
 // TMA descriptor helper (api.cu): 3-D map over a row-major (outer, rows, inner) tensor of
 // nnop_dtype_t elements, box (box_inner, box_rows, 1), 128-byte swizzle, zero OOB fill.

@@ -9,6 +9,7 @@ array is passed as the row-major tensor `(B, H, L, E)` holding the same bytes.
 from ._lib import NNopError, LIB_PATH, lib  # noqa: F401
 from .ops import (  # noqa: F401
     flash_attention, _flash_attention, grad_flash_attention,
+    flash_attention_varlen, _flash_attention_varlen, grad_flash_attention_varlen,
     online_softmax, grad_online_softmax,
     rms_norm, _rms_norm, grad_rms_norm,
     layer_norm, _layer_norm, grad_layer_norm,
@@ -24,7 +25,8 @@ __all__ = [
     "_layer_norm", "grad_layer_norm", "llama_rope", "grad_llama_rope", "LlamaRotaryEmbedding",
     "device_info", "set_attention_path", "last_attention_path", "selftest_umma",
     "shard_slices", "shard_attention_inputs", "NNopError", "set_timing_events",
-    "HostAttentionPipeline",
+    "HostAttentionPipeline", "flash_attention_varlen", "_flash_attention_varlen",
+    "grad_flash_attention_varlen",
 ]
 # the reference spells its pullbacks with a nabla; reachable via getattr(nnop_b200, "∇flash_attention")
 globals().update({

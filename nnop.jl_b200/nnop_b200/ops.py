@@ -155,6 +155,85 @@ def flash_attention(q, k, v, pair=None, *, causal: bool, kpad_mask=None):
 
 
 # ------------------------------------------------------------------------------------------
+# packed variable-length flash attention (additive API)
+# ------------------------------------------------------------------------------------------
+def _varlen_dims(q, k, v, cu_q, cu_k):
+    if q.dim() != 3 or k.dim() != 3 or v.dim() != 3:
+        raise NNopError(1, "packed q, k, v must be 3-dimensional (E, L_total, H) arrays")
+    QH, TQ, E = q.shape
+    KH, TK, KE = k.shape
+    if E != KE:
+        raise NNopError(1, f"Embedding dim of Q `{E}` must be the same as of K `{KE}`.")
+    if tuple(k.shape) != tuple(v.shape):
+        raise NNopError(1, f"Shapes of K `{tuple(k.shape)}` and V `{tuple(v.shape)}` must be the same.")
+    if k.dtype != q.dtype or v.dtype != q.dtype:
+        raise NNopError(2, "q, k, v must share one element type")
+    for c in (cu_q, cu_k):
+        if c.dtype != torch.int32 or c.dim() != 1:
+            raise NNopError(1, "cu_seqlens must be Int32 vectors of nseq+1 row offsets")
+    if cu_q.numel() != cu_k.numel():
+        raise NNopError(1, "cu_seqlens_q and cu_seqlens_k must describe the same number of sequences")
+    return QH, TQ, E, KH, TK, cu_q.numel() - 1
+
+
+def _flash_attention_varlen(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q: int,
+                            max_seqlen_k: int, *, causal: bool):
+    """Packed `_flash_attention`: q (QH, total_q, E), k/v (KH, total_k, E) [Julia (E, total, H)],
+    cu_seqlens Int32 device vectors.  Returns ``(o, lse)`` with lse (QH, total_q)."""
+    _req(q, k, v, cu_seqlens_q, cu_seqlens_k)
+    QH, TQ, E, KH, TK, nseq = _varlen_dims(q, k, v, cu_seqlens_q, cu_seqlens_k)
+    o = torch.empty_like(q)
+    lse = torch.empty((QH, TQ), dtype=torch.float32, device=q.device)
+    check(lib.nnop_flash_attn_varlen_fwd(_p(o), _p(lse), _p(q), _p(k), _p(v), _p(cu_seqlens_q),
+                                         _p(cu_seqlens_k), nseq, int(max_seqlen_q), int(max_seqlen_k),
+                                         TQ, TK, _dt(q), E, QH, KH, int(bool(causal)),
+                                         1.0 / math.sqrt(E), _stream()))
+    return o, lse
+
+
+def grad_flash_attention_varlen(dO, o, lse, q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q: int,
+                                max_seqlen_k: int, *, causal: bool):
+    """Packed `∇flash_attention`.  Returns ``(dq, dk, dv)``."""
+    _req(dO, o, lse, q, k, v, cu_seqlens_q, cu_seqlens_k)
+    QH, TQ, E, KH, TK, nseq = _varlen_dims(q, k, v, cu_seqlens_q, cu_seqlens_k)
+    if tuple(dO.shape) != tuple(q.shape) or dO.dtype != q.dtype:
+        raise NNopError(1, "Δ must have the shape and element type of q")
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ws_bytes = lib.nnop_flash_attn_varlen_bwd_workspace_bytes(_dt(q), E, nseq, TQ, QH)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=q.device)
+    check(lib.nnop_flash_attn_varlen_bwd(_p(dq), _p(dk), _p(dv), _p(dO), _p(o), _p(lse), _p(q), _p(k),
+                                         _p(v), _p(cu_seqlens_q), _p(cu_seqlens_k), nseq,
+                                         int(max_seqlen_q), int(max_seqlen_k), TQ, TK, _dt(q), E, QH,
+                                         KH, int(bool(causal)), 1.0 / math.sqrt(E), _p(ws), ws_bytes,
+                                         _stream()))
+    return dq, dk, dv
+
+
+class _FlashAttentionVarlenFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, cu_q, cu_k, max_q, max_k, causal):
+        o, lse = _flash_attention_varlen(q, k, v, cu_q, cu_k, max_q, max_k, causal=causal)
+        ctx.save_for_backward(o, lse, q, k, v, cu_q, cu_k)
+        ctx.meta = (max_q, max_k, causal)
+        return o
+
+    @staticmethod
+    def backward(ctx, dO):
+        o, lse, q, k, v, cu_q, cu_k = ctx.saved_tensors
+        max_q, max_k, causal = ctx.meta
+        dq, dk, dv = grad_flash_attention_varlen(dO.contiguous(), o, lse, q, k, v, cu_q, cu_k, max_q,
+                                                 max_k, causal=causal)
+        return dq, dk, dv, None, None, None, None, None
+
+
+def flash_attention_varlen(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q: int, max_seqlen_k: int,
+                           *, causal: bool):
+    """`flash_attention` over a packed batch of variable-length sequences (differentiable)."""
+    return _FlashAttentionVarlenFn.apply(q, k, v, cu_seqlens_q, cu_seqlens_k, int(max_seqlen_q),
+                                         int(max_seqlen_k), bool(causal))
+
+
+# ------------------------------------------------------------------------------------------
 # online softmax
 # ------------------------------------------------------------------------------------------
 def _softmax_fwd(x):

@@ -1,0 +1,159 @@
+"""Packed variable-length flash attention (additive API, SURVEY.md 8 f1 / BASELINE config 4) through
+the C ABI vs the oracle applied sequence by sequence.  Tolerance: BASELINE.json's 2e-2 max-abs for
+BF16/FP16 on O, dQ, dK, dV (scaled by magnitude above 2, as in test_attention_gpu.py)."""
+import math
+
+import pytest
+import torch
+
+from helpers import max_abs
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _packed(lens_q, lens_k, QH, KH, E, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    TQ, TK = sum(lens_q), sum(lens_k)
+    q = torch.randn(QH, TQ, E, generator=g).to(dtype)
+    k = torch.randn(KH, TK, E, generator=g).to(dtype)
+    v = torch.randn(KH, TK, E, generator=g).to(dtype)
+    dO = torch.randn(QH, TQ, E, generator=g).to(dtype)
+    cu = lambda ls: torch.tensor([0] + list(torch.tensor(ls).cumsum(0)), dtype=torch.int32)
+    return q, k, v, dO, cu(lens_q), cu(lens_k)
+
+
+def _oracle(q, k, v, dO, cu_q, cu_k, causal):
+    """Per-sequence naive attention fwd + bwd (fp64), re-packed."""
+    o = torch.zeros_like(q, dtype=torch.float64)
+    lse = torch.zeros(q.shape[0], q.shape[1], dtype=torch.float64)
+    dq = torch.zeros_like(q, dtype=torch.float64)
+    dk = torch.zeros_like(k, dtype=torch.float64)
+    dv = torch.zeros_like(v, dtype=torch.float64)
+    for z in range(cu_q.numel() - 1):
+        a, b = int(cu_q[z]), int(cu_q[z + 1])
+        c, d = int(cu_k[z]), int(cu_k[z + 1])
+        if b == a:
+            continue
+        if d == c:
+            lse[:, a:b] = -math.inf
+            continue
+        qs, ks, vs, ds = (t.double()[None] for t in (q[:, a:b], k[:, c:d], v[:, c:d], dO[:, a:b]))
+        oz, lz = O.naive_attention(qs, ks, vs, causal=causal, return_lse=True)
+        gq, gk, gv, _ = O.naive_attention_bwd(ds, qs, ks, vs, causal=causal)
+        o[:, a:b], lse[:, a:b] = oz[0], lz[0]
+        dq[:, a:b], dk[:, c:d], dv[:, c:d] = gq[0], gk[0], gv[0]
+    return o, lse, dq, dk, dv
+
+
+def _check(nnop, lens_q, lens_k, QH, KH, E, dtype, causal, seed=0):
+    q, k, v, dO, cu_q, cu_k = _packed(lens_q, lens_k, QH, KH, E, dtype, seed)
+    dev = lambda t: t.cuda()
+    mq, mk = max(lens_q), max(lens_k)
+    o, lse = nnop._flash_attention_varlen(dev(q), dev(k), dev(v), dev(cu_q), dev(cu_k), mq, mk, causal=causal)
+    assert nnop.last_attention_path() == 1
+    dq, dk, dv = nnop.grad_flash_attention_varlen(dev(dO), o, lse, dev(q), dev(k), dev(v), dev(cu_q),
+                                                  dev(cu_k), mq, mk, causal=causal)
+    ro, rl, rq, rk, rv = _oracle(q, k, v, dO, cu_q, cu_k, causal)
+    mag = lambda r: max(1.0, r.abs().max().item() / 2)
+    assert max_abs(o, ro) < TOL, "o"
+    fin = torch.isfinite(rl)
+    assert torch.equal(torch.isfinite(lse.cpu()), fin), "lse finiteness"
+    assert max_abs(lse.cpu()[fin], rl[fin]) < 1e-3, "lse"
+    assert max_abs(dq, rq) < TOL * mag(rq), "dq"
+    assert max_abs(dk, rk) < TOL * mag(rk), "dk"
+    assert max_abs(dv, rv) < TOL * mag(rv), "dv"
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("E", [64, 128])
+def test_varlen_ragged(nnop, E, dtype, causal):
+    # lengths straddling the 128 / 256 tile edges, a 1-token sequence and the reference's ragged Ls
+    lens = [255, 1, 128, 513, 256, 129, 64, 511]
+    _check(nnop, lens, lens, 4, 4, E, dtype, causal)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_varlen_gqa(nnop, causal):
+    lens = [300, 77, 1024, 5]
+    _check(nnop, lens, lens, 8, 2, 128, torch.bfloat16, causal)
+
+
+def test_varlen_cross_lengths(nnop):
+    # non-causal with different query / key lengths per sequence (test/attention_tests.jl:14-18 QL != KL)
+    _check(nnop, [100, 257, 31], [513, 64, 200], 2, 2, 128, torch.bfloat16, False)
+
+
+def test_varlen_empty_sequences(nnop):
+    # zero-length sequences in the middle and at the end; a sequence with queries but no keys
+    _check(nnop, [130, 0, 64, 0], [130, 0, 64, 0], 2, 1, 64, torch.bfloat16, True)
+    _check(nnop, [40, 200], [0, 200], 2, 2, 128, torch.bfloat16, False)
+
+
+def test_varlen_matches_dense(nnop):
+    """A packed batch of equal-length sequences must reproduce the dense kernel bit for bit."""
+    B, H, L, E = 3, 4, 384, 128
+    g = torch.Generator().manual_seed(3)
+    q, k, v, dO = (torch.randn(B, H, L, E, generator=g).to(torch.bfloat16).cuda() for _ in range(4))
+    o, lse = nnop._flash_attention(q, k, v, causal=True)
+    dq, dk, dv, _ = nnop.grad_flash_attention(dO, o, lse, q, k, v, causal=True)
+    pk = lambda t: t.permute(1, 0, 2, 3).reshape(H, B * L, E).contiguous()
+    cu = torch.arange(0, (B + 1) * L, L, dtype=torch.int32).cuda()
+    o2, lse2 = nnop._flash_attention_varlen(pk(q), pk(k), pk(v), cu, cu, L, L, causal=True)
+    d2 = nnop.grad_flash_attention_varlen(pk(dO), o2, lse2, pk(q), pk(k), pk(v), cu, cu, L, L, causal=True)
+    assert torch.equal(o2, pk(o))
+    assert torch.equal(lse2, lse.permute(1, 0, 2).reshape(H, B * L))
+    # dQ goes through fp32 atomics whose order is not fixed: equal up to rounding of the last bit
+    for a, b in zip(d2, (dq, dk, dv)):
+        assert max_abs(a, pk(b)) <= 2 ** -7 * max(1.0, b.abs().max().item())
+
+
+def test_varlen_config4_shape_properties(nnop):
+    """BASELINE config 4 shape: 64 sequences, L log-uniform in [128, 16384], H=32, E=128, bf16
+    causal.  Size-independent checks: causal row 0 of every sequence = v[0]; constant V => constant O;
+    sum_k dV = sum_q dO per sequence and head."""
+    g = torch.Generator().manual_seed(0)
+    lens = torch.exp(torch.empty(64).uniform_(math.log(128), math.log(16384), generator=g)).round().int().tolist()
+    H, E = 32, 128
+    T = sum(lens)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).cuda()
+    q = torch.randn(H, T, E, generator=g).to(torch.bfloat16).cuda()
+    k = torch.randn(H, T, E, generator=g).to(torch.bfloat16).cuda()
+    v = torch.randn(H, T, E, generator=g).to(torch.bfloat16).cuda()
+    o, lse = nnop._flash_attention_varlen(q, k, v, cu, cu, max(lens), max(lens), causal=True)
+    starts = cu[:-1].long()
+    assert torch.equal(o[:, starts], v[:, starts])          # first row sees only its own key
+    qk0 = (q[:, starts].float() * k[:, starts].float()).sum(-1) / math.sqrt(E)
+    assert (lse[:, starts] - qk0).abs().max().item() < 1e-3     # one visible key: lse = q.k/sqrt(E)
+    vc = torch.full_like(v, 0.5)
+    oc, _ = nnop._flash_attention_varlen(q, k, vc, cu, cu, max(lens), max(lens), causal=True)
+    assert (oc.float() - 0.5).abs().max().item() < 4e-3
+    dO = torch.randn(H, T, E, generator=g).to(torch.bfloat16).cuda()
+    dq, dk, dv = nnop.grad_flash_attention_varlen(dO, o, lse, q, k, v, cu, cu, max(lens), max(lens), causal=True)
+    for z in (0, 17, 63):
+        a, b = int(cu[z]), int(cu[z + 1])
+        s_dv = dv[:, a:b].float().sum(1)
+        s_do = dO[:, a:b].float().sum(1)
+        assert (s_dv - s_do).abs().max().item() < 2e-2 * max(1.0, s_do.abs().max().item())
+    # one short sequence against the oracle
+    z = min(range(64), key=lambda i: lens[i])
+    a, b = int(cu[z]), int(cu[z + 1])
+    qs, ks, vs, ds = (t[:2, a:b].double().cpu()[None] for t in (q, k, v, dO))
+    ro = O.naive_attention(qs, ks, vs, causal=True)
+    rq, rk, rv, _ = O.naive_attention_bwd(ds, qs, ks, vs, causal=True)
+    assert max_abs(o[:2, a:b], ro[0]) < TOL
+    assert max_abs(dq[:2, a:b], rq[0]) < TOL * max(1.0, rq.abs().max().item() / 2)
+    assert max_abs(dk[:2, a:b], rk[0]) < TOL * max(1.0, rk.abs().max().item() / 2)
+    assert max_abs(dv[:2, a:b], rv[0]) < TOL * max(1.0, rv.abs().max().item() / 2)
+
+
+def test_varlen_errors(nnop):
+    q = torch.randn(2, 64, 128, device="cuda")
+    cu = torch.tensor([0, 64], dtype=torch.int32, device="cuda")
+    with pytest.raises(nnop.NNopError, match="Float16 / BFloat16"):
+        nnop._flash_attention_varlen(q, q, q, cu, cu, 64, 64, causal=False)
+    qh = torch.randn(2, 64, 32, device="cuda").bfloat16()
+    with pytest.raises(nnop.NNopError, match="64 and 128"):
+        nnop._flash_attention_varlen(qh, qh, qh, cu, cu, 64, 64, causal=False)
