@@ -126,6 +126,24 @@ int nnop_flash_attn_varlen_bwd(void* dq, void* dk, void* dv, const void* dO, con
                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Helpers of the sequence-sharded ("ring") attention variant (additive: the reference has no
+ * multi-GPU path).  A rank attends its local queries to one K/V block per ring step with
+ * nnop_flash_attn_fwd and folds the partial result into fp32 accumulators:
+ *   nnop_attn_merge: (o_acc, lse_acc) <- logsumexp-weighted combination with (o_part, lse_part);
+ *     o_acc (E, rows) float in/out, lse_acc (rows) float in, lse_out (rows) float out (must not
+ *     alias lse_acc unless init), o_part (E, rows) T, lse_part (rows) float; init != 0 copies.
+ *   nnop_accumulate_f32: acc[n] (+)= float(part[n])  (dq over steps; travelling dk / dv); n % 8 == 0.
+ *   nnop_store_rows_from_f32: out[:, offset : offset+rows, slab] = T(acc[:, :, slab]) for
+ *     acc (E, rows, n_slabs) float and out (E, out_slab_rows, n_slabs) T.
+ */
+int nnop_attn_merge(float* o_acc, float* lse_acc, float* lse_out, const void* o_part,
+                    const float* lse_part, int dtype, int E, int64_t rows, int init, void* stream);
+int nnop_accumulate_f32(float* acc, const void* part, int dtype, int64_t n, int init, void* stream);
+int nnop_store_rows_from_f32(void* out, const float* acc, int dtype, int E, int64_t n_slabs,
+                             int64_t rows, int64_t out_slab_rows, int64_t out_row_offset,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * online softmax over dim 1 of x (N, cols).  Replaces `online_softmax` / `online_softmax!`
  * (src/softmax.jl:60-68, :19-58) and `∇online_softmax` (src/softmax.jl:70-80).
  */

@@ -101,6 +101,68 @@ function CRC.rrule(::typeof(_flash_attention), q, k, v, pair::Maybe{AbstractArra
     return o, _pullback
 end
 
+# ------------------------------------------------------------------ packed variable-length attention
+# Additive API (the reference only has the dense `kpad_mask`, src/attention.jl:73-79): sequences are
+# concatenated along L, q (E, total_q, QH), k/v (E, total_k, KH), cu_seqlens :: CuVector{Int32} of
+# nseq+1 row offsets (0-based, cu[1] == 0, cu[end] == total).  Float16 / BFloat16, E in (64, 128).
+function _flash_attention_varlen(
+    q::CuArray{T,3}, k::CuArray{T,3}, v::CuArray{T,3},
+    cu_seqlens_q::CuVector{Int32}, cu_seqlens_k::CuVector{Int32},
+    max_seqlen_q::Integer, max_seqlen_k::Integer; causal::Bool,
+) where T <: Union{Float16, CUDA.BFloat16}
+    E, TQ, QH = size(q)
+    KE, TK, KH = size(k)
+    E == KE || error("Embedding dim of Q `$E` must be the same as of K `$KE`.")
+    size(k) == size(v) || error("Shapes of K `$(size(k))` and V `$(size(v))` must be the same.")
+    nseq = length(cu_seqlens_q) - 1
+    o = similar(q)
+    lse = CUDA.zeros(Float32, TQ, QH)
+    check(ccall((:nnop_flash_attn_varlen_fwd, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
+         Cint, Cint, Cint, Int64, Int64, Cint, Cint, Cint, Cint, Cint, Cfloat, Ptr{Cvoid}),
+        ptr(o), ptr(lse), ptr(q), ptr(k), ptr(v), ptr(cu_seqlens_q), ptr(cu_seqlens_k),
+        nseq, max_seqlen_q, max_seqlen_k, TQ, TK, dtype_code(T), E, QH, KH, causal,
+        Float32(inv(sqrt(E))), stream()))
+    return o, lse
+end
+
+function ∇flash_attention_varlen(
+    Δ::CuArray{T,3}, o::CuArray{T,3}, lse, q::CuArray{T,3}, k::CuArray{T,3}, v::CuArray{T,3},
+    cu_seqlens_q::CuVector{Int32}, cu_seqlens_k::CuVector{Int32},
+    max_seqlen_q::Integer, max_seqlen_k::Integer; causal::Bool,
+) where T <: Union{Float16, CUDA.BFloat16}
+    E, TQ, QH = size(q)
+    _, TK, KH = size(k)
+    nseq = length(cu_seqlens_q) - 1
+    dq, dk, dv = similar(q), similar(k), similar(v)
+    nbytes = ccall((:nnop_flash_attn_varlen_bwd_workspace_bytes, libnnop_b200), Csize_t,
+        (Cint, Cint, Cint, Int64, Cint), dtype_code(T), E, nseq, TQ, QH)
+    ws = CuArray{UInt8}(undef, max(nbytes, 1))
+    check(ccall((:nnop_flash_attn_varlen_bwd, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
+         CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
+         Cint, Cint, Cint, Int64, Int64, Cint, Cint, Cint, Cint, Cint, Cfloat, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        ptr(dq), ptr(dk), ptr(dv), ptr(Δ), ptr(o), ptr(lse), ptr(q), ptr(k), ptr(v),
+        ptr(cu_seqlens_q), ptr(cu_seqlens_k), nseq, max_seqlen_q, max_seqlen_k, TQ, TK,
+        dtype_code(T), E, QH, KH, causal, Float32(inv(sqrt(E))), ptr(ws), nbytes, stream()))
+    CUDA.unsafe_free!(ws)
+    return dq, dk, dv
+end
+
+flash_attention_varlen(q, k, v, cu_q, cu_k, max_q, max_k; causal::Bool) =
+    _flash_attention_varlen(q, k, v, cu_q, cu_k, max_q, max_k; causal)[1]
+
+function CRC.rrule(::typeof(flash_attention_varlen), q, k, v, cu_q, cu_k, max_q, max_k; causal::Bool)
+    o, lse = _flash_attention_varlen(q, k, v, cu_q, cu_k, max_q, max_k; causal)
+    function _pullback(Δ)
+        Δd = convert(typeof(o), CRC.unthunk(Δ))
+        dq, dk, dv = ∇flash_attention_varlen(Δd, o, lse, q, k, v, cu_q, cu_k, max_q, max_k; causal)
+        nt = CRC.NoTangent()
+        return nt, dq, dk, dv, nt, nt, nt, nt
+    end
+    return o, _pullback
+end
+
 # ------------------------------------------------------------------ online softmax (src/softmax.jl:60-86)
 function online_softmax(x::CuMatrix{T}) where T <: FloatT
     y = similar(x)

@@ -18,6 +18,10 @@ from .ops import (  # noqa: F401
     set_timing_events, HostAttentionPipeline,
 )
 from .sharding import shard_slices, shard_attention_inputs  # noqa: F401
+from .ring import (  # noqa: F401
+    ring_flash_attention, ring_attention_forward, ring_attention_backward, ring_schedule,
+    zigzag_shard, zigzag_unshard, contiguous_shard,
+)
 
 __all__ = [
     "flash_attention", "_flash_attention", "grad_flash_attention", "online_softmax",
@@ -26,7 +30,8 @@ __all__ = [
     "device_info", "set_attention_path", "last_attention_path", "selftest_umma",
     "shard_slices", "shard_attention_inputs", "NNopError", "set_timing_events",
     "HostAttentionPipeline", "flash_attention_varlen", "_flash_attention_varlen",
-    "grad_flash_attention_varlen",
+    "grad_flash_attention_varlen", "ring_flash_attention", "ring_attention_forward",
+    "ring_attention_backward", "ring_schedule", "zigzag_shard", "zigzag_unshard", "contiguous_shard",
 ]
 # the reference spells its pullbacks with a nabla; reachable via getattr(nnop_b200, "∇flash_attention")
 globals().update({

@@ -51,6 +51,9 @@ SIGNATURES = {
     "nnop_flash_attn_varlen_fwd": (_i, [_vp] * 7 + [_i] * 3 + [_i64, _i64] + [_i] * 5 + [_f, _vp]),
     "nnop_flash_attn_varlen_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i64, _i]),
     "nnop_flash_attn_varlen_bwd": (_i, [_vp] * 11 + [_i] * 3 + [_i64, _i64] + [_i] * 5 + [_f, _vp, _sz, _vp]),
+    "nnop_attn_merge": (_i, [_vp] * 5 + [_i, _i, _i64, _i, _vp]),
+    "nnop_accumulate_f32": (_i, [_vp, _vp, _i, _i64, _i, _vp]),
+    "nnop_store_rows_from_f32": (_i, [_vp, _vp, _i, _i] + [_i64] * 4 + [_vp]),
     "nnop_softmax_fwd": (_i, [_vp, _vp, _i, _i64, _i64, _vp]),
     "nnop_softmax_bwd": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp]),
     "nnop_rms_norm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i64, _f, _f, _vp]),

@@ -1,0 +1,261 @@
+"""Sequence-sharded ("ring") flash attention across the GPUs of one node (BASELINE config 5).
+
+Additive: the reference has no multi-GPU path.  One process per GPU
+(`torch.distributed`); every rank owns a slice of the sequence axis of q, k, v.  K/V blocks travel
+round the ring (rank r -> r+1) over NVLink while the rank attends its queries to the block it
+holds with the dense kernels (`nnop_flash_attn_fwd` / `_bwd`); partial results are folded with
+`nnop_attn_merge` (log-sum-exp weights, fp32 accumulators).  The next block's transfer is posted
+before the current block's kernels, so the copy runs under the math.
+
+Causal attention uses the zig-zag layout: the sequence is cut into 2W chunks and rank r owns
+chunks (r, 2W-1-r), which makes every ring step the same amount of work on every rank:
+  step 0            local causal attention (chunk pairs (0,0) causal, (1,0) full, (1,1) causal)
+  block from s < r  both local query chunks attend the sender's FIRST chunk, no mask
+  block from s > r  the local SECOND query chunk attends both of the sender's chunks, no mask
+Backward runs the same schedule with `∇flash_attention` on each pair, using the final (merged)
+o / lse -- P = exp(S - lse) is then already globally normalised -- with dq accumulated locally
+and dk / dv travelling with their K/V block in fp32.
+
+Kernels are reached through a small backend object so that the schedule (this file) can be
+exercised on CPU under gloo with a stand-in; the default backend is the CUDA library and refuses
+CPU tensors -- there is no fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from ._lib import NNopError, check, lib
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------
+# zig-zag layout helpers (host-side index logic only)
+# ------------------------------------------------------------------------------------------
+def zigzag_chunks(rank: int, world: int):
+    """Global chunk ids (of 2*world) owned by `rank`."""
+    return rank, 2 * world - 1 - rank
+
+
+def zigzag_shard(x: torch.Tensor, rank: int, world: int, dim: int = 2) -> torch.Tensor:
+    """Local slice of a full-sequence tensor in zig-zag order (chunks r and 2W-1-r concatenated)."""
+    L = x.shape[dim]
+    if L % (2 * world) != 0:
+        raise NNopError(1, f"sequence length `{L}` must be divisible by 2*world = {2 * world}")
+    c = L // (2 * world)
+    a, b = zigzag_chunks(rank, world)
+    return torch.cat([x.narrow(dim, a * c, c), x.narrow(dim, b * c, c)], dim=dim).contiguous()
+
+
+def zigzag_unshard(parts, dim: int = 2) -> torch.Tensor:
+    """Inverse of `zigzag_shard` given every rank's local tensor (rank order)."""
+    world = len(parts)
+    c = parts[0].shape[dim] // 2
+    chunks = [None] * (2 * world)
+    for r, p in enumerate(parts):
+        a, b = zigzag_chunks(r, world)
+        chunks[a] = p.narrow(dim, 0, c)
+        chunks[b] = p.narrow(dim, c, c)
+    return torch.cat(chunks, dim=dim)
+
+
+def contiguous_shard(x: torch.Tensor, rank: int, world: int, dim: int = 2) -> torch.Tensor:
+    L = x.shape[dim]
+    if L % world != 0:
+        raise NNopError(1, f"sequence length `{L}` must be divisible by world = {world}")
+    c = L // world
+    return x.narrow(dim, rank * c, c).contiguous()
+
+
+def ring_schedule(rank: int, world: int, causal: bool):
+    """Per ring step: list of (q_chunk, kv_chunk, causal_flag) pairs this rank computes on the block
+    that originated at rank (rank - step) % world.  Chunk ids are local (0 / 1); non-causal uses
+    one chunk per rank."""
+    steps = []
+    for s in range(world):
+        src = (rank - s) % world
+        if not causal:
+            steps.append((src, [(0, 0, False)]))
+        elif s == 0:
+            steps.append((src, [(0, 0, True), (1, 0, False), (1, 1, True)]))
+        elif src < rank:
+            steps.append((src, [(0, 0, False), (1, 0, False)]))
+        else:
+            steps.append((src, [(1, 0, False), (1, 1, False)]))
+    return steps
+
+
+# ------------------------------------------------------------------------------------------
+# kernel backend (CUDA library)
+# ------------------------------------------------------------------------------------------
+class CudaBackend:
+    """The product path: every call is one or two launches of libnnop_b200.so."""
+
+    acc_dtype = torch.float32
+
+    @staticmethod
+    def _need_cuda(*ts):
+        for t in ts:
+            if not t.is_cuda:
+                raise NNopError(6, "ring attention runs on CUDA tensors only (there is no CPU path)")
+
+    def attn_fwd(self, q, k, v, causal):
+        return ops._flash_attention(q, k, v, causal=causal)
+
+    def attn_bwd(self, dO, o, lse, q, k, v, causal):
+        return ops.grad_flash_attention(dO, o, lse, q, k, v, causal=causal)[:3]
+
+    def merge(self, o_acc, lse_acc, o_part, lse_part, init):
+        """Fold (o_part, lse_part) into (o_acc, lse_acc); returns the new lse tensor."""
+        self._need_cuda(o_acc, o_part)
+        lse_new = lse_acc if init else torch.empty_like(lse_acc)
+        check(lib.nnop_attn_merge(o_acc.data_ptr(), lse_acc.data_ptr(), lse_new.data_ptr(),
+                                  o_part.data_ptr(), lse_part.data_ptr(), ops._dt(o_part),
+                                  o_part.shape[-1], lse_part.numel(), int(init), ops._stream()))
+        return lse_new
+
+    def accumulate(self, acc, part, init):
+        self._need_cuda(acc, part)
+        check(lib.nnop_accumulate_f32(acc.data_ptr(), part.data_ptr(), ops._dt(part), part.numel(),
+                                      int(init), ops._stream()))
+
+    def store_rows(self, out, acc, row_offset):
+        """out[..., row_offset : row_offset + rows, :] = acc (cast to out.dtype)."""
+        self._need_cuda(out, acc)
+        rows, E = acc.shape[-2], acc.shape[-1]
+        check(lib.nnop_store_rows_from_f32(out.data_ptr(), acc.data_ptr(), ops._dt(out), E,
+                                           acc.numel() // (rows * E), rows, out.shape[-2], row_offset,
+                                           ops._stream()))
+
+
+# ------------------------------------------------------------------------------------------
+# ring exchange
+# ------------------------------------------------------------------------------------------
+class _Ring:
+    def __init__(self, group):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.next = dist.get_global_rank(group, (self.rank + 1) % self.world) if group is not None \
+            else (self.rank + 1) % self.world
+        self.prev = dist.get_global_rank(group, (self.rank - 1) % self.world) if group is not None \
+            else (self.rank - 1) % self.world
+
+    def start(self, send: torch.Tensor, recv: torch.Tensor):
+        """Post send -> next, recv <- prev; returns handles to wait on."""
+        if self.world == 1:
+            return []
+        ops_ = [dist.P2POp(dist.isend, send, self.next, self.group),
+                dist.P2POp(dist.irecv, recv, self.prev, self.group)]
+        return dist.batch_isend_irecv(ops_)
+
+    @staticmethod
+    def wait(handles):
+        for h in handles:
+            h.wait()
+
+
+def _split(x, causal):
+    """Chunk-contiguous copies of a local tensor along L: [first half, second half] or [x]."""
+    if not causal:
+        return [x.contiguous()]
+    L = x.shape[2]
+    if L % 2 != 0:
+        raise NNopError(1, f"causal ring attention needs an even local sequence length, got `{L}`")
+    return [x[:, :, :L // 2].contiguous(), x[:, :, L // 2:].contiguous()]
+
+
+def ring_attention_forward(q, k, v, *, causal: bool, group=None, backend=None):
+    """Forward over the local shards q (B,QH,Ll,E), k/v (B,KH,Ll,E) [Julia (E,Ll,H,B)].
+    Returns ``(o, residuals)``; residuals feed `ring_attention_backward`."""
+    be = backend or CudaBackend()
+    ring = _Ring(group)
+    qs, ks, vs = _split(q, causal), _split(k, causal), _split(v, causal)
+    nch = len(qs)
+    kv = torch.stack(ks + vs)            # (2*nch, B, KH, c, E): one buffer per hop
+    kv_next = torch.empty_like(kv)
+    o_acc = [torch.empty(x.shape, dtype=be.acc_dtype, device=x.device) for x in qs]
+    lse = [torch.empty(x.shape[:3], dtype=torch.float32, device=x.device) for x in qs]
+    started = [False] * nch
+    for s, (src, pairs) in enumerate(ring_schedule(ring.rank, ring.world, causal)):
+        handles = ring.start(kv, kv_next) if s + 1 < ring.world else []
+        for qc, kc, cz in pairs:
+            o_p, lse_p = be.attn_fwd(qs[qc], kv[kc], kv[nch + kc], cz)
+            lse[qc] = be.merge(o_acc[qc], lse[qc], o_p, lse_p, not started[qc])
+            started[qc] = True
+        ring.wait(handles)
+        if handles:
+            kv, kv_next = kv_next, kv
+    o = torch.empty_like(q)
+    o_ch = []
+    c = qs[0].shape[2]
+    for i in range(nch):
+        be.store_rows(o, o_acc[i], i * c)
+        oc = torch.empty_like(qs[i])
+        be.store_rows(oc, o_acc[i], 0)
+        o_ch.append(oc)
+    return o, (qs, ks, vs, o_ch, lse)
+
+
+def ring_attention_backward(dO, residuals, *, causal: bool, group=None, backend=None):
+    """Backward; returns local ``(dq, dk, dv)`` in the layout of the forward's inputs."""
+    be = backend or CudaBackend()
+    ring = _Ring(group)
+    qs, ks, vs, o_ch, lse = residuals
+    nch = len(qs)
+    dOs = _split(dO, causal)
+    kv = torch.stack(ks + vs)
+    kv_next = torch.empty_like(kv)
+    dkv = torch.zeros(kv.shape, dtype=be.acc_dtype, device=kv.device)   # travels with its K/V block
+    dkv_next = torch.empty_like(dkv)
+    dq_acc = [torch.empty(x.shape, dtype=be.acc_dtype, device=x.device) for x in qs]
+    started = [False] * nch
+    for s, (src, pairs) in enumerate(ring_schedule(ring.rank, ring.world, causal)):
+        last = s + 1 == ring.world
+        h_kv = ring.start(kv, kv_next) if not last else []      # prefetch the next block under the math
+        for qc, kc, cz in pairs:
+            dq_p, dk_p, dv_p = be.attn_bwd(dOs[qc], o_ch[qc], lse[qc], qs[qc], kv[kc], kv[nch + kc], cz)
+            be.accumulate(dq_acc[qc], dq_p, not started[qc])
+            started[qc] = True
+            be.accumulate(dkv[kc], dk_p, False)
+            be.accumulate(dkv[nch + kc], dv_p, False)
+        ring.wait(h_kv)
+        # the gradient block moves on with its K/V block (after the last step: home to its owner)
+        h_g = ring.start(dkv, dkv_next)
+        ring.wait(h_g)
+        if h_g:
+            dkv, dkv_next = dkv_next, dkv
+        if h_kv:
+            kv, kv_next = kv_next, kv
+    dq = torch.empty_like(dO)
+    dk = torch.empty_like(torch.cat(ks, dim=2)) if nch > 1 else torch.empty_like(ks[0])
+    dv = torch.empty_like(dk)
+    c = qs[0].shape[2]
+    for i in range(nch):
+        if not started[i]:      # cannot happen (every chunk attends at least its own block)
+            dq_acc[i].zero_()
+        be.store_rows(dq, dq_acc[i], i * c)
+        be.store_rows(dk, dkv[i], i * c)
+        be.store_rows(dv, dkv[nch + i], i * c)
+    return dq, dk, dv
+
+
+class _RingAttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, causal, group, backend):
+        o, res = ring_attention_forward(q, k, v, causal=causal, group=group, backend=backend)
+        ctx.res, ctx.meta = res, (causal, group, backend)
+        return o
+
+    @staticmethod
+    def backward(ctx, dO):
+        causal, group, backend = ctx.meta
+        dq, dk, dv = ring_attention_backward(dO.contiguous(), ctx.res, causal=causal, group=group,
+                                             backend=backend)
+        return dq, dk, dv, None, None, None
+
+
+def ring_flash_attention(q, k, v, *, causal: bool, group=None, backend=None):
+    """`flash_attention` over a sequence sharded across the ranks of `group` (differentiable).
+    Causal inputs must be in zig-zag order (`zigzag_shard`)."""
+    return _RingAttentionFn.apply(q, k, v, bool(causal), group, backend)
