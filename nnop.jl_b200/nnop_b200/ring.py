@@ -131,8 +131,28 @@ class CudaBackend:
 # ------------------------------------------------------------------------------------------
 # ring exchange
 # ------------------------------------------------------------------------------------------
+_ring_groups = {}
+
+
+def ring_group(base_group=None):
+    """Process group the K/V rotation runs on.  Under NCCL it is a dedicated group whose kernels
+    launch on a HIGH-PRIORITY stream: the attention kernels keep every SM busy (one CTA per SM, all
+    shared memory), and on a normal-priority stream a send/recv kernel posted under them only gets
+    SMs when the attention grid drains (measured: 0.84 ms -> 11 ms per 268 MB hop).  Collective:
+    every rank of `base_group` must make the first call.  Other backends: `base_group` itself."""
+    if dist.get_backend(base_group) != "nccl":
+        return base_group
+    key = id(base_group) if base_group is not None else None
+    if key not in _ring_groups:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        ranks = dist.get_process_group_ranks(base_group if base_group is not None else dist.group.WORLD)
+        _ring_groups[key] = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+    return _ring_groups[key]
+
+
 class _Ring:
     def __init__(self, group):
+        group = ring_group(group)
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
