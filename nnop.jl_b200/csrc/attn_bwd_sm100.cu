@@ -50,6 +50,7 @@ struct BwdParams {
   void* dk_ptr;
   void* dv_ptr;
   int64_t total_k;
+  const uint8_t* kpad;  // (B, KL) key padding mask, 1 = attend, or nullptr (dense mode only)
 };
 
 // first padded-statistics row of packed sequence z (each sequence is padded to whole 128-row blocks)
@@ -132,7 +133,15 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   const int nq = (QL + 127) >> 7;
   const int i0 = p.causal ? j : 0;
   const int nqi = nq > i0 ? nq - i0 : 0;
-  const int n_it = nqi * g;
+  // key padding mask (src/attention.jl:73-79): a block with no attended key does no work at all;
+  // otherwise the masked key rows (thread <-> key row in the compute warpgroups) are zeroed in P^T
+  bool key_keep = true;
+  if (p.kpad) {
+    const int kr = k0 + (threadIdx.x & 127);
+    key_keep = kr < KL && p.kpad[static_cast<int64_t>(b) * p.KL + kr] != 0;
+  }
+  const bool any_key = p.kpad ? __syncthreads_or(key_keep) != 0 : true;
+  const int n_it = any_key ? nqi * g : 0;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -337,7 +346,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         for (int c = 0; c < 64; ++c)
           if (row > c0 + c) pf[c] = 0.f;
       }
-      if (packed && k0 + row >= KL) {  // this key row belongs to the next packed sequence
+      if ((packed && k0 + row >= KL) || !key_keep) {  // next packed sequence's key / padded key
 #pragma unroll
         for (int c = 0; c < 64; ++c) pf[c] = 0.f;
       }
@@ -530,7 +539,9 @@ attn_bwd_prep_kernel(float* __restrict__ deltap, float* __restrict__ lse2p,
   for (int sft = 1; sft < LPR; sft <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
   if (li == 0) {
     deltap[rowp] = q < QL ? acc : 0.f;
-    lse2p[rowp] = q < QL ? lse[bh * QL + q] * kLog2e : INFINITY;
+    // a fully masked row has lse = -inf: give it +inf like the padding rows so that P = 0
+    const float l = q < QL ? lse[bh * QL + q] : INFINITY;
+    lse2p[rowp] = l == -INFINITY ? INFINITY : l * kLog2e;
   }
 }
 
@@ -566,7 +577,8 @@ attn_bwd_prep_packed_kernel(float* __restrict__ deltap, float* __restrict__ lse2
   if (li == 0) {
     const int64_t pr = static_cast<int64_t>(h) * QLp + packed_stat_row(q_off, z) + r;
     deltap[pr] = r < QL ? acc : 0.f;
-    lse2p[pr] = r < QL ? lse[static_cast<int64_t>(h) * total_q + q_off + r] * kLog2e : INFINITY;
+    const float l = r < QL ? lse[static_cast<int64_t>(h) * total_q + q_off + r] : INFINITY;
+    lse2p[pr] = l == -INFINITY ? INFINITY : l * kLog2e;
   }
 }
 
@@ -643,6 +655,7 @@ int launch_bwd(const AttnParams& a) {
   bp.causal = a.causal;
   bp.scale = a.scale; bp.scale_log2 = a.scale * kLog2e;
   bp.cu_q = a.cu_q; bp.cu_k = a.cu_k; bp.dk_ptr = a.dk; bp.dv_ptr = a.dv; bp.total_k = a.total_k;
+  bp.kpad = packed ? nullptr : a.kpad;
   dim3 grid((a.KL + 127) / 128, a.KH, packed ? a.nseq : a.B);
   timing_begin(1, a.stream);
   kern<<<grid, kBwdThreads, S::kTotal, a.stream>>>(tq, tk, tv, tdo, tdk, tdv, tdqa, bp);

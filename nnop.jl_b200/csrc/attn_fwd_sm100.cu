@@ -62,6 +62,7 @@ struct FwdParams {
   const int* cu_k;
   void* o_ptr;       // raw output pointer for partial tiles (a TMA store would spill into the next sequence)
   int64_t total_q;
+  const uint8_t* kpad;  // (B, KL) key padding mask, 1 = attend, or nullptr (dense mode only)
 };
 
 template <int D>
@@ -121,6 +122,23 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   }
   const int bh_q = b * p.QH + h;
   const int bh_kv = b * p.KH + h / (p.QH / p.KH);
+  // key padding mask (src/attention.jl:73-79): keys past the last attended one are never loaded
+  // (a prefix-shaped mask costs nothing beyond its own length); blocks that still contain masked
+  // keys are masked element-wise in the softmax warpgroups
+  const uint8_t* kmask = p.kpad ? p.kpad + static_cast<int64_t>(b) * p.KL : nullptr;
+  if (kmask) {
+    __shared__ int s_kl_eff;
+    if (threadIdx.x == 0) s_kl_eff = 0;
+    __syncthreads();
+    int last = 0;
+    for (int kk = threadIdx.x; kk < KL; kk += kFwdThreads)
+      if (kmask[kk]) last = kk + 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    if (lane == 0 && last > 0) atomicMax(&s_kl_eff, last);
+    __syncthreads();
+    KL = s_kl_eff;
+  }
   const bool act1 = q0 + 128 < QL;
   const int nb0 = ((p.causal ? min(KL, q0 + 128) : KL) + 127) >> 7;
   const int nb1 = act1 ? (((p.causal ? min(KL, q0 + 256) : KL) + 127) >> 7) : 0;
@@ -317,7 +335,20 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       float l = 0.f;
 
       const uint64_t sl2x2 = pack_f2(sl2, sl2);
+      // key padding: lane holds mask bytes 4*lane .. 4*lane+3 of a block; fetched one block ahead
+      auto mask_bytes = [&](int blk) -> uint32_t {
+        uint32_t r = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kk = blk * 128 + 4 * lane + j;
+          if (kk < KL && kmask[kk]) r |= 1u << (8 * j);
+        }
+        return r;
+      };
+      uint32_t mb_next = kmask ? mask_bytes(0) : 0u;
       for (int i = 0; i < nbt; ++i) {
+        const uint32_t mb = mb_next;
+        if (kmask && i + 1 < nbt) mb_next = mask_bytes(i + 1);
         mbar_wait(&s_full[t], i & 1);
         tc_fence_after();
         if (wq == 0) FWD_STAMP(i, 5 * t + 0);
@@ -333,14 +364,23 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         }
 
         const int k0 = i * 128;
-        const bool need_mask = (k0 + 128 > KL) || (p.causal && (k0 + 127 > q0 + t * 128));
+        // bit l of kw[j] = mask of key 4*l + j of this block (all ones without a padding mask)
+        uint32_t kw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (kmask) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) kw[j] = __ballot_sync(0xffffffffu, (mb >> (8 * j)) & 1u);
+        }
+        const bool need_mask = (k0 + 128 > KL) || (p.causal && (k0 + 127 > q0 + t * 128)) ||
+                               ((kw[0] & kw[1] & kw[2] & kw[3]) != 0xffffffffu);
         if (need_mask) {
           const int lim = p.causal ? min(KL - 1, q_row) : (KL - 1);  // last visible key
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (k0 + c * 32 + j > lim) sr[c][j] = 0xff800000u;  // -inf
+            for (int j = 0; j < 32; ++j) {
+              const int kk = c * 32 + j;
+              if (k0 + kk > lim || !((kw[kk & 3] >> (kk >> 2)) & 1u)) sr[c][j] = 0xff800000u;  // -inf
+            }
         }
         // exp2(S*scale*log2e - m_used) of one 32-key chunk; every kPolyEvery-th pair runs on the
         // FMA pipe (exp2_poly2) instead of the MUFU
@@ -520,6 +560,7 @@ int launch_fwd(const AttnParams& a) {
   fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
   fp.scale_log2 = a.scale * kLog2e;
   fp.cu_q = a.cu_q; fp.cu_k = a.cu_k; fp.o_ptr = a.o; fp.total_q = a.total_q;
+  fp.kpad = packed ? nullptr : a.kpad;
   dim3 grid((a.QL + 255) / 256, a.QH, packed ? a.nseq : a.B);
   timing_begin(0, a.stream);
   kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, fp);
@@ -540,7 +581,7 @@ bool attn_sm100_supported(const AttnParams& a, bool backward) {
   if (backward && !attn_sm100_bwd_available()) return false;
   if (a.dtype != NNOP_F16 && a.dtype != NNOP_BF16) return false;
   if (a.E != 64 && a.E != 128) return false;
-  if (a.pair || a.kpad) return false;
+  if (a.pair) return false;  // the additive bias is served by the generic path
   if (a.QL < 1 || a.KL < 1) return false;
   if (a.QH > 65535 || a.B > 65535 || a.nseq > 65535) return false;
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };

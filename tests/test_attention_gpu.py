@@ -185,9 +185,57 @@ def test_tcgen05_matches_generic_path(nnop, causal):
         assert max_abs(a, b) < H16_TOL * max(1.0, b.abs().max().item() / 2)
 
 
-def test_16bit_pair_and_mask_fall_to_generic(nnop):
+def test_16bit_pair_falls_to_generic(nnop):
     q, k, v, dO, pr, m = _inputs(2, 2, 2, 300, 300, 64, torch.bfloat16, 5, pair=True, mask=True)
     _check(nnop, q, k, v, dO, pr, m, True, 4e-2, expect_path=0)
+
+
+def _zero_masked_check(nnop, q, k, v, dO, m, causal):
+    """kpad_mask with fully masked rows: outputs 0 / lse -inf instead of the reference's NaN."""
+    dev = lambda t: t.cuda()
+    o, lse = nnop._flash_attention(dev(q), dev(k), dev(v), causal=causal, kpad_mask=dev(m))
+    assert nnop.last_attention_path() == 1
+    D = lambda t: t.double()
+    ro, rl = O.naive_attention(D(q), D(k), D(v), causal=causal, kpad_mask=m, zero_masked_rows=True, return_lse=True)
+    assert max_abs(o, ro) < H16_TOL
+    fin = torch.isfinite(rl)
+    assert torch.equal(torch.isfinite(lse.cpu()), fin) and max_abs(lse.cpu()[fin], rl[fin]) < 1e-3
+    dq, dk, dv, _ = nnop.grad_flash_attention(dev(dO), o, lse, dev(q), dev(k), dev(v), causal=causal, kpad_mask=dev(m))
+    rq, rk, rv, _ = O.naive_attention_bwd(D(dO), D(q), D(k), D(v), causal=causal, kpad_mask=m, zero_masked_rows=True)
+    mag = lambda r: max(1.0, r.abs().max().item() / 2)
+    assert max_abs(dq, rq) < H16_TOL * mag(rq) and max_abs(dk, rk) < H16_TOL * mag(rk) and max_abs(dv, rv) < H16_TOL * mag(rv)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("E", [128, 64])
+@pytest.mark.parametrize("causal", [False, True])
+def test_tcgen05_kpad_mask(nnop, dtype, E, causal):
+    """kpad_mask on the tensor-core path: the reference's own pattern (test/attention_tests.jl:27-28,
+    last 11 keys of the last batch element), prefix-shaped padding (trailing blocks never loaded),
+    scattered holes, and an entirely padded batch element."""
+    for (B, QH, KH, QL, KL) in [(3, 2, 2, 255, 255), (2, 4, 2, 512, 512), (2, 2, 1, 300, 700)]:
+        if causal and QL != KL:
+            continue
+        q, k, v, dO, _, m = _inputs(B, QH, KH, QL, KL, E, dtype, QL + KL, mask=True)
+        _check(nnop, q, k, v, dO, None, m, causal, H16_TOL, expect_path=1)
+        # prefix-shaped: batch element b keeps only its first len_b keys
+        mp = torch.zeros(B, KL, dtype=torch.bool)
+        for b, n in enumerate([KL, KL // 3 + 1, 129][:B]):
+            mp[b, :n] = True
+        if not causal:   # with a causal mask every row still sees key 0, so no row is empty
+            _check(nnop, q, k, v, dO, None, mp, causal, H16_TOL, expect_path=1)
+        else:
+            _check(nnop, q, k, v, dO, None, mp, causal, H16_TOL, expect_path=1)
+        # scattered holes (key 0 kept so that no row is empty under the causal mask)
+        g = torch.Generator().manual_seed(KL)
+        ms = torch.rand(B, KL, generator=g) > 0.3
+        ms[:, 0] = True
+        _check(nnop, q, k, v, dO, None, ms, causal, H16_TOL, expect_path=1)
+        # one batch element entirely padded, and a hole at key 0 (causal row 0 then sees nothing)
+        mz = ms.clone()
+        mz[-1, :] = False
+        mz[0, 0] = False
+        _zero_masked_check(nnop, q, k, v, dO, mz, causal)
 
 
 def test_full_size_properties_config_c2(nnop):
