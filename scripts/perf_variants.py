@@ -21,8 +21,10 @@ def err():
         d = nn.grad_flash_attention(dO,o,lse,q,k,v,causal=True)
         e += [(a.float()-b).abs().max().item() for a,b in zip(d[:3],g)]
     return e
-def t(B,H,L,E,causal,iters=8):
-    q,k,v,dO = (torch.randn(B,H,L,E,device="cuda",dtype=torch.bfloat16) for _ in range(4))
+def t(B,H,L,E,causal,iters=8,KH=None):
+    KH = KH or H
+    q,dO = (torch.randn(B,H,L,E,device="cuda",dtype=torch.bfloat16) for _ in range(2))
+    k,v = (torch.randn(B,KH,L,E,device="cuda",dtype=torch.bfloat16) for _ in range(2))
     f = 4.0*B*H*L*L*E*(0.5 if causal else 1)
     for _ in range(3): o,lse = nn._flash_attention(q,k,v,causal=causal)
     a,b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,7 +41,7 @@ def t(B,H,L,E,causal,iters=8):
         tb = a.elapsed_time(b)/iters
         s += " | bwd %%.3f ms %%.0f TF/s | tot %%.0f TF/s" %% (tb, 2.5*f/tb/1e9, 3.5*f/(tf+tb)/1e9)
     return s
-print("err", ["%%.4f" %% x for x in err()], "| C2:", t(8,32,8192,128,True), "| noncausal:", t(4,32,8192,128,False), "| L2048:", t(8,32,2048,128,True), flush=True)
+print("err", ["%%.4f" %% x for x in err()], "| C2:", t(8,32,8192,128,True), "| noncausal:", t(4,32,8192,128,False), "| L2048:", t(8,32,2048,128,True), "| GQA32/8:", t(4,32,8192,128,True,KH=8), flush=True)
 '''
 bwd = "--bwd" in sys.argv
 for name in [a for a in sys.argv[1:] if not a.startswith("--")]:
