@@ -34,7 +34,12 @@ constexpr float kLog2e = 1.4426950408889634f;
 // development aid: pipeline timeline of CTA (0,0,0), 16 clock64 stamps per q-block step
 __device__ long long g_bwd_trace[256 * 16];
 #define BWD_STAMP(i, k) do { if (tr) g_bwd_trace[(i) * 16 + (k)] = clock64(); } while (0)
+// every CTA that runs on SM 0 logs (j, n_it, 6 clock stamps): per-CTA fixed costs and gaps
+__device__ long long g_bwd_cta_log[1024 * 16];
+__device__ int g_bwd_cta_n;
+#define BWD_CTA(k) do { if (cta_slot >= 0) g_bwd_cta_log[cta_slot * 16 + (k)] = clock64(); } while (0)
 #else
+#define BWD_CTA(k) do { } while (0)
 #define BWD_STAMP(i, k) do { } while (0)
 #endif
 
@@ -111,6 +116,16 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   const int lane = threadIdx.x & 31;
 #ifdef NNOP_BWD_TRACE
   const bool tr = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  int& s_cta_slot = *reinterpret_cast<int*>(smem + S::kBar + S::kNumBars * 8 + 8);  // spare bytes after the TMEM slot
+  if (threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    s_cta_slot = smid == 0 ? atomicAdd(&g_bwd_cta_n, 1) : -1;
+    if (s_cta_slot >= 1024) s_cta_slot = -1;
+    if (s_cta_slot >= 0) g_bwd_cta_log[s_cta_slot * 16 + 0] = clock64();
+  }
+  __syncthreads();
+  const int cta_slot = lane == 0 ? s_cta_slot : -1;
 #endif
 
   // ---- work assignment ----------------------------------------------------------------
@@ -175,6 +190,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 256 + D;
+  if (threadIdx.x == 0) BWD_CTA(1);
 
   if (warp < 4) {
     setmaxnreg_dec<88>();  // 512 thr x 128 regs at launch -> 88 / 136 / 152 (sum = 64K regs)
@@ -262,6 +278,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         mbar_wait(p_full, it & 1);
         tc_fence_after();
         BWD_STAMP(it, 0);
+        if (it == 0) BWD_CTA(2);
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
@@ -309,6 +326,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         }
       }
       commit(dkdv_full);
+      BWD_CTA(3);
     }
   } else if (warp < 12) {
     // ================================ compute warpgroups ===============================
@@ -398,6 +416,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       mbar_wait(dkdv_full, 0);
       tc_fence_after();
     }
+    if (warp == 4) BWD_CTA(4);
     {
       const uint32_t tsrc = tmem_base + lane_off + (half ? kColDK : kColDV);
       const float mul = half ? p.scale : 1.f;
@@ -424,6 +443,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           *reinterpret_cast<uint4*>(stage + bx * S::kBox + row * 128 + ((cin ^ (row & 7)) << 4)) = v;
         }
       }
+      if (warp == 4) BWD_CTA(8);   // TMEM drained, staged
       const int rows_left = KL - k0;
       if (packed && rows_left < 128) {
         // partial last block of a packed sequence: copy only its own rows (coalesced 16-byte stores)
@@ -447,7 +467,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           for (int bx = 0; bx < S::kNBox; ++bx)
             tma_store_3d(half ? &tm_dk : &tm_dv, stage + bx * S::kBox, bx * 64, k_off + k0, bh_kv);
           bulk_commit();
+          if (warp == 4) BWD_CTA(9);
           bulk_wait_read<0>();
+          if (warp == 4) BWD_CTA(10);
         }
       }
     }
@@ -494,12 +516,21 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         ++nred;
       }
     }
+    if (issuer) BWD_CTA(11);
     if (issuer) bulk_wait<0>();
+    if (issuer) BWD_CTA(12);
   }
 
   // ---- teardown -------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+#ifdef NNOP_BWD_TRACE
+  if (threadIdx.x == 0 && cta_slot >= 0) {
+    g_bwd_cta_log[cta_slot * 16 + 5] = clock64();
+    g_bwd_cta_log[cta_slot * 16 + 6] = blockIdx.x;
+    g_bwd_cta_log[cta_slot * 16 + 7] = n_it;
+  }
+#endif
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -675,6 +706,15 @@ int launch_bwd(const AttnParams& a) {
 #ifdef NNOP_BWD_TRACE
 extern "C" int nnop_debug_bwd_trace(long long* host_out, int n) {
   return static_cast<int>(cudaMemcpyFromSymbol(host_out, g_bwd_trace, sizeof(long long) * n));
+}
+extern "C" int nnop_debug_bwd_cta_log(long long* host_out, int max_ctas, int reset) {
+  int n = 0;
+  cudaMemcpyFromSymbol(&n, g_bwd_cta_n, sizeof(int));
+  if (n > max_ctas) n = max_ctas;
+  if (n > 1024) n = 1024;
+  cudaMemcpyFromSymbol(host_out, g_bwd_cta_log, sizeof(long long) * 16 * n);
+  if (reset) { int z = 0; cudaMemcpyToSymbol(g_bwd_cta_n, &z, sizeof(int)); }
+  return n;
 }
 #endif
 

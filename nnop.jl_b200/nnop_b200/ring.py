@@ -218,7 +218,12 @@ def ring_attention_forward(q, k, v, *, causal: bool, group=None, backend=None):
 
 
 def ring_attention_backward(dO, residuals, *, causal: bool, group=None, backend=None):
-    """Backward; returns local ``(dq, dk, dv)`` in the layout of the forward's inputs."""
+    """Backward; returns local ``(dq, dk, dv)`` in the layout of the forward's inputs.
+
+    Both transfers of a step run under its kernels: the next K/V block is prefetched, and the
+    travelling dK/dV of the block being worked on (accumulated by the previous rank during the
+    previous step) arrives while this rank computes its own contribution into a step-local fp32
+    buffer; the two are added afterwards and sent on at the start of the next step."""
     be = backend or CudaBackend()
     ring = _Ring(group)
     qs, ks, vs, o_ch, lse = residuals
@@ -226,34 +231,47 @@ def ring_attention_backward(dO, residuals, *, causal: bool, group=None, backend=
     dOs = _split(dO, causal)
     kv = torch.stack(ks + vs)
     kv_next = torch.empty_like(kv)
-    dkv = torch.zeros(kv.shape, dtype=be.acc_dtype, device=kv.device)   # travels with its K/V block
-    dkv_next = torch.empty_like(dkv)
+    mk = lambda: torch.empty(kv.shape, dtype=be.acc_dtype, device=kv.device)
+    step_g, g_in, g_out = mk(), mk(), None       # this step's contribution / arriving / leaving
     dq_acc = [torch.empty(x.shape, dtype=be.acc_dtype, device=x.device) for x in qs]
     started = [False] * nch
     for s, (src, pairs) in enumerate(ring_schedule(ring.rank, ring.world, causal)):
         last = s + 1 == ring.world
-        h_kv = ring.start(kv, kv_next) if not last else []      # prefetch the next block under the math
+        h_kv = ring.start(kv, kv_next) if not last else []
+        h_g = ring.start(g_out, g_in) if s > 0 else []
+        touched = [False] * (2 * nch)
         for qc, kc, cz in pairs:
             dq_p, dk_p, dv_p = be.attn_bwd(dOs[qc], o_ch[qc], lse[qc], qs[qc], kv[kc], kv[nch + kc], cz)
             be.accumulate(dq_acc[qc], dq_p, not started[qc])
             started[qc] = True
-            be.accumulate(dkv[kc], dk_p, False)
-            be.accumulate(dkv[nch + kc], dv_p, False)
+            be.accumulate(step_g[kc], dk_p, not touched[kc])
+            be.accumulate(step_g[nch + kc], dv_p, not touched[nch + kc])
+            touched[kc] = touched[nch + kc] = True
+        for c, t in enumerate(touched):
+            if not t:
+                step_g[c].zero_()
         ring.wait(h_kv)
-        # the gradient block moves on with its K/V block (after the last step: home to its owner)
-        h_g = ring.start(dkv, dkv_next)
         ring.wait(h_g)
-        if h_g:
-            dkv, dkv_next = dkv_next, dkv
+        if s > 0:
+            be.accumulate(g_in, step_g, False)       # travelling gradient += this rank's share
+            g_out, g_in = g_in, g_out
+        else:
+            g_out, step_g = step_g, mk()
+            if g_in is None:
+                g_in = mk()
         if h_kv:
             kv, kv_next = kv_next, kv
+    # after the last step the gradient block sits one hop before its owner
+    if ring.world > 1:
+        ring.wait(ring.start(g_out, g_in))
+        dkv = g_in
+    else:
+        dkv = g_out
     dq = torch.empty_like(dO)
     dk = torch.empty_like(torch.cat(ks, dim=2)) if nch > 1 else torch.empty_like(ks[0])
     dv = torch.empty_like(dk)
     c = qs[0].shape[2]
     for i in range(nch):
-        if not started[i]:      # cannot happen (every chunk attends at least its own block)
-            dq_acc[i].zero_()
         be.store_rows(dq, dq_acc[i], i * c)
         be.store_rows(dk, dkv[i], i * c)
         be.store_rows(dv, dkv[nch + i], i * c)
