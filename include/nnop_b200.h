@@ -63,6 +63,11 @@ int nnop_device_info(int device, nnop_device_info_t* out);
 int nnop_set_attention_path(int mode);
 /* 1 if the last flash-attention call on this thread ran the tcgen05 path, else 0. */
 int nnop_last_attention_path(void);
+/* Backward kernel selection on the tcgen05 path (diagnostics / A-B timing).  0 (default): one CTA
+ * per kv block; 1 (or env NNOP_BWD_PAIR=1): E = 128 dense problems run the experimental CTA-pair
+ * kernel (tcgen05 cta_group::2, two kv blocks per cluster sharing the Q / dO operand halves; same
+ * results, currently slower).  Process-wide. */
+int nnop_set_bwd_pair_mode(int mode);
 
 /* ---------------------------------------------------------------------------------------
  * flash attention forward.  Replaces `_flash_attention` + kernel `_flash_attention_fwd!`

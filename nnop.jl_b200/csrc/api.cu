@@ -127,6 +127,11 @@ extern "C" int nnop_set_attention_path(int mode) {
   return NNOP_OK;
 }
 extern "C" int nnop_last_attention_path(void) { return g_last_path; }
+extern "C" int nnop_set_bwd_pair_mode(int mode) {
+  if (mode < 0 || mode > 1) return fail(NNOP_ERR_ARG, "backward pair mode must be 0 or 1");
+  attn_sm100_set_bwd_pair_mode(mode);
+  return NNOP_OK;
+}
 
 extern "C" int nnop_flash_attn_fwd(void* o, float* lse, const void* q, const void* k, const void* v,
                                    const void* pair, const uint8_t* kpad_mask, int dtype, int E,

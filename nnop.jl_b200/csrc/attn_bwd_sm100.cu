@@ -11,7 +11,9 @@
 //             128-row q blocks i (causal: i >= j only).  Per step, five 128x128x128 MMAs:
 //                S^T  = K_j Q_i^T          (smem x smem)            -> TMEM [0,128)
 //                dP^T = V_j dO_i^T         (smem x smem)            -> TMEM [128,256)
-//                dV  += P^T dO_i           (A = P^T bf16 in TMEM, aliasing S^T)
+//                dV  += P^T dO_i           (A = P^T bf16 in TMEM, aliasing S^T: each compute warpgroup packs its
+//                                           64 q columns into the first 32 columns of its OWN half of S^T, so
+//                                           neither can overwrite logits the other has not read yet)
 //                dQ_i = dS K_j             (A = dS^T smem read MN-major) -> TMEM [128,128+E), aliasing dP^T
 //                dK  += dS^T Q_i           (A = dS^T smem read K-major)
 //             P^T = exp2(S^T*scale*log2e - lse2[q]) and dS^T = P^T o (dP^T - delta[q]) are computed
@@ -21,6 +23,10 @@
 //             Issue order per step: dV(i), S^T(i+1), dQ(i), dK(i), dP^T(i+1) so the tensor pipe
 //             works on step i's products while the warpgroups exponentiate step i+1.
 //   3. post:  dQ = T(scale * dQ_accum).
+#include <stdlib.h>
+
+#include <atomic>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -29,6 +35,21 @@ namespace {
 
 constexpr int kBwdThreads = 512;
 constexpr float kLog2e = 1.4426950408889634f;
+
+// 0 (default) = one CTA per kv block, 1 = CTA pairs (cta_group::2) where eligible; env NNOP_BWD_PAIR /
+// nnop_set_bwd_pair_mode.  The pair kernel is exact but measured slower (5 600 vs 4 000 clk per step
+// on config C2): what it saves on the shared-memory port it loses to cross-CTA barrier round trips
+// on the dP -> dS -> dQ -> drain -> dP chain.  Kept as an experiment; see DESIGN.md 4.2.
+std::atomic<int> g_bwd_pair_mode{-1};
+inline int bwd_pair_mode() {
+  int m = g_bwd_pair_mode.load();
+  if (m < 0) {
+    const char* e = getenv("NNOP_BWD_PAIR");
+    m = e ? atoi(e) : 0;
+    g_bwd_pair_mode.store(m);
+  }
+  return m;
+}
 
 #ifdef NNOP_BWD_TRACE
 // development aid: pipeline timeline of CTA (0,0,0), 16 clock64 stamps per q-block step
@@ -282,8 +303,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_ts_lo(tm + kColDV, tm + kColS + ks * 8, m_lo, (S::kdO + ks * 2048) >> 4, m_hi, id_tv,
-                       (acc | (ks > 0)) ? 1u : 0u);
+            umma_ts_lo(tm + kColDV, tm + kColS + (ks >> 2) * 64 + (ks & 3) * 8, m_lo,
+                       (S::kdO + ks * 2048) >> 4, m_hi, id_tv, (acc | (ks > 0)) ? 1u : 0u);
         }
         commit(do_empty);
         // S^T(i+1)
@@ -372,7 +393,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) pk[c] = pack2<T>(pf[2 * c], pf[2 * c + 1]);
-        tmem_st_x32(tmem_base + lane_off + kColS + half * 32, pk);
+        tmem_st_x32(tmem_base + lane_off + kColS + half * 64, pk);  // inside this half's own S^T columns
       }
       tmem_st_wait();
       tc_fence_before();
@@ -537,6 +558,466 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   }
 }
 
+// =========================================================================================
+// CTA-pair variant (E = 128, dense layout): a cluster of two CTAs owns kv blocks (j, j+1) of one
+// kv head and walks the SAME q blocks in lockstep.  S^T, dP^T, dV and dK become M=256
+// cta_group::2 MMAs issued by the leader CTA: each CTA supplies its own 128 key rows of A and only
+// HALF of the Q_i / dO_i operand (64 q rows for the K-major uses, 64 head-dim columns for the
+// MN-major uses), which cuts the shared-memory port traffic of a step from 512 KB to 448 KB per CTA
+// (that port, not the tensor pipe, bounds this kernel).  dQ_i = dS K_j stays a
+// per-CTA cta_group::1 MMA (its two partial products have different B operands).
+// Cross-CTA protocol: TMA loads of both CTAs count on the leader's barriers; the compute / drain
+// warpgroups of CTA 1 arrive remotely on the leader's p_full / ds_pair / dq_empty; the leader's
+// commits are multicast to the same-offset barriers of both CTAs.
+// =========================================================================================
+struct PairSmem {
+  static constexpr int D = 128;
+  static constexpr int kTile = 128 * D * 2;   // K_j, V_j (32 KB each)
+  static constexpr int kBox = 128 * 64 * 2;   // 128 rows x 64 columns
+  static constexpr int kHalf = 16384;         // half of a Q_i / dO_i tile
+  static constexpr int kK = 0;
+  static constexpr int kV = kK + kTile;
+  static constexpr int kQA = kV + kTile;       // 2 stages x (64 q rows x 128 d): two 8 KB boxes each
+  static constexpr int kQB = kQA + 2 * kHalf;  // 2 stages x (128 q rows x 64 d)
+  static constexpr int kdOA = kQB + 2 * kHalf;
+  static constexpr int kdOB = kdOA + kHalf;
+  static constexpr int kdS = kdOB + kHalf;     // 128 x 128 16-bit, two boxes
+  static constexpr int kdQs = kdS + 2 * kBox;  // 2 x (128 rows x 32 fp32)
+  static constexpr int kStat = kdQs + 2 * 16384;
+  static constexpr int kBar = kStat + 2048;
+  static constexpr int kNumBars = 18;
+  static constexpr int kTotal = kBar + kNumBars * 8 + 16;
+};
+
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBwdThreads, 1)
+attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_q,     // box 64 x 128 rows
+                     const __grid_constant__ CUtensorMap tm_q64,   // box 64 x 64 rows
+                     const __grid_constant__ CUtensorMap tm_k,
+                     const __grid_constant__ CUtensorMap tm_v,
+                     const __grid_constant__ CUtensorMap tm_do,
+                     const __grid_constant__ CUtensorMap tm_do64,
+                     const __grid_constant__ CUtensorMap tm_dk,
+                     const __grid_constant__ CUtensorMap tm_dv,
+                     const __grid_constant__ CUtensorMap tm_dqa, const BwdParams p) {
+  using S = PairSmem;
+  constexpr int D = 128;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem + S::kK;
+  uint8_t* sV = smem + S::kV;
+  uint8_t* sQA = smem + S::kQA;
+  uint8_t* sQB = smem + S::kQB;
+  uint8_t* sdOA = smem + S::kdOA;
+  uint8_t* sdOB = smem + S::kdOB;
+  uint8_t* sdS = smem + S::kdS;
+  uint8_t* sdQ = smem + S::kdQs;
+  float* s_lse = reinterpret_cast<float*>(smem + S::kStat);         // [2][128]
+  float* s_del = reinterpret_cast<float*>(smem + S::kStat + 1024);  // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
+  uint64_t* kv_full = bars + 0;     // leader: K, V of both CTAs landed
+  uint64_t* q_full = bars + 1;      // [2] leader: Q halves of both CTAs landed
+  uint64_t* q_empty = bars + 3;     // [2] both (multicast commit)
+  uint64_t* do_full = bars + 5;     // leader
+  uint64_t* do_empty = bars + 6;    // both (multicast)
+  uint64_t* s_full = bars + 7;      // both (multicast)
+  uint64_t* p_full = bars + 8;      // leader: 16 warp arrivals (8 local + 8 remote)
+  uint64_t* dp_full = bars + 9;     // both (multicast)
+  uint64_t* ds_local = bars + 10;   // per CTA: 8 warp arrivals (gates the local dQ MMA)
+  uint64_t* ds_pair = bars + 11;    // leader: 16 warp arrivals (gates the pair's dK MMA)
+  uint64_t* dq_full = bars + 12;    // per CTA
+  uint64_t* dq_empty = bars + 13;   // leader: 8 warp arrivals (4 local + 4 remote)
+  uint64_t* dkdv_full = bars + 14;  // both (multicast)
+  uint64_t* stat_full = bars + 15;  // [2] per CTA: lse2 / delta of the stage landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S::kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+#ifdef NNOP_BWD_TRACE
+  const bool tr = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#endif
+
+  // ---- work assignment (identical trip counts in both CTAs) ------------------------------
+  const int j = blockIdx.x;          // this CTA's kv block
+  const int j0 = j & ~1;             // the pair's first block
+  const int k0 = j * 128;
+  const int hk = blockIdx.y, b = blockIdx.z;
+  const int QL = p.QL, KL = p.KL;
+  const int g = p.QH / p.KH;
+  const int bh_kv = b * p.KH + hk;
+  const int nq = (QL + 127) >> 7;
+  const int i0 = p.causal ? j0 : 0;
+  const int nqi = nq > i0 ? nq - i0 : 0;
+  const int n_it = nqi * g;
+  bool key_keep = true;
+  if (p.kpad) {
+    const int kr = k0 + (threadIdx.x & 127);
+    key_keep = kr < KL && p.kpad[static_cast<int64_t>(b) * p.KL + kr] != 0;
+  }
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("nnop: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_q64);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_do64);
+    tma_prefetch_desc(&tm_dqa);
+    mbar_init(kv_full, 1);
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    mbar_init(&q_empty[0], 1);
+    mbar_init(&q_empty[1], 1);
+    mbar_init(do_full, 1);
+    mbar_init(do_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 16);
+    mbar_init(dp_full, 1);
+    mbar_init(ds_local, 8);
+    mbar_init(ds_pair, 16);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 8);
+    mbar_init(dkdv_full, 1);
+    mbar_init(&stat_full[0], 1);
+    mbar_init(&stat_full[1], 1);
+    fence_mbar_init();
+  }
+  cluster_sync_all();  // barriers of both CTAs exist before any remote arrive / TMA completion
+  if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 256 + D;
+
+  if (warp < 4) {
+    setmaxnreg_dec<88>();
+    if (warp == 0 && lane == 0 && n_it > 0) {
+      // ================================ TMA producer (both CTAs) =====================
+      if (leader) mbar_arrive_expect_tx(kv_full, 4 * S::kTile);
+#pragma unroll
+      for (int bx = 0; bx < 2; ++bx) {
+        tma_load_3d_pair(sK + bx * S::kBox, &tm_k, kv_full, bx * 64, k0, bh_kv);
+        tma_load_3d_pair(sV + bx * S::kBox, &tm_v, kv_full, bx * 64, k0, bh_kv);
+      }
+      auto load_q = [&](int it) {
+        const int s = it & 1;
+        const int bh_q = b * p.QH + hk * g + it / nqi;
+        const int q0 = (i0 + it % nqi) * 128;
+        mbar_wait(&q_empty[s], ((it >> 1) & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(&q_full[s], 4 * S::kHalf);
+        // K-major half: q rows [64*rank, 64*rank+64), all of E (two 8 KB boxes)
+#pragma unroll
+        for (int bx = 0; bx < 2; ++bx)
+          tma_load_3d_pair(sQA + s * S::kHalf + bx * 8192, &tm_q64, &q_full[s], bx * 64,
+                           q0 + 64 * static_cast<int>(rank), bh_q);
+        // MN-major half: all 128 q rows, E columns [64*rank, 64*rank+64)
+        tma_load_3d_pair(sQB + s * S::kHalf, &tm_q, &q_full[s], 64 * static_cast<int>(rank), q0, bh_q);
+        const int64_t soff = static_cast<int64_t>(bh_q) * p.QLp + q0;
+        mbar_arrive_expect_tx(&stat_full[s], 1024);
+        bulk_load_1d(s_lse + s * 128, p.lse2p + soff, 512, &stat_full[s]);
+        bulk_load_1d(s_del + s * 128, p.deltap + soff, 512, &stat_full[s]);
+      };
+      auto load_do = [&](int it) {
+        const int bh_q = b * p.QH + hk * g + it / nqi;
+        const int q0 = (i0 + it % nqi) * 128;
+        mbar_wait(do_empty, (it & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(do_full, 4 * S::kHalf);
+#pragma unroll
+        for (int bx = 0; bx < 2; ++bx)
+          tma_load_3d_pair(sdOA + bx * 8192, &tm_do64, do_full, bx * 64, q0 + 64 * static_cast<int>(rank), bh_q);
+        tma_load_3d_pair(sdOB, &tm_do, do_full, 64 * static_cast<int>(rank), q0, bh_q);
+      };
+      load_q(0);
+      load_do(0);
+      if (n_it > 1) load_q(1);
+      for (int it = 1; it < n_it; ++it) {
+        load_do(it);
+        if (it + 1 < n_it) load_q(it + 1);
+      }
+    } else if (warp == 1 && n_it > 0) {
+      // ================================ MMA issuer ===================================
+      constexpr bool BF = is_bf16<T>::value;
+      constexpr uint32_t id2_kk = make_idesc_f16(256, 128, BF, false, false);  // S^T, dP^T (pair)
+      constexpr uint32_t id2_tv = make_idesc_f16(256, D, BF, false, true);     // dV, dK (pair)
+      constexpr uint32_t id_mm = make_idesc_f16(128, D, BF, true, true);       // dQ (per CTA)
+      const uint32_t tm = uniform_u32(tmem_base);
+      const uint32_t sbase = uniform_u32(smem_u32(smem));
+      const uint64_t kmaj = make_smem_desc_sw128(sbase, 16, 1024);
+      const uint64_t mnmaj = make_smem_desc_sw128(sbase, S::kBox, 1024);
+      const uint32_t k_lo = desc_lo(kmaj), k_hi = desc_hi(kmaj);
+      const uint32_t m_lo = desc_lo(mnmaj), m_hi = desc_hi(mnmaj);
+      auto dq_local = [&]() {   // dQ_i = dS K_j on this CTA's tensor core
+#ifdef NNOP_PAIR_NO_DQ
+        if (false) {
+#else
+        if (elect_one()) {
+#endif
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ss_lo(tm + kColDP, m_lo, (S::kdS + ks * 2048) >> 4, m_hi, m_lo, (S::kK + ks * 2048) >> 4,
+                       m_hi, id_mm, ks > 0 ? 1u : 0u);
+        }
+        if (elect_one()) tc_commit(dq_full);
+      };
+      if (leader) {
+        // D[256 x 128] = [A_cta0; A_cta1][256 x E] * B[128 x E]^T; B rows split 64 / 64 over the CTAs
+        auto mma_kk = [&](uint32_t dcol, uint32_t a0, uint32_t b0) {
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks) {
+              const uint32_t aoff = (ks >> 2) * S::kBox + (ks & 3) * 32;
+              const uint32_t boff = (ks >> 2) * 8192 + (ks & 3) * 32;
+              umma2_ss_lo(tm + dcol, k_lo, (a0 + aoff) >> 4, k_hi, k_lo, (b0 + boff) >> 4, k_hi, id2_kk,
+                          ks > 0 ? 1u : 0u);
+            }
+          }
+        };
+        auto commit = [&](uint64_t* bar) {
+          if (elect_one()) tc_commit_pair(bar);
+        };
+        mbar_wait_cluster(kv_full, 0);
+        mbar_wait_cluster(&q_full[0], 0);
+        tc_fence_after();
+        mma_kk(kColS, S::kK, S::kQA);
+        commit(s_full);
+        mbar_wait_cluster(do_full, 0);
+        tc_fence_after();
+        mma_kk(kColDP, S::kV, S::kdOA);
+        commit(dp_full);
+        for (int it = 0; it < n_it; ++it) {
+          const int s = it & 1;
+          const uint32_t acc = it > 0 ? 1u : 0u;
+          // dV += P^T dO_i  (B: 128 q x 64 d of each CTA, MN-major)
+          mbar_wait_cluster(p_full, it & 1);
+          tc_fence_after();
+          BWD_STAMP(it, 0);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma2_ts_lo(tm + kColDV, tm + kColS + (ks >> 2) * 64 + (ks & 3) * 8, m_lo,
+                          (S::kdOB + ks * 2048) >> 4, m_hi, id2_tv, (acc | (ks > 0)) ? 1u : 0u);
+          }
+          commit(do_empty);
+          if (it + 1 < n_it) {
+            mbar_wait_cluster(&q_full[s ^ 1], ((it + 1) >> 1) & 1);
+            tc_fence_after();
+            mma_kk(kColS, S::kK, S::kQA + static_cast<uint32_t>((s ^ 1) * S::kHalf));
+            commit(s_full);
+          }
+          // dQ_i (this CTA's share)
+          mbar_wait(ds_local, it & 1);
+          tc_fence_after();
+          dq_local();
+          // dK += dS^T Q_i  (A: dS^T K-major; B: 128 q x 64 d of each CTA, MN-major)
+          mbar_wait_cluster(ds_pair, it & 1);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t off = (ks >> 2) * S::kBox + (ks & 3) * 32;
+              umma2_ss_lo(tm + kColDK, k_lo, (S::kdS + off) >> 4, k_hi, m_lo,
+                          (S::kQB + s * S::kHalf + ks * 2048) >> 4, m_hi, id2_tv, (acc | (ks > 0)) ? 1u : 0u);
+            }
+          }
+          commit(&q_empty[s]);
+          // dP^T(i+1): its TMEM columns hold dQ_i of BOTH CTAs until their drain warpgroups read them
+          if (it + 1 < n_it) {
+            mbar_wait_cluster(do_full, (it + 1) & 1);
+            mbar_wait_cluster(dq_empty, it & 1);
+            tc_fence_after();
+            mma_kk(kColDP, S::kV, S::kdOA);
+            commit(dp_full);
+          }
+        }
+        commit(dkdv_full);
+      } else {
+        for (int it = 0; it < n_it; ++it) {
+          mbar_wait(ds_local, it & 1);
+          tc_fence_after();
+          dq_local();
+        }
+      }
+    }
+  } else if (warp < 12) {
+    // ================================ compute warpgroups ===============================
+    setmaxnreg_inc<136>();
+    const int half = (warp - 4) >> 2;  // which 64 q columns
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;    // key row within the block
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const int c0 = half * 64;
+    const float sl2 = p.scale_log2;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1;
+      const int i = i0 + it % nqi;
+      // ---- P^T ----
+      mbar_wait(&stat_full[s], (it >> 1) & 1);
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      uint32_t sr[2][32];
+      tmem_ld_x32(tmem_base + lane_off + kColS + c0, sr[0]);
+      tmem_ld_x32(tmem_base + lane_off + kColS + c0 + 32, sr[1]);
+      tmem_ld_wait();
+      float pf[64];
+      const float4* l4 = reinterpret_cast<const float4*>(s_lse + s * 128 + c0);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const float4 l = l4[u];
+        pf[4 * u + 0] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 0) & 31]), sl2, -l.x));
+        pf[4 * u + 1] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 1) & 31]), sl2, -l.y));
+        pf[4 * u + 2] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 2) & 31]), sl2, -l.z));
+        pf[4 * u + 3] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 3) & 31]), sl2, -l.w));
+      }
+      if (p.causal && i == j) {  // diagonal block: key k0+row is visible to query q0+c iff row <= c
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (row > c0 + c) pf[c] = 0.f;
+      }
+      if ((p.causal && i < j) || !key_keep) {  // the pair's first q block lies above CTA 1's diagonal
+#pragma unroll
+        for (int c = 0; c < 64; ++c) pf[c] = 0.f;
+      }
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) pk[c] = pack2<T>(pf[2 * c], pf[2 * c + 1]);
+        tmem_st_x32(tmem_base + lane_off + kColS + half * 64, pk);  // inside this half's own S^T columns
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(p_full, 0);
+      // ---- dS^T ----
+      mbar_wait(dp_full, it & 1);
+      tc_fence_after();
+      tmem_ld_x32(tmem_base + lane_off + kColDP + c0, sr[0]);
+      tmem_ld_x32(tmem_base + lane_off + kColDP + c0 + 32, sr[1]);
+      tmem_ld_wait();
+      const float4* d4 = reinterpret_cast<const float4*>(s_del + s * 128 + c0);
+      uint8_t* drow = sdS + half * S::kBox + row * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const float4 da = d4[2 * ch], db = d4[2 * ch + 1];
+        const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        float ds[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = 8 * ch + e;
+          ds[e] = pf[c] * (__uint_as_float(sr[c >> 5][c & 31]) - dl[e]);
+        }
+        uint4 v;
+        v.x = pack2<T>(ds[0], ds[1]);
+        v.y = pack2<T>(ds[2], ds[3]);
+        v.z = pack2<T>(ds[4], ds[5]);
+        v.w = pack2<T>(ds[6], ds[7]);
+        *reinterpret_cast<uint4*>(drow + ((ch ^ (row & 7)) << 4)) = v;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(ds_local);
+        mbar_arrive_cluster(ds_pair, 0);
+      }
+    }
+    // ---- epilogue: dV (half 0) / dK (half 1) -> 16-bit -> swizzled smem -> TMA store ------
+    if (n_it > 0) {
+      mbar_wait(dkdv_full, 0);
+      tc_fence_after();
+    }
+    {
+      const uint32_t tsrc = tmem_base + lane_off + (half ? kColDK : kColDV);
+      const float mul = half ? p.scale : 1.f;
+      uint8_t* stage = (half ? sQB : sQA);  // 32 KB each: the Q stages are free by now
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t r[32];
+        if (n_it > 0) {
+          tmem_ld_x32(tsrc + c * 32, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) r[x] = 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 v;
+          v.x = pack2<T>(__uint_as_float(r[8 * u + 0]) * mul, __uint_as_float(r[8 * u + 1]) * mul);
+          v.y = pack2<T>(__uint_as_float(r[8 * u + 2]) * mul, __uint_as_float(r[8 * u + 3]) * mul);
+          v.z = pack2<T>(__uint_as_float(r[8 * u + 4]) * mul, __uint_as_float(r[8 * u + 5]) * mul);
+          v.w = pack2<T>(__uint_as_float(r[8 * u + 6]) * mul, __uint_as_float(r[8 * u + 7]) * mul);
+          const int chunk = c * 4 + u;
+          const int bx = chunk >> 3, cin = chunk & 7;
+          *reinterpret_cast<uint4*>(stage + bx * S::kBox + row * 128 + ((cin ^ (row & 7)) << 4)) = v;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + half, 128);
+      if (wq == 0 && lane == 0) {
+#pragma unroll
+        for (int bx = 0; bx < 2; ++bx)
+          tma_store_3d(half ? &tm_dk : &tm_dv, stage + bx * S::kBox, bx * 64, k0, bh_kv);
+        bulk_commit();
+        bulk_wait_read<0>();
+      }
+    }
+  } else {
+    // ================================ dQ drain warpgroup ===============================
+    setmaxnreg_inc<152>();
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;  // query row within the block
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const bool issuer = (warp == 12 && lane == 0);
+    int nred = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int bh_q = b * p.QH + hk * g + it / nqi;
+      const int q0 = (i0 + it % nqi) * 128;
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      uint32_t r[D / 32][32];
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) tmem_ld_x32(tmem_base + lane_off + kColDP + c * 32, r[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(dq_empty, 0);
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint8_t* stage = sdQ + (nred & 1) * 16384;
+        if (issuer) bulk_wait_read<1>();
+        named_bar_sync(3, 128);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint4 v = make_uint4(r[c][4 * u], r[c][4 * u + 1], r[c][4 * u + 2], r[c][4 * u + 3]);
+          *reinterpret_cast<uint4*>(stage + row * 128 + ((u ^ (row & 7)) << 4)) = v;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (issuer) {
+          tma_reduce_add_3d(&tm_dqa, stage, c * 32, q0, bh_q);
+          bulk_commit();
+        }
+        ++nred;
+      }
+    }
+    if (issuer) bulk_wait<0>();
+  }
+
+  // ---- teardown: both CTAs must be done with the pair's TMEM before it is released ---------
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // prep: delta, lse2 (padded), zero dQ accumulator.  LPR lanes per row, one 16-byte vector each.
 // ---------------------------------------------------------------------------------------
@@ -678,8 +1159,6 @@ int launch_bwd(const AttnParams& a) {
   if (int rc = make_tmap_3d(&tdk, a.dk, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&tdv, a.dv, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&tdqa, dqa, NNOP_F32, D, rows_q, bhq, 32, 128)) return rc;
-  auto kern = attn_bwd_sm100_kernel<T, D>;
-  NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   BwdParams bp;
   bp.lse2p = lse2p; bp.deltap = deltap;
   bp.QL = a.QL; bp.KL = a.KL; bp.QH = a.QH; bp.KH = a.KH; bp.QLp = static_cast<int>(QLp);
@@ -687,11 +1166,31 @@ int launch_bwd(const AttnParams& a) {
   bp.scale = a.scale; bp.scale_log2 = a.scale * kLog2e;
   bp.cu_q = a.cu_q; bp.cu_k = a.cu_k; bp.dk_ptr = a.dk; bp.dv_ptr = a.dv; bp.total_k = a.total_k;
   bp.kpad = packed ? nullptr : a.kpad;
-  dim3 grid((a.KL + 127) / 128, a.KH, packed ? a.nseq : a.B);
-  timing_begin(1, a.stream);
-  kern<<<grid, kBwdThreads, S::kTotal, a.stream>>>(tq, tk, tv, tdo, tdk, tdv, tdqa, bp);
-  timing_end(1, a.stream);
-  NNOP_LAUNCH_CHECK();
+  const int nkv = (a.KL + 127) / 128;
+  bool use_pair = false;
+  if constexpr (D == 128) use_pair = !packed && nkv >= 2 && bwd_pair_mode() != 0;
+  if (use_pair) {
+    if constexpr (D == 128) {
+      alignas(64) CUtensorMap tq64, tdo64;
+      if (int rc = make_tmap_3d(&tq64, a.q, a.dtype, D, rows_q, bhq, 64, 64)) return rc;
+      if (int rc = make_tmap_3d(&tdo64, a.dO, a.dtype, D, rows_q, bhq, 64, 64)) return rc;
+      auto kern = attn_bwd_pair_kernel<T>;
+      NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::kTotal));
+      dim3 grid(2 * ((nkv + 1) / 2), a.KH, a.B);   // __cluster_dims__(2,1,1): blocks (2m, 2m+1) pair up
+      timing_begin(1, a.stream);
+      kern<<<grid, kBwdThreads, PairSmem::kTotal, a.stream>>>(tq, tq64, tk, tv, tdo, tdo64, tdk, tdv, tdqa, bp);
+      timing_end(1, a.stream);
+      NNOP_LAUNCH_CHECK();
+    }
+  } else {
+    auto kern = attn_bwd_sm100_kernel<T, D>;
+    NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    dim3 grid(nkv, a.KH, packed ? a.nseq : a.B);
+    timing_begin(1, a.stream);
+    kern<<<grid, kBwdThreads, S::kTotal, a.stream>>>(tq, tk, tv, tdo, tdk, tdv, tdqa, bp);
+    timing_end(1, a.stream);
+    NNOP_LAUNCH_CHECK();
+  }
   {
     const int64_t n8 = BH * rows_q * D / 8;
     attn_bwd_post_kernel<T><<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, a.stream>>>(
@@ -719,6 +1218,7 @@ extern "C" int nnop_debug_bwd_cta_log(long long* host_out, int max_ctas, int res
 #endif
 
 bool attn_sm100_bwd_available() { return true; }
+void attn_sm100_set_bwd_pair_mode(int mode) { g_bwd_pair_mode.store(mode); }
 
 size_t attn_sm100_bwd_workspace_bytes(int E, int QL, int QH, int B) {
   const size_t QLp = static_cast<size_t>((QL + 127) / 128) * 128;

@@ -396,6 +396,123 @@ __device__ __forceinline__ void umma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uin
 }
 
 // -------------------------------------------------------------------------------------
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): one M=256 MMA spans both CTAs' tensor cores; each
+// CTA supplies its own 128 rows of A and HALF of B (N/2 rows for K-major B, N/2 columns for
+// MN-major B) at the same shared-memory offset, so per CTA an SS MMA reads 6 KB instead of 8 KB
+// through the shared-memory port (scripts/micro/umma_2cta.cu).  Issued by the leader CTA (rank 0).
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// wait on a barrier that other CTAs of the cluster arrive on
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > NNOP_MBAR_TIMEOUT_CYCLES) {
+      printf("nnop: cluster mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS)
+               : "memory");
+}
+// TMA load whose completion bytes are counted on the LEADER CTA's barrier (same offset, peer bit cleared)
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                 int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+      "[%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives on the same-offset barrier in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void umma2_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t a_off,
+                                            uint32_t a_hi, uint32_t b_lo, uint32_t b_off,
+                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 la, lb;\n"
+      ".reg .b64 da, db;\n"
+      "add.u32 la, %1, %2;\n"
+      "add.u32 lb, %4, %5;\n"
+      "mov.b64 da, {la, %3};\n"
+      "mov.b64 db, {lb, %6};\n"
+      "setp.ne.b32 p, %8, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %7, {%9, %9, %9, %9, %9, %9, %9, %9}, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_off), "r"(a_hi), "r"(b_lo), "r"(b_off), "r"(b_hi), "r"(idesc),
+      "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
+                                            uint32_t b_off, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 lb;\n"
+      ".reg .b64 db;\n"
+      "add.u32 lb, %2, %3;\n"
+      "mov.b64 db, {lb, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %5, {%7, %7, %7, %7, %7, %7, %7, %7}, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_off), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+// -------------------------------------------------------------------------------------
 // tcgen05.ld / tcgen05.st, shape 32x32b: thread i of warp w touches TMEM lane 32*(w%4)+i,
 // N consecutive 32-bit columns starting at the address' column field.
 // -------------------------------------------------------------------------------------

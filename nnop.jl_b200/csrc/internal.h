@@ -83,6 +83,7 @@ bool attn_sm100_supported(const AttnParams& p, bool backward);
 int attn_sm100_fwd(const AttnParams& p);
 int attn_sm100_bwd(const AttnParams& p);
 bool attn_sm100_bwd_available();
+void attn_sm100_set_bwd_pair_mode(int mode);  // 0: single-CTA backward, 1: CTA pairs where eligible
 size_t attn_sm100_bwd_workspace_bytes(int E, int QL, int QH, int B);
 size_t attn_sm100_bwd_packed_workspace_bytes(int E, int64_t total_q, int nseq, int QH);
 

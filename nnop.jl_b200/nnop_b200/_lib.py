@@ -45,6 +45,7 @@ SIGNATURES = {
     "nnop_device_info": (_i, [_i, C.POINTER(DeviceInfo)]),
     "nnop_set_attention_path": (_i, [_i]),
     "nnop_last_attention_path": (_i, []),
+    "nnop_set_bwd_pair_mode": (_i, [_i]),
     "nnop_flash_attn_fwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, _vp]),
     "nnop_flash_attn_bwd_workspace_bytes": (_sz, [_i] * 7),
     "nnop_flash_attn_bwd": (_i, [_vp] * 12 + [_i] * 8 + [_f, _vp, _sz, _vp]),

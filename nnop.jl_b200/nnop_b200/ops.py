@@ -66,6 +66,11 @@ def last_attention_path() -> int:
     return lib.nnop_last_attention_path()
 
 
+def set_bwd_pair_mode(mode: int) -> None:
+    """0 (default): one CTA per kv block; 1: experimental CTA-pair backward (cta_group::2) for E = 128."""
+    check(lib.nnop_set_bwd_pair_mode(int(mode)))
+
+
 def selftest_umma(a: torch.Tensor, b: torch.Tensor, which: int) -> torch.Tensor:
     _req(a, b)
     out = torch.empty(128, 128, dtype=torch.float32, device=a.device)

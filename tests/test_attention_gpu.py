@@ -277,3 +277,26 @@ def test_full_size_properties_config_c2(nnop):
     assert max_abs(dq[b:b + 1, h:h + 1], rq) < H16_TOL
     assert max_abs(dk[b:b + 1, h:h + 1], rk) < H16_TOL * 2
     assert max_abs(dv[b:b + 1, h:h + 1], rv) < H16_TOL * 2
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_pair_backward_matches_single_cta(nnop, causal):
+    """The experimental CTA-pair backward (tcgen05 cta_group::2) must reproduce the default kernel:
+    dK / dV bit for bit, dQ up to the order of its fp32 atomics.  Fresh tensors on every trial:
+    cold pages once exposed a race between the two compute warpgroups on the P^T / S^T alias."""
+    try:
+        for trial, (B, QH, KH, QL, KL) in enumerate([(1, 1, 1, 512, 256), (2, 4, 2, 1024, 1024), (1, 2, 2, 300, 700),
+                                                     (1, 2, 1, 1000, 1000), (2, 2, 2, 640, 640), (1, 1, 1, 384, 256)] * 3):
+            if causal and QL != KL:
+                continue
+            q, k, v, dO, _, _ = _inputs(B, QH, KH, QL, KL, 128, torch.bfloat16, trial)
+            qd, kd, vd, dOd = q.cuda(), k.cuda(), v.cuda(), dO.cuda()
+            o, lse = nnop._flash_attention(qd, kd, vd, causal=causal)
+            nnop.set_bwd_pair_mode(0)
+            ref = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=causal)
+            nnop.set_bwd_pair_mode(1)
+            got = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=causal)
+            assert max_abs(got[0], ref[0]) <= 2 ** -7 * max(1.0, ref[0].abs().max().item())
+            assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
+    finally:
+        nnop.set_bwd_pair_mode(0)
