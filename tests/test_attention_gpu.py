@@ -300,3 +300,24 @@ def test_pair_backward_matches_single_cta(nnop, causal):
             assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
     finally:
         nnop.set_bwd_pair_mode(0)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_bitwise_repeatability_on_cold_buffers(nnop, causal):
+    """O, lse, dK and dV have a fixed summation order, so repeated runs must agree bit for bit -- also
+    when every run touches freshly allocated (cold) memory, which shifts the timing between the
+    warp-specialised roles.  (dQ is an fp32 atomic reduction: equal up to its last bits.)"""
+    B, QH, KH, L, E = 2, 4, 2, 1024, 128
+    q, k, v, dO, _, _ = _inputs(B, QH, KH, L, L, E, torch.bfloat16, 21)
+    keep, first = [], None
+    for trial in range(12):
+        qd, kd, vd, dOd = (x.clone().cuda() for x in (q, k, v, dO))   # new device buffers every time
+        keep.append((qd, kd, vd, dOd))
+        o, lse = nnop._flash_attention(qd, kd, vd, causal=causal)
+        dq, dk, dv, _ = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=causal)
+        if first is None:
+            first = (o, lse, dq, dk, dv)
+            continue
+        assert torch.equal(o, first[0]) and torch.equal(lse, first[1]), f"forward differs on run {trial}"
+        assert torch.equal(dk, first[3]) and torch.equal(dv, first[4]), f"dK/dV differ on run {trial}"
+        assert max_abs(dq, first[2]) <= 2 ** -7 * max(1.0, first[2].abs().max().item())
