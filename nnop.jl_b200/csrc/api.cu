@@ -133,10 +133,25 @@ extern "C" int nnop_set_bwd_pair_mode(int mode) {
   return NNOP_OK;
 }
 
+extern "C" size_t nnop_flash_attn_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH,
+                                                      int KH, int B) {
+  if (E <= 0 || QL <= 0 || KL <= 0 || QH <= 0 || KH <= 0 || B <= 0) return 0;
+  return attn_sm100_fwd_workspace_bytes(dtype, E, QL, KL, QH, KH, B);
+}
+
 extern "C" int nnop_flash_attn_fwd(void* o, float* lse, const void* q, const void* k, const void* v,
                                    const void* pair, const uint8_t* kpad_mask, int dtype, int E,
                                    int QL, int KL, int QH, int KH, int B, int causal, float scale,
                                    void* stream) {
+  return nnop_flash_attn_fwd_ws(o, lse, q, k, v, pair, kpad_mask, dtype, E, QL, KL, QH, KH, B, causal,
+                                scale, nullptr, 0, stream);
+}
+
+extern "C" int nnop_flash_attn_fwd_ws(void* o, float* lse, const void* q, const void* k,
+                                      const void* v, const void* pair, const uint8_t* kpad_mask,
+                                      int dtype, int E, int QL, int KL, int QH, int KH, int B,
+                                      int causal, float scale, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
   clear_error();
   if (int rc = validate(dtype, E, QL, KL, QH, KH, B)) return rc;
   if (static_cast<int64_t>(B) * QL == 0) return NNOP_OK;
@@ -146,6 +161,10 @@ extern "C" int nnop_flash_attn_fwd(void* o, float* lse, const void* q, const voi
   p.dtype = dtype; p.E = E; p.QL = QL; p.KL = KL; p.QH = QH; p.KH = KH; p.B = B;
   p.causal = causal ? 1 : 0; p.scale = scale;
   p.stream = static_cast<cudaStream_t>(stream);
+  if (workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && KL > 0 &&
+      workspace_bytes >= attn_sm100_fwd_workspace_bytes(dtype, E, QL, KL, QH, KH, B) &&
+      attn_sm100_fwd_workspace_bytes(dtype, E, QL, KL, QH, KH, B) > 0)
+    p.fwd_ws = workspace;  // enables the tensor-core Float32 forward (E = 64)
   const int mode = g_path_mode.load();
   const bool fast_ok = attn_sm100_supported(p, false);
   if (mode == 2 && !fast_ok)

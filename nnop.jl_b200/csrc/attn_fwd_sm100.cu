@@ -78,7 +78,13 @@ struct FwdSmem {
   static constexpr int kDynBytes = kTotal + 1024;  // slack for manual 1024-byte alignment
 };
 
-template <typename T, int D>
+// SPLIT = true is the Float32 (E = 64) path: every fp32 operand x arrives as two bf16 terms
+// [hi | lo] side by side in a 128-wide row (x ~ hi + lo, 16 mantissa bits; written by
+// split_f32_kernel), S = Qh Kh^T + Qh Kl^T + Ql Kh^T is three chained MMAs, P is split in registers
+// into Ph + Pl (two TMEM operands), O' = (Ph + Pl) [Vh | Vl] accumulates both V terms side by side
+// and the epilogue adds the two halves and writes fp32.  Same tiles, barriers and shared-memory /
+// TMEM footprint as the bf16 E = 128 kernel; 1.75x its tensor time for half its FLOPs.
+template <typename T, int D, bool SPLIT = false>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
                       const __grid_constant__ CUtensorMap tm_k,
@@ -228,10 +234,22 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         const uint64_t b0 = dk0 + static_cast<uint64_t>(((slot % kNStage) * S::kTileBytes) >> 4);
         const uint32_t d = tm + t * 128;
         if (elect_one()) {
+          if constexpr (SPLIT) {
+            // box 0 = hi terms, box 1 = lo terms: hi*hi, hi*lo, lo*hi (lo*lo is below fp32 rounding)
 #pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks) {
-            const uint32_t off = ((ks >> 2) * S::kBoxBytes + (ks & 3) * 32) >> 4;
-            umma_ss(d, a0 + off, b0 + off, idesc_qk, ks > 0 ? 1u : 0u);
+            for (int part = 0; part < 3; ++part)
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint32_t aoff = ((part == 2 ? S::kBoxBytes : 0) + k4 * 32) >> 4;
+                const uint32_t boff = ((part == 1 ? S::kBoxBytes : 0) + k4 * 32) >> 4;
+                umma_ss(d, a0 + aoff, b0 + boff, idesc_qk, (part | k4) ? 1u : 0u);
+              }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks) {
+              const uint32_t off = ((ks >> 2) * S::kBoxBytes + (ks & 3) * 32) >> 4;
+              umma_ss(d, a0 + off, b0 + off, idesc_qk, ks > 0 ? 1u : 0u);
+            }
           }
         }
       };
@@ -255,8 +273,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         const uint32_t a = tm + t * 128;  // P aliases S columns [0, 64)
         if (elect_one()) {
 #pragma unroll
-          for (int j = 4 * hf; j < 4 * hf + 4; ++j)
+          for (int j = 4 * hf; j < 4 * hf + 4; ++j) {
             umma_ts(d, a + j * 8, b0 + ((j * 2048) >> 4), idesc_pv, (acc || j > 0) ? 1u : 0u);
+            if constexpr (SPLIT)  // the low term of P (S columns 64..) against the same [Vh | Vl] rows
+              umma_ts(d, a + 64 + j * 8, b0 + ((j * 2048) >> 4), idesc_pv, 1u);
+          }
         }
       };
       auto commit = [&](uint64_t* bar) {
@@ -449,6 +470,14 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
             pr[j] = pack2<T>(pf[2 * j], pf[2 * j + 1]);
           }
           tmem_st_x16(tS + c * 16, pr);
+          if constexpr (SPLIT) {  // low term: p - bf16(p), also 16-bit
+            uint32_t plo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              plo[j] = pack2<T>(pf[2 * j] - __uint_as_float(pr[j] << 16),
+                                pf[2 * j + 1] - __uint_as_float(pr[j] & 0xffff0000u));
+            tmem_st_x16(tS + 64 + c * 16, plo);
+          }
           if (kSplitPV ? (c & 1) : (c == 3)) {  // (half of) the keys are in TMEM: release the tensor pipe
             tmem_st_wait();
             tc_fence_before();
@@ -467,6 +496,26 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       tc_fence_after();
       const float inv_l = l > 0.f ? 1.f / l : 0.f;
       uint8_t* stage = sQ + t * S::kTileBytes;
+      if constexpr (SPLIT) {
+        // O'[:, 0:64] = P Vh, O'[:, 64:128] = P Vl: add them, normalise, stage as fp32 (two boxes of
+        // 32 floats x 128 rows, same 128-byte swizzle) for the fp32 TMA store
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ohi[32], olo[32];
+          tmem_ld_x32(tO + c * 32, ohi);
+          tmem_ld_x32(tO + 64 + c * 32, olo);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 v;
+            v.x = (__uint_as_float(ohi[4 * u + 0]) + __uint_as_float(olo[4 * u + 0])) * inv_l;
+            v.y = (__uint_as_float(ohi[4 * u + 1]) + __uint_as_float(olo[4 * u + 1])) * inv_l;
+            v.z = (__uint_as_float(ohi[4 * u + 2]) + __uint_as_float(olo[4 * u + 2])) * inv_l;
+            v.w = (__uint_as_float(ohi[4 * u + 3]) + __uint_as_float(olo[4 * u + 3])) * inv_l;
+            *reinterpret_cast<float4*>(stage + c * S::kBoxBytes + row * 128 + ((u ^ (row & 7)) << 4)) = v;
+          }
+        }
+      } else {
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
         uint32_t orow[32];
@@ -483,6 +532,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           const int bx = chunk >> 3, cin = chunk & 7;
           *reinterpret_cast<uint4*>(stage + bx * S::kBoxBytes + row * 128 + ((cin ^ (row & 7)) << 4)) = v;
         }
+      }
       }
       if (q_row < QL) {
         const int64_t li = packed ? static_cast<int64_t>(h) * p.total_q + q_off + q_row
@@ -511,7 +561,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         if (wq == 0 && lane == 0) {
 #pragma unroll
           for (int bx = 0; bx < S::kNBox; ++bx)
-            tma_store_3d(&tm_o, stage + bx * S::kBoxBytes, bx * 64, q_off + q0 + t * 128, bh_q);
+            tma_store_3d(&tm_o, stage + bx * S::kBoxBytes, bx * (SPLIT ? 32 : 64), q_off + q0 + t * 128, bh_q);
           bulk_commit();
           bulk_wait_read<0>();
         }
@@ -537,6 +587,64 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
+}
+
+// x (rows, 64) fp32 -> (rows, 128) bf16 = [hi(64) | lo(64)], hi = bf16(x), lo = bf16(x - hi)
+__global__ void __launch_bounds__(256)
+split_f32_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ in, int64_t n4) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;  // one float4 per thread
+  if (i >= n4) return;
+  const float4 x = reinterpret_cast<const float4*>(in)[i];
+  const int64_t row = i >> 4;          // 16 float4 per 64-float row
+  const int c4 = static_cast<int>(i & 15);
+  const uint32_t h0 = pack2<__nv_bfloat16>(x.x, x.y), h1 = pack2<__nv_bfloat16>(x.z, x.w);
+  const uint32_t l0 = pack2<__nv_bfloat16>(x.x - __uint_as_float(h0 << 16), x.y - __uint_as_float(h0 & 0xffff0000u));
+  const uint32_t l1 = pack2<__nv_bfloat16>(x.z - __uint_as_float(h1 << 16), x.w - __uint_as_float(h1 & 0xffff0000u));
+  uint2* o = reinterpret_cast<uint2*>(out + row * 128);
+  o[c4] = make_uint2(h0, h1);
+  o[16 + c4] = make_uint2(l0, l1);
+}
+
+int launch_split(__nv_bfloat16* out, const void* in, int64_t rows, cudaStream_t st) {
+  const int64_t n4 = rows * 16;
+  if (n4 == 0) return NNOP_OK;
+  split_f32_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(out, static_cast<const float*>(in), n4);
+  NNOP_LAUNCH_CHECK();
+  return NNOP_OK;
+}
+
+// Float32, E = 64: split q, k, v into [hi | lo] bf16 rows in the workspace, then the SPLIT kernel
+int launch_fwd_f32(const AttnParams& a) {
+  using T = __nv_bfloat16;
+  constexpr int D = 128;
+  using S = FwdSmem<D>;
+  const int64_t rq = static_cast<int64_t>(a.B) * a.QH * a.QL, rk = static_cast<int64_t>(a.B) * a.KH * a.KL;
+  T* qs = static_cast<T*>(a.fwd_ws);
+  T* ks = qs + rq * 128;
+  T* vs = ks + rk * 128;
+  if (int rc = launch_split(qs, a.q, rq, a.stream)) return rc;
+  if (int rc = launch_split(ks, a.k, rk, a.stream)) return rc;
+  if (int rc = launch_split(vs, a.v, rk, a.stream)) return rc;
+  alignas(64) CUtensorMap tq, tk, tv, to;
+  const uint64_t bhq = static_cast<uint64_t>(a.B) * a.QH, bhk = static_cast<uint64_t>(a.B) * a.KH;
+  if (int rc = make_tmap_3d(&tq, qs, NNOP_BF16, D, a.QL, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tk, ks, NNOP_BF16, D, a.KL, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tv, vs, NNOP_BF16, D, a.KL, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&to, a.o, NNOP_F32, 64, a.QL, bhq, 32, 128)) return rc;
+  auto kern = attn_fwd_sm100_kernel<T, D, true>;
+  NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynBytes));
+  FwdParams fp;
+  fp.lse = a.lse;
+  fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
+  fp.scale_log2 = a.scale * kLog2e;
+  fp.cu_q = nullptr; fp.cu_k = nullptr; fp.o_ptr = a.o; fp.total_q = 0;
+  fp.kpad = a.kpad;
+  dim3 grid((a.QL + 255) / 256, a.QH, a.B);
+  timing_begin(0, a.stream);
+  kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, fp);
+  timing_end(0, a.stream);
+  NNOP_LAUNCH_CHECK();
+  return NNOP_OK;
 }
 
 template <typename T, int D>
@@ -579,7 +687,8 @@ extern "C" int nnop_debug_fwd_trace(long long* host_out, int n) {
 
 bool attn_sm100_supported(const AttnParams& a, bool backward) {
   if (backward && !attn_sm100_bwd_available()) return false;
-  if (a.dtype != NNOP_F16 && a.dtype != NNOP_BF16) return false;
+  const bool f32_split = a.dtype == NNOP_F32 && a.E == 64 && !backward && a.fwd_ws != nullptr && !a.cu_q;
+  if (a.dtype != NNOP_F16 && a.dtype != NNOP_BF16 && !f32_split) return false;
   if (a.E != 64 && a.E != 128) return false;
   if (a.pair) return false;  // the additive bias is served by the generic path
   if (a.QL < 1 || a.KL < 1) return false;
@@ -590,7 +699,13 @@ bool attn_sm100_supported(const AttnParams& a, bool backward) {
   return true;
 }
 
+size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B) {
+  if (dtype != NNOP_F32 || E != 64) return 0;
+  return (static_cast<size_t>(B) * QH * QL + 2 * static_cast<size_t>(B) * KH * KL) * 128 * 2;
+}
+
 int attn_sm100_fwd(const AttnParams& a) {
+  if (a.dtype == NNOP_F32) return launch_fwd_f32(a);
   if (a.dtype == NNOP_BF16)
     return a.E == 128 ? launch_fwd<__nv_bfloat16, 128>(a) : launch_fwd<__nv_bfloat16, 64>(a);
   return a.E == 128 ? launch_fwd<__half, 128>(a) : launch_fwd<__half, 64>(a);

@@ -66,6 +66,8 @@ struct AttnParams {
   const int* cu_k;
   int nseq;
   int64_t total_q, total_k;
+  // forward workspace (nnop_flash_attn_fwd_ws): [hi | lo] bf16 copies of q, k, v for the Float32 path
+  void* fwd_ws;
 };
 
 // one-shot timing hook (api.cu); which: 0 forward kernel, 1 backward main kernel
@@ -81,6 +83,7 @@ int attn_bwd_preprocess(const AttnParams& p);
 // attn_fwd_sm100.cu / attn_bwd_sm100.cu -- tcgen05 + TMA path (bf16/f16, E in {64,128})
 bool attn_sm100_supported(const AttnParams& p, bool backward);
 int attn_sm100_fwd(const AttnParams& p);
+size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B);
 int attn_sm100_bwd(const AttnParams& p);
 bool attn_sm100_bwd_available();
 void attn_sm100_set_bwd_pair_mode(int mode);  // 0: single-CTA backward, 1: CTA pairs where eligible

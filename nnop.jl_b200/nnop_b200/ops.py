@@ -111,9 +111,11 @@ def _flash_attention(q, k, v, pair=None, *, causal: bool, kpad_mask=None):
     o = torch.empty_like(q)
     lse = torch.empty((B, QH, QL), dtype=torch.float32, device=q.device)
     scale = 1.0 / math.sqrt(E)
-    check(lib.nnop_flash_attn_fwd(_p(o), _p(lse), _p(q), _p(k), _p(v), _p(pair), _p(kpad_mask),
-                                  _dt(q), E, QL, KL, QH, KH, B, int(bool(causal)), scale,
-                                  _stream()))
+    ws_bytes = lib.nnop_flash_attn_fwd_workspace_bytes(_dt(q), E, QL, KL, QH, KH, B) if pair is None else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if ws_bytes else None
+    check(lib.nnop_flash_attn_fwd_ws(_p(o), _p(lse), _p(q), _p(k), _p(v), _p(pair), _p(kpad_mask),
+                                     _dt(q), E, QL, KL, QH, KH, B, int(bool(causal)), scale,
+                                     _p(ws), ws_bytes, _stream()))
     return o, lse
 
 

@@ -68,7 +68,8 @@ def test_noncausal_reference_grid(nnop, E, use_pair, use_padmask):
     for QL in LS:
         for KL in LS:
             q, k, v, dO, pr, m = _inputs(3, 2, 2, QL, KL, E, torch.float32, QL * 7 + KL, use_pair, use_padmask)
-            _check(nnop, q, k, v, dO, pr, m, False, F32_TOL, expect_path=0)
+            # Float32 E = 64 without a pair bias takes the split-bf16 tensor-core forward
+            _check(nnop, q, k, v, dO, pr, m, False, F32_TOL, expect_path=int(E == 64 and not use_pair))
 
 
 @pytest.mark.parametrize("E", [16, 32, 64])
@@ -77,7 +78,7 @@ def test_noncausal_reference_grid(nnop, E, use_pair, use_padmask):
 def test_causal_reference_grid(nnop, E, use_pair, use_padmask):
     for L in LS:
         q, k, v, dO, pr, m = _inputs(3, 2, 2, L, L, E, torch.float32, L, use_pair, use_padmask)
-        _check(nnop, q, k, v, dO, pr, m, True, F32_TOL, expect_path=0)
+        _check(nnop, q, k, v, dO, pr, m, True, F32_TOL, expect_path=int(E == 64 and not use_pair))
 
 
 @pytest.mark.parametrize("QH", [4, 6, 8])
@@ -87,7 +88,7 @@ def test_gqa_reference_grid(nnop, QH, KVH, causal):
     for E in (32, 64):
         for L in (255, 256, 257, 512):
             q, k, v, dO, pr, m = _inputs(2, QH, KVH, L, L, E, torch.float32, L + QH)
-            _check(nnop, q, k, v, dO, pr, m, causal, F32_TOL, expect_path=0)
+            _check(nnop, q, k, v, dO, pr, m, causal, F32_TOL, expect_path=int(E == 64))
 
 
 def test_attention_golden(nnop):
@@ -321,3 +322,26 @@ def test_bitwise_repeatability_on_cold_buffers(nnop, causal):
         assert torch.equal(o, first[0]) and torch.equal(lse, first[1]), f"forward differs on run {trial}"
         assert torch.equal(dk, first[3]) and torch.equal(dv, first[4]), f"dK/dV differ on run {trial}"
         assert max_abs(dq, first[2]) <= 2 ** -7 * max(1.0, first[2].abs().max().item())
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_f32_tensor_core_forward_vs_simt_and_oracle(nnop, causal):
+    """Float32 E = 64 forward on the tensor cores (operands split into two bf16 terms, fp32
+    accumulation; README config C1 family): within BASELINE.json's 1e-4 of the fp64 oracle, and
+    close to the SIMT fp32 path, on the reference's ragged lengths, with GQA and a key padding mask."""
+    for (B, QH, KH, QL, KL) in [(2, 4, 4, 1024, 1024), (1, 4, 2, 255, 511), (2, 6, 2, 513, 513), (1, 2, 2, 4096, 4096)]:
+        if causal and QL != KL:
+            continue
+        q, k, v, _, _, m = _inputs(B, QH, KH, QL, KL, 64, torch.float32, QL + 3, mask=True)
+        qd, kd, vd, md = q.cuda(), k.cuda(), v.cuda(), m.cuda()
+        o, lse = nnop._flash_attention(qd, kd, vd, causal=causal, kpad_mask=md)
+        assert nnop.last_attention_path() == 1
+        ro, rl = O.naive_attention(q.double(), k.double(), v.double(), causal=causal, kpad_mask=m, return_lse=True)
+        assert max_abs(o, ro) < F32_TOL and max_abs(lse, rl) < F32_TOL
+        try:
+            nnop.set_attention_path(1)
+            o_s, lse_s = nnop._flash_attention(qd, kd, vd, causal=causal, kpad_mask=md)
+            assert nnop.last_attention_path() == 0
+        finally:
+            nnop.set_attention_path(0)
+        assert max_abs(o, o_s) < F32_TOL and max_abs(lse, lse_s) < F32_TOL
