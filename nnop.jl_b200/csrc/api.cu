@@ -179,11 +179,15 @@ extern "C" int nnop_flash_attn_fwd_ws(void* o, float* lse, const void* q, const 
 
 extern "C" size_t nnop_flash_attn_bwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH,
                                                       int KH, int B) {
-  (void)dtype; (void)KL; (void)KH;
   if (E <= 0 || QL <= 0 || QH <= 0 || B <= 0) return 0;
   // delta (B,QH,QL) fp32, 256-byte aligned, then the fp32 dQ accumulator of the tcgen05 path
   size_t delta = (static_cast<size_t>(B) * QH * QL * sizeof(float) + 255) & ~static_cast<size_t>(255);
-  return delta + attn_sm100_bwd_workspace_bytes(E, QL, QH, B);
+  size_t rest = attn_sm100_bwd_workspace_bytes(E, QL, QH, B);
+  if (dtype == NNOP_F32 && E == 64 && KL > 0 && KH > 0) {  // split-bf16 copies of q, k, v, dO (tensor-core Float32 path)
+    const size_t f32 = attn_f32_bwd_workspace_bytes(QL, KL, QH, KH, B);
+    if (f32 > rest) rest = f32;
+  }
+  return delta + rest;
 }
 
 extern "C" int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, const void* dO,
@@ -216,11 +220,19 @@ extern "C" int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, co
   p.causal = causal ? 1 : 0; p.scale = scale;
   p.stream = static_cast<cudaStream_t>(stream);
   const int mode = g_path_mode.load();
-  const bool fast_ok = attn_sm100_supported(p, true);
+  // Float32, E = 64, no pair bias: split-bf16 tensor-core backward (attn_bwd_f32_sm100.cu)
+  const bool al16 = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+                      reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dO) |
+                      reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
+                      reinterpret_cast<uintptr_t>(dv)) & 15) == 0;
+  const bool f32_tc = dtype == NNOP_F32 && E == 64 && !pair && QL > 0 && KL > 0 && al16 &&
+                      QH <= 65535 && B <= 65535;
+  const bool fast_ok = f32_tc || attn_sm100_supported(p, true);
   if (mode == 2 && !fast_ok)
     return fail(NNOP_ERR_ARG, "tcgen05 attention path required but the problem does not qualify");
   if (fast_ok && mode != 1) {
     g_last_path = 1;
+    if (f32_tc) return attn_f32_bwd(p);
     return attn_sm100_bwd(p);  // runs its own preprocess (delta, lse2, dQ accumulator zeroing)
   }
   g_last_path = 0;

@@ -78,8 +78,8 @@ struct FwdSmem {
   static constexpr int kDynBytes = kTotal + 1024;  // slack for manual 1024-byte alignment
 };
 
-// SPLIT = true is the Float32 (E = 64) path: every fp32 operand x arrives as two bf16 terms
-// [hi | lo] side by side in a 128-wide row (x ~ hi + lo, 16 mantissa bits; written by
+// SPLIT = true is the Float32 (E = 64) path: every fp32 operand x arrives as two fp16 terms
+// [hi | lo] side by side in a 128-wide row (x ~ hi + lo, 22 significant bits; written by
 // split_f32_kernel), S = Qh Kh^T + Qh Kl^T + Ql Kh^T is three chained MMAs, P is split in registers
 // into Ph + Pl (two TMEM operands), O' = (Ph + Pl) [Vh | Vl] accumulates both V terms side by side
 // and the epilogue adds the two halves and writes fp32.  Same tiles, barriers and shared-memory /
@@ -474,8 +474,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
             uint32_t plo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              plo[j] = pack2<T>(pf[2 * j] - __uint_as_float(pr[j] << 16),
-                                pf[2 * j + 1] - __uint_as_float(pr[j] & 0xffff0000u));
+              plo[j] = pack2<T>(pf[2 * j] - unpack_lo<T>(pr[j]), pf[2 * j + 1] - unpack_hi<T>(pr[j]));
             tmem_st_x16(tS + 64 + c * 16, plo);
           }
           if (kSplitPV ? (c & 1) : (c == 3)) {  // (half of) the keys are in TMEM: release the tensor pipe
@@ -589,23 +588,26 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   }
 }
 
-// x (rows, 64) fp32 -> (rows, 128) bf16 = [hi(64) | lo(64)], hi = bf16(x), lo = bf16(x - hi)
+// x (rows, 64) fp32 -> (rows, 128) fp16 = [hi(64) | lo(64)], hi = fp16(x), lo = fp16(x - hi): 22
+// significant bits (bf16 terms would give 16, not enough for 1e-4 absolute on gradients of
+// magnitude ~5).  |x| must stay below 65504 -- the reference itself stages Q and K as Float16 in
+// its backward (src/attention_bwd.jl:19-20).
 __global__ void __launch_bounds__(256)
-split_f32_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ in, int64_t n4) {
+split_f32_kernel(__half* __restrict__ out, const float* __restrict__ in, int64_t n4) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;  // one float4 per thread
   if (i >= n4) return;
   const float4 x = reinterpret_cast<const float4*>(in)[i];
   const int64_t row = i >> 4;          // 16 float4 per 64-float row
   const int c4 = static_cast<int>(i & 15);
-  const uint32_t h0 = pack2<__nv_bfloat16>(x.x, x.y), h1 = pack2<__nv_bfloat16>(x.z, x.w);
-  const uint32_t l0 = pack2<__nv_bfloat16>(x.x - __uint_as_float(h0 << 16), x.y - __uint_as_float(h0 & 0xffff0000u));
-  const uint32_t l1 = pack2<__nv_bfloat16>(x.z - __uint_as_float(h1 << 16), x.w - __uint_as_float(h1 & 0xffff0000u));
+  const uint32_t h0 = pack2<__half>(x.x, x.y), h1 = pack2<__half>(x.z, x.w);
+  const uint32_t l0 = pack2<__half>(x.x - unpack_lo<__half>(h0), x.y - unpack_hi<__half>(h0));
+  const uint32_t l1 = pack2<__half>(x.z - unpack_lo<__half>(h1), x.w - unpack_hi<__half>(h1));
   uint2* o = reinterpret_cast<uint2*>(out + row * 128);
   o[c4] = make_uint2(h0, h1);
   o[16 + c4] = make_uint2(l0, l1);
 }
 
-int launch_split(__nv_bfloat16* out, const void* in, int64_t rows, cudaStream_t st) {
+int launch_split(__half* out, const void* in, int64_t rows, cudaStream_t st) {
   const int64_t n4 = rows * 16;
   if (n4 == 0) return NNOP_OK;
   split_f32_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(out, static_cast<const float*>(in), n4);
@@ -615,7 +617,7 @@ int launch_split(__nv_bfloat16* out, const void* in, int64_t rows, cudaStream_t 
 
 // Float32, E = 64: split q, k, v into [hi | lo] bf16 rows in the workspace, then the SPLIT kernel
 int launch_fwd_f32(const AttnParams& a) {
-  using T = __nv_bfloat16;
+  using T = __half;
   constexpr int D = 128;
   using S = FwdSmem<D>;
   const int64_t rq = static_cast<int64_t>(a.B) * a.QH * a.QL, rk = static_cast<int64_t>(a.B) * a.KH * a.KL;
@@ -627,9 +629,9 @@ int launch_fwd_f32(const AttnParams& a) {
   if (int rc = launch_split(vs, a.v, rk, a.stream)) return rc;
   alignas(64) CUtensorMap tq, tk, tv, to;
   const uint64_t bhq = static_cast<uint64_t>(a.B) * a.QH, bhk = static_cast<uint64_t>(a.B) * a.KH;
-  if (int rc = make_tmap_3d(&tq, qs, NNOP_BF16, D, a.QL, bhq, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tk, ks, NNOP_BF16, D, a.KL, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tv, vs, NNOP_BF16, D, a.KL, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tq, qs, NNOP_F16, D, a.QL, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tk, ks, NNOP_F16, D, a.KL, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tv, vs, NNOP_F16, D, a.KL, bhk, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&to, a.o, NNOP_F32, 64, a.QL, bhq, 32, 128)) return rc;
   auto kern = attn_fwd_sm100_kernel<T, D, true>;
   NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynBytes));
@@ -697,6 +699,10 @@ bool attn_sm100_supported(const AttnParams& a, bool backward) {
   if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.o)) return false;
   if (backward && (!al(a.dq) || !al(a.dk) || !al(a.dv) || !al(a.dO))) return false;
   return true;
+}
+
+int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, cudaStream_t st) {
+  return launch_split(static_cast<__half*>(out_bf16x2), in_f32, rows, st);
 }
 
 size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B) {

@@ -74,6 +74,24 @@ __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
   return r;
 }
 
+// the two 16-bit elements of a packed register back as floats (lo = first element)
+template <typename T>
+__device__ __forceinline__ float unpack_lo(uint32_t v);
+template <typename T>
+__device__ __forceinline__ float unpack_hi(uint32_t v);
+template <>
+__device__ __forceinline__ float unpack_lo<__nv_bfloat16>(uint32_t v) { return __uint_as_float(v << 16); }
+template <>
+__device__ __forceinline__ float unpack_hi<__nv_bfloat16>(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+template <>
+__device__ __forceinline__ float unpack_lo<__half>(uint32_t v) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xffffu)));
+}
+template <>
+__device__ __forceinline__ float unpack_hi<__half>(uint32_t v) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16)));
+}
+
 // -------------------------------------------------------------------------------------
 // packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100: two lanes per issue slot) and a
 // software exp2 that runs on the FMA/ALU pipes, used to take load off the MUFU (XU) pipe

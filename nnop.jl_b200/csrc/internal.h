@@ -84,6 +84,11 @@ int attn_bwd_preprocess(const AttnParams& p);
 bool attn_sm100_supported(const AttnParams& p, bool backward);
 int attn_sm100_fwd(const AttnParams& p);
 size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B);
+// (rows, 64) fp32 -> (rows, 128) bf16 rows [hi(64) | lo(64)] with x ~ hi + lo (Float32 tensor-core path)
+int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, cudaStream_t st);
+// attn_bwd_f32_sm100.cu -- Float32 (E = 64) backward on the tensor cores (split-bf16 operands)
+size_t attn_f32_bwd_workspace_bytes(int QL, int KL, int QH, int KH, int B);
+int attn_f32_bwd(const AttnParams& p);
 int attn_sm100_bwd(const AttnParams& p);
 bool attn_sm100_bwd_available();
 void attn_sm100_set_bwd_pair_mode(int mode);  // 0: single-CTA backward, 1: CTA pairs where eligible
