@@ -92,7 +92,7 @@ int nnop_flash_attn_fwd(void* o, float* lse, const void* q, const void* k, const
  * nnop_flash_attn_fwd_workspace_bytes(...) bytes (256-byte aligned), Float32 problems with E = 64
  * and no `pair` run on the tensor cores: q, k, v are split into two bf16 terms each (x ~ hi + lo,
  * 16 mantissa bits), S = Qh Kh^T + Qh Kl^T + Ql Kh^T and O = (Ph + Pl)(Vh + Vl) accumulate in fp32;
- * max abs error vs the fp64 oracle stays below 1e-4.  Without it (or for other shapes) the call
+ * max abs error vs an fp64 evaluation stays below 1e-4.  Without it (or for other shapes) the call
  * is identical to nnop_flash_attn_fwd.  The size query returns 0 where no workspace is used. */
 size_t nnop_flash_attn_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B);
 int nnop_flash_attn_fwd_ws(void* o, float* lse, const void* q, const void* k, const void* v,

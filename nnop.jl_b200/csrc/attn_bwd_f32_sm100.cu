@@ -15,7 +15,7 @@
 //    dK' += (dSh + dSl)^T [Qh | Ql]                          16                  -> TMEM [384,512)
 // X' = [X.h-part | X.l-part] accumulates both terms of the second operand side by side (N = 128); the
 // consumer adds the two 64-column halves.  fp32 accumulation throughout; measured max abs error vs
-// the fp64 oracle ~1e-6 (tolerance 1e-4).  fp16 terms bound the inputs to |x| < 65504, as the
+// an fp64 evaluation ~1e-6 (tolerance 1e-4).  fp16 terms bound the inputs to |x| < 65504, as the
 // reference's own Float16 staging of Q and K does (src/attention_bwd.jl:19-20).  Shared memory is full (two dS tiles), so Q_i and dO_i are
 // single-buffered and S^T(i+1) is issued after dK(i): slower per FLOP than the 16-bit kernel, still
 // an order of magnitude faster than the fp32 SIMT path.  Dense layout, kpad_mask, GQA, ragged sizes.
