@@ -50,11 +50,16 @@ function _flash_attention(
 
     o = similar(q)
     lse = CUDA.zeros(Float32, QL, QH, B)
-    check(ccall((:nnop_flash_attn_fwd, libnnop_b200), Cint,
+    # optional workspace: lets Float32 (E = 64, no pair) run on the tensor cores (split fp16 operands)
+    nbytes = isnothing(pair) ? ccall((:nnop_flash_attn_fwd_workspace_bytes, libnnop_b200), Csize_t,
+        (Cint, Cint, Cint, Cint, Cint, Cint, Cint), dtype_code(T), QE, QL, KL, QH, KH, B) : Csize_t(0)
+    ws = nbytes > 0 ? CuArray{UInt8}(undef, nbytes) : nothing
+    check(ccall((:nnop_flash_attn_fwd_ws, libnnop_b200), Cint,
         (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
-         Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cfloat, Ptr{Cvoid}),
+         Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cfloat, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
         ptr(o), ptr(lse), ptr(q), ptr(k), ptr(v), ptr(pair), ptr(kpad_mask),
-        dtype_code(T), QE, QL, KL, QH, KH, B, causal, Float32(inv(sqrt(QE))), stream()))
+        dtype_code(T), QE, QL, KL, QH, KH, B, causal, Float32(inv(sqrt(QE))), ptr(ws), nbytes, stream()))
+    isnothing(ws) || CUDA.unsafe_free!(ws)
     return o, lse, nothing
 end
 
