@@ -27,6 +27,10 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr float kLog2e = 1.4426950408889634f;
+// dK' / dV' live in fp32 TMEM accumulators whose additions are not round-to-nearest (measured bias
+// ~2^-25 of the accumulator per MMA).  Every kFlushEvery q blocks (16 MMAs each) the drain warpgroup
+// moves them out with exact fp32 reduce-adds into dk / dv and the accumulation restarts from zero.
+constexpr int kFlushEvery = 4;
 using T = __half;
 
 struct Params {
@@ -49,7 +53,7 @@ struct Smem {
   static constexpr int kStage = kdSl + kTile;  // 128 rows x 64 fp32 (two boxes of 32 floats)
   static constexpr int kStat = kStage + kTile; // lse2[128], delta[128]
   static constexpr int kBar = kStat + 1024;
-  static constexpr int kNumBars = 12;
+  static constexpr int kNumBars = 14;
   static constexpr int kTotal = kBar + kNumBars * 8 + 16;
 };
 
@@ -85,6 +89,8 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* dq_full = bars + 9;
   uint64_t* dq_empty = bars + 10;
   uint64_t* dkdv_full = bars + 11;
+  uint64_t* flush_full = bars + 12;   // MMA -> drain: accumulators of the last kFlushEvery steps complete
+  uint64_t* flush_done = bars + 13;   // drain -> MMA: accumulators read out, may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S::kNumBars);
 
   const int warp = threadIdx.x >> 5;
@@ -112,6 +118,8 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_dq);
+    tma_prefetch_desc(&tm_dk);
+    tma_prefetch_desc(&tm_dv);
     mbar_init(kv_full, 1);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
@@ -124,6 +132,8 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 4);
     mbar_init(dkdv_full, 1);
+    mbar_init(flush_full, 1);
+    mbar_init(flush_done, 4);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -195,8 +205,13 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc_fence_after();
       mma_3term(kColDP, S::kV, S::kdO);
       commit(dp_full);
+      int nflush = 0;
       for (int it = 0; it < n_it; ++it) {
-        const uint32_t acc = it > 0 ? 1u : 0u;
+        const bool fresh = it % kFlushEvery == 0;   // first step after a flush (or the first at all)
+        const uint32_t acc = fresh ? 0u : 1u;
+        if (fresh && it > 0) {                      // the drain warpgroup must have read dV' / dK' out
+          mbar_wait(flush_done, (nflush - 1) & 1);
+        }
         // dV' += (Ph + Pl)^T [dOh | dOl]: q columns 16*ks.. of P^T live in the half (ks >> 2) of S^T
         mbar_wait(p_full, it & 1);
         tc_fence_after();
@@ -233,6 +248,10 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
         }
         commit(q_empty);
+        if ((it + 1) % kFlushEvery == 0 && it + 1 < n_it) {
+          commit(flush_full);
+          ++nflush;
+        }
         if (it + 1 < n_it) {
           mbar_wait(q_full, (it + 1) & 1);
           tc_fence_after();
@@ -363,10 +382,10 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       fence_proxy_async_smem();
       named_bar_sync(1 + half, 128);
-      if (wq == 0 && lane == 0) {
+      if (wq == 0 && lane == 0 && n_it > 0) {   // dk / dv were zeroed by the launcher: add the remainder
 #pragma unroll
         for (int bx = 0; bx < 2; ++bx)
-          tma_store_3d(half ? &tm_dk : &tm_dv, stage + bx * S::kBox, bx * 32, k0, bh_kv);
+          tma_reduce_add_3d(half ? &tm_dk : &tm_dv, stage + bx * S::kBox, bx * 32, k0, bh_kv);
         bulk_commit();
         bulk_wait_read<0>();
       }
@@ -378,6 +397,7 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int row = wq * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
     const bool issuer = (warp == 12 && lane == 0);
+    int nflush = 0;
     for (int it = 0; it < n_it; ++it) {
       const int bh_q = b * p.QH + hk * g + it / nqi;
       const int q0 = (i0 + it % nqi) * 128;
@@ -409,6 +429,44 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tma_reduce_add_3d(&tm_dq, sStage, 0, q0, bh_q);
         tma_reduce_add_3d(&tm_dq, sStage + S::kBox, 32, q0, bh_q);
         bulk_commit();
+      }
+      if ((it + 1) % kFlushEvery == 0 && it + 1 < n_it) {
+        // ---- flush dV' and dK' (see kFlushEvery) ----
+        mbar_wait(flush_full, (nflush++) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t tsrc = tmem_base + lane_off + (which ? kColDK : kColDV);
+          const float mul = which ? p.scale : 1.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld_x32(tsrc + c * 32, r[c]);
+          tmem_ld_wait();
+          if (which == 1) {   // both accumulators are in registers / staged: the MMA warp may go on
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(flush_done);
+          }
+          if (issuer) bulk_wait_read<0>();
+          named_bar_sync(3, 128);
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              float4 v;
+              v.x = (__uint_as_float(r[c][4 * u + 0]) + __uint_as_float(r[c + 2][4 * u + 0])) * mul;
+              v.y = (__uint_as_float(r[c][4 * u + 1]) + __uint_as_float(r[c + 2][4 * u + 1])) * mul;
+              v.z = (__uint_as_float(r[c][4 * u + 2]) + __uint_as_float(r[c + 2][4 * u + 2])) * mul;
+              v.w = (__uint_as_float(r[c][4 * u + 3]) + __uint_as_float(r[c + 2][4 * u + 3])) * mul;
+              *reinterpret_cast<float4*>(sStage + c * S::kBox + row * 128 + ((u ^ (row & 7)) << 4)) = v;
+            }
+          fence_proxy_async_smem();
+          named_bar_sync(3, 128);
+          if (issuer) {
+            tma_reduce_add_3d(which ? &tm_dk : &tm_dv, sStage, 0, k0, bh_kv);
+            tma_reduce_add_3d(which ? &tm_dk : &tm_dv, sStage + S::kBox, 32, k0, bh_kv);
+            bulk_commit();
+          }
+        }
       }
     }
     if (issuer) bulk_wait<0>();
@@ -480,6 +538,8 @@ int attn_f32_bwd(const AttnParams& a) {
         static_cast<const float*>(a.o), a.lse, a.QL, QLp, n_rows_p);
     NNOP_LAUNCH_CHECK();
   }
+  NNOP_CUDA_CHECK(cudaMemsetAsync(a.dk, 0, static_cast<size_t>(BHk) * a.KL * 64 * sizeof(float), a.stream));
+  NNOP_CUDA_CHECK(cudaMemsetAsync(a.dv, 0, static_cast<size_t>(BHk) * a.KL * 64 * sizeof(float), a.stream));
   if (int rc = attn_split_f32_rows(qs, a.q, BH * a.QL, a.stream)) return rc;
   if (int rc = attn_split_f32_rows(dos, a.dO, BH * a.QL, a.stream)) return rc;
   if (int rc = attn_split_f32_rows(ks, a.k, BHk * a.KL, a.stream)) return rc;

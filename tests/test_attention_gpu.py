@@ -50,12 +50,10 @@ def _check(nnop, q, k, v, dO, pr, m, causal, tol, expect_path=None):
                                                   causal=causal, kpad_mask=dev(m))
     rq, rk, rv, rp = O.naive_attention_bwd(D(dO), D(q), D(k), D(v), D(pr), causal=causal, kpad_mask=m)
     # 16-bit outputs: the bound is absolute for O(1) values and follows the output rounding
-    # (2^-8 relative for bf16) once a gradient's magnitude exceeds 2.  Float32 on the tensor cores
-    # (E = 64, no pair): dK / dV sum hundreds of MMAs into one fp32 TMEM accumulator whose additions
-    # are not round-to-nearest (measured bias ~ 2^-25 per accumulation), so there too the 1e-4 bound
-    # is taken relative to magnitudes above 2 (the reference's own check is 1e-3 norm-wise).
-    tc_f32 = tol <= 1e-3 and q.shape[-1] == 64 and pr is None
-    mag = (lambda r: max(1.0, r.abs().max().item() / 2)) if (tol > 1e-3 or tc_f32) else (lambda r: 1.0)
+    # (2^-8 relative for bf16) once a gradient's magnitude exceeds 2.  Float32 keeps the strict
+    # 1e-4, also on the tensor-core path (E = 64): its dK / dV accumulators are flushed with exact
+    # fp32 adds every few q blocks precisely so that this bound holds for gradients of magnitude ~10.
+    mag = (lambda r: max(1.0, r.abs().max().item() / 2)) if tol > 1e-3 else (lambda r: 1.0)
     assert max_abs(dq, rq) < tol * mag(rq), "dq"
     assert max_abs(dk, rk) < tol * mag(rk), "dk"
     assert max_abs(dv, rv) < tol * mag(rv), "dv"
