@@ -19,6 +19,7 @@ region).  `roofline`: the backward main kernel (dominant launch) against the mea
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -158,6 +159,37 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+@contextlib.contextmanager
+def gpu_local_cpus(local_rank):
+    """Pin this thread to the CPUs NVML reports as local to the GPU while the pinned host buffers are
+    allocated (first touch places their pages on that NUMA node), then restore the affinity."""
+    note = ["default placement"]
+    old = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64 + 16)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        old = os.sched_getaffinity(0)
+        local = cpus & old
+        if local and local != old:
+            os.sched_setaffinity(0, local)
+            note[0] = f"allocated from {len(local)} GPU-local CPUs of {len(old)} (NVML affinity)"
+        else:
+            old = None
+    except Exception as e:  # NVML missing or affinity not permitted: keep the default placement
+        old = None
+        note[0] = f"default placement ({type(e).__name__})"
+    try:
+        yield note
+    finally:
+        if old is not None:
+            os.sched_setaffinity(0, old)
+
+
 # ---------------------------------------------------------------------------------- GPU arm
 def run_ours(args, rank, local_rank, world):
     import torch
@@ -215,10 +247,12 @@ def run_ours(args, rank, local_rank, world):
     e2e = None
     if not args.no_e2e:
         pin = lambda t_: torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True).copy_(t_)
-        hq, hk, hv, hdO = pin(q), pin(k), pin(v), pin(dO)
-        out = {n: torch.empty(s.shape, dtype=s.dtype, pin_memory=True) for n, s in
-               (("o", q), ("dq", q), ("dk", k), ("dv", k))}
-        pipe = nn.HostAttentionPipeline(q.shape, k.shape, torch.bfloat16, causal=CAUSAL, chunk=1, device=dev)
+        with gpu_local_cpus(local_rank) as numa_note:   # first touch: pinned pages on the GPU's NUMA node
+            hq, hk, hv, hdO = pin(q), pin(k), pin(v), pin(dO)
+            out = {n: torch.empty(s.shape, dtype=s.dtype, pin_memory=True) for n, s in
+                   (("o", q), ("dq", q), ("dk", k), ("dv", k))}
+        pipe = nn.HostAttentionPipeline(q.shape, k.shape, torch.bfloat16, causal=CAUSAL, chunk=1,
+                                        kv_heads=args.e2e_kv_heads, device=dev)
         for _ in range(2):
             pipe(hq, hk, hv, hdO, out)
         barrier()
@@ -234,7 +268,10 @@ def run_ours(args, rank, local_rank, world):
         ms_e2e = te.item() / args.steps
         e2e = {"value": world * (f_fwd + f_bwd) / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-               "ms_per_step": ms_e2e}
+               "ms_per_step": ms_e2e,
+               "pipeline": f"{B * (KH // pipe.kv_heads)} chunks of {pipe.kv_heads} kv heads x 1 batch element, "
+                           f"{len(pipe.slots)} device slots, H2D / compute / D2H on three streams",
+               "pinned_host_memory": numa_note[0]}
         del hq, hk, hv, hdO, out, pipe
 
     if rank != 0:
@@ -300,6 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-kv-heads", type=int, default=16, help="kv heads per host-pipeline chunk")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

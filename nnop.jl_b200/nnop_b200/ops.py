@@ -467,23 +467,38 @@ def set_timing_events(which: int, start: "torch.cuda.Event | None", stop: "torch
 class HostAttentionPipeline:
     """flash_attention forward + backward on HOST (pinned) arrays.
 
-    The batch axis is cut into chunks; chunk c+1 is copied host->device while chunk c computes and
-    chunk c-1's results (o, dq, dk, dv) are copied device->host, on three CUDA streams with two
-    device staging slots.  Every (kv-head group, batch) unit is independent (src/attention.jl:152),
-    so chunking changes no result.  Device staging is allocated once and reused across calls.
+    The (kv-head group, batch) axis is cut into chunks; chunk c+1 is copied host->device while
+    chunk c computes and chunk c-1's results (o, dq, dk, dv) are copied device->host, on three CUDA
+    streams with `nslots` device staging slots.  Every (kv-head group, batch) unit is independent
+    (src/attention.jl:152) and a GQA group is never split, so chunking changes no result.  A chunk
+    is `chunk` batch elements, or -- with `kv_heads` -- `kv_heads` kv heads (and their q heads) of one
+    batch element: both are contiguous slabs of the (B, H, L, E) arrays.  Small chunks keep the
+    pipeline's fill and drain (one chunk in, one chunk out, not overlapped) short against the
+    PCIe-bound steady state.  Device staging is allocated once and reused across calls.
     """
 
-    def __init__(self, q_shape, kv_shape, dtype, *, causal: bool, chunk: int = 1, device=None):
+    def __init__(self, q_shape, kv_shape, dtype, *, causal: bool, chunk: int = 1, kv_heads: int = 0,
+                 nslots: int = 3, device=None):
         self.causal = bool(causal)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-        self.B = q_shape[0]
-        self.chunk = max(1, min(chunk, self.B))
-        cq = (self.chunk,) + tuple(q_shape[1:])
-        ck = (self.chunk,) + tuple(kv_shape[1:])
+        self.B, self.QH, self.KH = q_shape[0], q_shape[1], kv_shape[1]
+        if self.QH % self.KH:
+            raise NNopError(1, "number of q heads must be a multiple of the number of kv heads")
+        self.g = self.QH // self.KH
+        self.kv_heads = self.KH if kv_heads <= 0 else min(kv_heads, self.KH)
+        self.chunk = max(1, min(chunk, self.B)) if self.kv_heads == self.KH else 1
+        cq = (self.chunk, self.kv_heads * self.g) + tuple(q_shape[2:])
+        ck = (self.chunk, self.kv_heads) + tuple(kv_shape[2:])
         mk = lambda shp: torch.empty(shp, dtype=dtype, device=self.dev)
-        self.slots = [dict(q=mk(cq), k=mk(ck), v=mk(ck), dO=mk(cq)) for _ in range(2)]
+        self.slots = [dict(q=mk(cq), k=mk(ck), v=mk(ck), dO=mk(cq)) for _ in range(max(2, nslots))]
         self.s_h2d, self.s_comp, self.s_d2h = (torch.cuda.Stream(self.dev) for _ in range(3))
         self.h2d_bytes = self.d2h_bytes = 0
+
+    def _chunks(self):
+        """(batch slice, kv-head slice) of every chunk, batch-major."""
+        for b0 in range(0, self.B, self.chunk):
+            for h0 in range(0, self.KH, self.kv_heads):
+                yield slice(b0, min(self.B, b0 + self.chunk)), slice(h0, min(self.KH, h0 + self.kv_heads))
 
     def __call__(self, q, k, v, dO, out):
         """q, dO (B,QH,QL,E), k, v (B,KH,KL,E): pinned CPU tensors.  out: dict of pinned CPU tensors
@@ -491,44 +506,46 @@ class HostAttentionPipeline:
         for t in (q, k, v, dO, *out.values()):
             if t.is_cuda or not t.is_pinned():
                 raise NNopError(6, "HostAttentionPipeline expects pinned host tensors")
-        B, ch = self.B, self.chunk
-        comp_done = [None, None]
-        d2h_done = []
+        ns, g = len(self.slots), self.g
+        comp_done = [None] * ns
+        last = None
         cur = torch.cuda.current_stream(self.dev)
         for s in (self.s_h2d, self.s_comp, self.s_d2h):
             s.wait_stream(cur)
         self.h2d_bytes = self.d2h_bytes = 0
-        for ci, b0 in enumerate(range(0, B, ch)):
-            b1 = min(B, b0 + ch)
-            n = b1 - b0
-            slot = self.slots[ci & 1]
+        for ci, (bs, hs) in enumerate(self._chunks()):
+            n, nh = bs.stop - bs.start, hs.stop - hs.start
+            qs = slice(hs.start * g, hs.stop * g)
+            slot = self.slots[ci % ns]
             with torch.cuda.stream(self.s_h2d):
-                if comp_done[ci & 1] is not None:
-                    self.s_h2d.wait_event(comp_done[ci & 1])  # slot inputs consumed
-                for name, src in (("q", q), ("k", k), ("v", v), ("dO", dO)):
-                    slot[name][:n].copy_(src[b0:b1], non_blocking=True)
-                    self.h2d_bytes += src[b0:b1].numel() * src.element_size()
+                if comp_done[ci % ns] is not None:
+                    self.s_h2d.wait_event(comp_done[ci % ns])  # slot inputs consumed
+                for name, src, sl in (("q", q, qs), ("k", k, hs), ("v", v, hs), ("dO", dO, qs)):
+                    part = src[bs, sl]
+                    slot[name][:n, :sl.stop - sl.start].copy_(part, non_blocking=True)
+                    self.h2d_bytes += part.numel() * part.element_size()
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.s_h2d)
             with torch.cuda.stream(self.s_comp):
                 self.s_comp.wait_event(ev_in)
-                qd, kd, vd, dOd = (slot[x][:n] for x in ("q", "k", "v", "dO"))
+                qd, dOd = slot["q"][:n, :nh * g], slot["dO"][:n, :nh * g]
+                kd, vd = slot["k"][:n, :nh], slot["v"][:n, :nh]
                 o, lse = _flash_attention(qd, kd, vd, causal=self.causal)
                 dq, dk, dv, _ = grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=self.causal)
                 ev_c = torch.cuda.Event()
                 ev_c.record(self.s_comp)
-                comp_done[ci & 1] = ev_c
+                comp_done[ci % ns] = ev_c
             with torch.cuda.stream(self.s_d2h):
                 self.s_d2h.wait_event(ev_c)
-                for name, src in (("o", o), ("dq", dq), ("dk", dk), ("dv", dv)):
-                    out[name][b0:b1].copy_(src, non_blocking=True)
+                for name, src, sl in (("o", o, qs), ("dq", dq, qs), ("dk", dk, hs), ("dv", dv, hs)):
+                    out[name][bs, sl].copy_(src, non_blocking=True)
                     src.record_stream(self.s_d2h)
                     self.d2h_bytes += src.numel() * src.element_size()
                 lse.record_stream(self.s_d2h)
-                ev_o = torch.cuda.Event()
-                ev_o.record(self.s_d2h)
-                d2h_done.append(ev_o)
+                last = torch.cuda.Event()
+                last.record(self.s_d2h)
         cur.wait_stream(self.s_d2h)
         cur.wait_stream(self.s_comp)
-        d2h_done[-1].synchronize()
+        if last is not None:
+            last.synchronize()
         return out

@@ -347,3 +347,25 @@ def test_f32_tensor_core_forward_vs_simt_and_oracle(nnop, causal):
         finally:
             nnop.set_attention_path(0)
         assert max_abs(o, o_s) < F32_TOL and max_abs(lse, lse_s) < F32_TOL
+
+
+@pytest.mark.parametrize("chunk,kv_heads", [(1, 0), (2, 0), (1, 1), (1, 2), (1, 3)])
+def test_host_pipeline_matches_device_call(nnop, chunk, kv_heads):
+    """HostAttentionPipeline (pinned host arrays, chunked over (kv-head group, batch)) returns bit for
+    bit what the device-resident call returns: every unit is independent (src/attention.jl:152)."""
+    B, QH, KH, L, E = 3, 8, 4, 384, 128
+    q, k, v, dO, _, _ = _inputs(B, QH, KH, L, L, E, torch.bfloat16, seed=7)
+    dq_, dk_, dv_, ddO = (t.cuda() for t in (q, k, v, dO))
+    o, lse = nnop._flash_attention(dq_, dk_, dv_, causal=True)
+    gq, gk, gv, _ = nnop.grad_flash_attention(ddO, o, lse, dq_, dk_, dv_, causal=True)
+    pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+    out = {n: torch.zeros(s.shape, dtype=s.dtype).pin_memory() for n, s in
+           (("o", q), ("dq", q), ("dk", k), ("dv", k))}
+    pipe = nnop.HostAttentionPipeline(q.shape, k.shape, torch.bfloat16, causal=True, chunk=chunk,
+                                      kv_heads=kv_heads)
+    for _ in range(2):   # second call reuses the staging slots
+        pipe(pin(q), pin(k), pin(v), pin(dO), out)
+    for name, ref in (("o", o), ("dq", gq), ("dk", gk), ("dv", gv)):
+        assert torch.equal(out[name], ref.cpu()), name
+    nbytes = lambda *ts: sum(t.numel() * t.element_size() for t in ts)
+    assert pipe.h2d_bytes == nbytes(q, k, v, dO) and pipe.d2h_bytes == nbytes(q, q, k, k)
