@@ -289,7 +289,7 @@ def run_ours(args, rank, local_rank, world):
             traffic = json.loads(tf.read_text()).get("attn_bwd_sm100_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "tensor", "kernel": "attn_bwd_sm100_kernel<bf16,128>", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": "attn_bwd_sm100_persist_kernel<bf16,128>", "achieved": achieved,
                 "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": traffic,
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "frac_of_burst": achieved / burst, "frac_of_nominal_2250": achieved / 2250.0,
@@ -320,7 +320,7 @@ def run_ours(args, rank, local_rank, world):
                    "flops_convention": "4*B*H*L^2*E/2 fwd, x2.5 bwd (SURVEY.md 8d)"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": 4 * args.steps * world,
         "gpu_launches_per_step_per_rank": {"attn_fwd_sm100_kernel": 1, "attn_bwd_prep_kernel": 1,
-                                           "attn_bwd_sm100_kernel": 1, "attn_bwd_post_kernel": 1},
+                                           "attn_bwd_sm100_persist_kernel": 1, "attn_bwd_post_kernel": 1},
         "roofline": roofline, "cpu_baseline": cpu,
         "fwd_bwd_tflops_frac_of_sustained_peak": value / world / sustained,
     }

@@ -63,10 +63,13 @@ int nnop_device_info(int device, nnop_device_info_t* out);
 int nnop_set_attention_path(int mode);
 /* 1 if the last flash-attention call on this thread ran the tcgen05 path, else 0. */
 int nnop_last_attention_path(void);
-/* Backward kernel selection on the tcgen05 path (diagnostics / A-B timing).  0 (default): one CTA
- * per kv block; 1 (or env NNOP_BWD_PAIR=1): E = 128 dense problems run the experimental CTA-pair
- * kernel (tcgen05 cta_group::2, two kv blocks per cluster sharing the Q / dO operand halves; same
- * results, currently slower).  Process-wide. */
+/* Backward kernel selection on the tcgen05 path (diagnostics / A-B timing), process-wide; env
+ * NNOP_BWD_PAIR gives the initial value.  0 (default): automatic -- dense problems without a key
+ * padding mask whose tile queue is at least two rounds deep run the persistent kernel (one CTA per
+ * SM, dynamic queue of (kv block, kv head, batch) tiles, epilogue overlapped with the next tile),
+ * everything else one CTA per tile; 1: E = 128 dense problems run the experimental CTA-pair kernel
+ * (tcgen05 cta_group::2; same results, currently slower); 2: always one CTA per tile; 3: persistent
+ * wherever eligible; 100+n: persistent on n CTAs (tests).  dK / dV are bit-identical across modes. */
 int nnop_set_bwd_pair_mode(int mode);
 
 /* ---------------------------------------------------------------------------------------

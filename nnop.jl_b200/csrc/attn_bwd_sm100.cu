@@ -59,7 +59,9 @@ __device__ long long g_bwd_trace[256 * 16];
 __device__ long long g_bwd_cta_log[1024 * 16];
 __device__ int g_bwd_cta_n;
 #define BWD_CTA(k) do { if (cta_slot >= 0) g_bwd_cta_log[cta_slot * 16 + (k)] = clock64(); } while (0)
+#define PT_STAMP(k) do { if (blockIdx.x == 0 && lane == 0 && tl < 1024) g_bwd_cta_log[tl * 16 + (k)] = clock64(); } while (0)
 #else
+#define PT_STAMP(k) do { } while (0)
 #define BWD_CTA(k) do { } while (0)
 #define BWD_STAMP(i, k) do { } while (0)
 #endif
@@ -95,7 +97,7 @@ struct BwdSmem {
   static constexpr int kdQs = kdS + 2 * kBox;   // 2 x (128 rows x 32 fp32)
   static constexpr int kStat = kdQs + 2 * 16384;  // lse2[2][128], delta[2][128]
   static constexpr int kBar = kStat + 2048;
-  static constexpr int kNumBars = 14;
+  static constexpr int kNumBars = 24;  // 14 used by the plain kernel, 24 by the persistent one
   static constexpr int kTotal = kBar + kNumBars * 8 + 16;
 };
 
@@ -552,6 +554,507 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     g_bwd_cta_log[cta_slot * 16 + 7] = n_it;
   }
 #endif
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// =========================================================================================
+// Persistent variant (dense layout, no key padding mask): one CTA per SM walks a dynamic queue of
+// (kv block, kv head, batch) tiles.  The plain kernel above spends ~9 % of a CTA's life outside
+// its steady state (prologue, dK/dV epilogue, launch gap; scripts/trace_bwd_ctas.py) and with one
+// CTA per SM nothing overlaps it.  Here the barrier phases, the Q_i / dO_i ring and TMEM run on
+// across tiles:
+//   * warp 3 is the scheduler: atomicAdd on a global tile counter (zeroed by the prep kernel), tile
+//     ids broadcast through a two-slot shared-memory ring (tile_full / tile_empty);
+//   * the TMA producer loads the next tile's V as soon as the last dP^T has read V (one step before
+//     the tile ends), its first Q_i / dO_i as their ring slots free up, and K after the last dQ;
+//   * the dK / dV epilogue moves to the dQ drain warpgroup (staging in its own 32 KB buffer), so the
+//     compute warpgroups go straight on to the next tile's logits; the MMA warp waits on dv_empty /
+//     dk_empty only before the next tile's first accumulating MMA overwrites the accumulators.
+// Per tile the summation order is that of the plain kernel, so dK / dV agree bit for bit.
+// =========================================================================================
+struct PersistBars {
+  enum : int {
+    kTileFull = 0,   // [2] scheduler -> all roles
+    kTileEmpty = 2,  // [2] all roles -> scheduler (14 arrivals)
+    kKFull = 4, kVFull = 5, kKEmpty = 6, kVEmpty = 7,
+    kQFull = 8,      // [2]
+    kQEmpty = 10,    // [2]
+    kDoFull = 12, kDoEmpty = 13,
+    kSFull = 14, kPFull = 15, kDpFull = 16, kDsFull = 17, kDqFull = 18, kDqEmpty = 19,
+    kDkDvFull = 20, kDvEmpty = 21, kDkEmpty = 22,
+    kSchedGo = 23,   // producer -> scheduler: the current tile is nearly loaded, claim the next one
+    kCount = 24
+  };
+};
+static_assert(PersistBars::kCount <= BwdSmem<128>::kNumBars, "barrier area too small");
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
+                              const __grid_constant__ CUtensorMap tm_k,
+                              const __grid_constant__ CUtensorMap tm_v,
+                              const __grid_constant__ CUtensorMap tm_do,
+                              const __grid_constant__ CUtensorMap tm_dk,
+                              const __grid_constant__ CUtensorMap tm_dv,
+                              const __grid_constant__ CUtensorMap tm_dqa, const BwdParams p,
+                              int* __restrict__ tile_counter, const int n_tiles, const int nkv) {
+  using S = BwdSmem<D>;
+  using PB = PersistBars;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem + S::kK;
+  uint8_t* sV = smem + S::kV;
+  uint8_t* sQ = smem + S::kQ;
+  uint8_t* sdO = smem + S::kdO;
+  uint8_t* sdS = smem + S::kdS;
+  uint8_t* sdQ = smem + S::kdQs;
+  float* s_lse = reinterpret_cast<float*>(smem + S::kStat);
+  float* s_del = reinterpret_cast<float*>(smem + S::kStat + 1024);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S::kNumBars);
+  volatile int* s_tile = reinterpret_cast<volatile int*>(tmem_slot + 2);  // [2]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = p.QH / p.KH;
+  const int nq = (p.QL + 127) >> 7;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("nnop: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dqa);
+    tma_prefetch_desc(&tm_dk);
+    tma_prefetch_desc(&tm_dv);
+    for (int i = 0; i < PB::kCount; ++i) {
+      uint32_t cnt = 1;
+      if (i == PB::kTileEmpty || i == PB::kTileEmpty + 1) cnt = 14;  // TMA + MMA + 8 compute + 4 drain
+      if (i == PB::kPFull || i == PB::kDsFull) cnt = 8;              // one arrival per compute warp
+      if (i == PB::kDqEmpty || i == PB::kDvEmpty || i == PB::kDkEmpty) cnt = 4;  // per drain warp
+      mbar_init(bars + i, cnt);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 256 + D;
+
+  // every consumer role fetches the n-th tile id the same way
+  auto next_tile = [&](int n) -> int {
+    const int slot = n & 1;
+    mbar_wait(bars + PB::kTileFull + slot, (n >> 1) & 1);
+    const int t = s_tile[slot];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + PB::kTileEmpty + slot);
+    return t;
+  };
+
+  if (warp < 4) {
+    setmaxnreg_dec<88>();
+    if (warp == 3) {
+      // ================================ tile scheduler ===============================
+      if (lane == 0) {
+        for (int n = 0;; ++n) {
+          const int slot = n & 1;
+          // a tile is claimed only when this CTA is about to need it: tiles claimed early would sit
+          // in the ring while other CTAs run dry at the end of the queue
+          if (n > 0) mbar_wait(bars + PB::kSchedGo, (n - 1) & 1);
+          mbar_wait(bars + PB::kTileEmpty + slot, ((n >> 1) & 1) ^ 1);
+          const int t = atomicAdd(tile_counter, 1);
+          s_tile[slot] = t < n_tiles ? t : -1;
+          mbar_arrive(bars + PB::kTileFull + slot);
+          if (t >= n_tiles) break;
+        }
+      }
+    } else if (warp == 0) {
+      // ================================ TMA producer =================================
+      if (lane == 0) {
+        int gs = 0;
+        for (int tl = 0;; ++tl) {
+          const int slot = tl & 1;
+          mbar_wait(bars + PB::kTileFull + slot, (tl >> 1) & 1);
+          const int t = s_tile[slot];
+          mbar_arrive(bars + PB::kTileEmpty + slot);
+          if (t < 0) break;
+          const int j = t % nkv, u = t / nkv;
+          const int hk = u % p.KH, b = u / p.KH;
+          const int k0 = j * 128, bh_kv = b * p.KH + hk;
+          const int i0 = p.causal ? j : 0;
+          const int nqi = nq - i0;
+          const int n_it = nqi * g;
+          auto load_q = [&](int it) {
+            const int gi = gs + it;
+            const int s = gi & 1;
+            const int bh_q = b * p.QH + hk * g + it / nqi;
+            const int q0 = (i0 + it % nqi) * 128;
+            mbar_wait(bars + PB::kQEmpty + s, ((gi >> 1) & 1) ^ 1);
+            mbar_arrive_expect_tx(bars + PB::kQFull + s, S::kTile + 1024);
+#pragma unroll
+            for (int bx = 0; bx < S::kNBox; ++bx)
+              tma_load_3d(sQ + s * S::kTile + bx * S::kBox, &tm_q, bars + PB::kQFull + s, bx * 64, q0, bh_q);
+            const int64_t soff = static_cast<int64_t>(bh_q) * p.QLp + q0;
+            bulk_load_1d(s_lse + s * 128, p.lse2p + soff, 512, bars + PB::kQFull + s);
+            bulk_load_1d(s_del + s * 128, p.deltap + soff, 512, bars + PB::kQFull + s);
+          };
+          auto load_do = [&](int it) {
+            const int gi = gs + it;
+            const int bh_q = b * p.QH + hk * g + it / nqi;
+            const int q0 = (i0 + it % nqi) * 128;
+            mbar_wait(bars + PB::kDoEmpty, (gi & 1) ^ 1);
+            mbar_arrive_expect_tx(bars + PB::kDoFull, S::kTile);
+#pragma unroll
+            for (int bx = 0; bx < S::kNBox; ++bx)
+              tma_load_3d(sdO + bx * S::kBox, &tm_do, bars + PB::kDoFull, bx * 64, q0, bh_q);
+          };
+          const int go_at = n_it > 2 ? n_it - 2 : 0;  // step whose loads trigger the next claim
+          if (go_at == 0) mbar_arrive(bars + PB::kSchedGo);
+          // in the order the previous tile releases them: V, Q ring slot, dO, K
+          mbar_wait(bars + PB::kVEmpty, (tl & 1) ^ 1);
+          mbar_arrive_expect_tx(bars + PB::kVFull, S::kTile);
+#pragma unroll
+          for (int bx = 0; bx < S::kNBox; ++bx)
+            tma_load_3d(sV + bx * S::kBox, &tm_v, bars + PB::kVFull, bx * 64, k0, bh_kv);
+          load_q(0);
+          load_do(0);
+          mbar_wait(bars + PB::kKEmpty, (tl & 1) ^ 1);
+          mbar_arrive_expect_tx(bars + PB::kKFull, S::kTile);
+#pragma unroll
+          for (int bx = 0; bx < S::kNBox; ++bx)
+            tma_load_3d(sK + bx * S::kBox, &tm_k, bars + PB::kKFull, bx * 64, k0, bh_kv);
+          if (n_it > 1) load_q(1);
+          for (int it = 1; it < n_it; ++it) {
+            if (it == go_at) mbar_arrive(bars + PB::kSchedGo);
+            load_do(it);
+            if (it + 1 < n_it) load_q(it + 1);
+          }
+          gs += n_it;
+        }
+      }
+    } else if (warp == 1) {
+      // ================================ MMA issuer ===================================
+      constexpr bool BF = is_bf16<T>::value;
+      constexpr uint32_t id_kk = make_idesc_f16(128, 128, BF, false, false);  // S^T, dP^T
+      constexpr uint32_t id_tv = make_idesc_f16(128, D, BF, false, true);     // dV (A in TMEM), dK
+      constexpr uint32_t id_mm = make_idesc_f16(128, D, BF, true, true);      // dQ
+      const uint32_t tm = uniform_u32(tmem_base);
+      const uint32_t sbase = uniform_u32(smem_u32(smem));
+      const uint64_t kmaj = make_smem_desc_sw128(sbase, 16, 1024);
+      const uint64_t mnmaj = make_smem_desc_sw128(sbase, S::kBox, 1024);
+      const uint32_t k_lo = desc_lo(kmaj), k_hi = desc_hi(kmaj);
+      const uint32_t m_lo = desc_lo(mnmaj), m_hi = desc_hi(mnmaj);
+      auto mma_kk = [&](uint32_t dcol, uint32_t a0, uint32_t b0) {
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t off = (ks >> 2) * S::kBox + (ks & 3) * 32;
+            umma_ss_lo(tm + dcol, k_lo, (a0 + off) >> 4, k_hi, k_lo, (b0 + off) >> 4, k_hi, id_kk,
+                       ks > 0 ? 1u : 0u);
+          }
+        }
+      };
+      auto commit = [&](int bar) {
+        if (elect_one()) tc_commit(bars + bar);
+      };
+      int gs = 0;
+      for (int tl = 0;; ++tl) {
+        const int t = next_tile(tl);
+        if (t < 0) break;
+        const int j = t % nkv;
+        const int n_it = (nq - (p.causal ? j : 0)) * g;
+        PT_STAMP(0);
+        // dP^T(0) = V dO_0^T: its TMEM columns hold the previous tile's last dQ until drained
+        mbar_wait(bars + PB::kVFull, tl & 1);
+        mbar_wait(bars + PB::kDoFull, gs & 1);
+        if (gs > 0) mbar_wait(bars + PB::kDqEmpty, (gs - 1) & 1);
+        tc_fence_after();
+        PT_STAMP(1);
+        mma_kk(kColDP, S::kV, S::kdO);
+        commit(PB::kDpFull);
+        if (n_it == 1) commit(PB::kVEmpty);
+        // S^T(0) = K Q_0^T
+        mbar_wait(bars + PB::kKFull, tl & 1);
+        mbar_wait(bars + PB::kQFull + (gs & 1), (gs >> 1) & 1);
+        tc_fence_after();
+        PT_STAMP(2);
+        mma_kk(kColS, S::kK, S::kQ + static_cast<uint32_t>((gs & 1) * S::kTile));
+        commit(PB::kSFull);
+        for (int it = 0; it < n_it; ++it) {
+          const int gi = gs + it;
+          const int s = gi & 1;
+          const uint32_t acc = it > 0 ? 1u : 0u;
+          const uint32_t qoff = static_cast<uint32_t>(s * S::kTile);
+          // dV += P^T dO_i
+          if (it == 0) mbar_wait(bars + PB::kDvEmpty, (tl & 1) ^ 1);  // previous tile's dV read out
+          mbar_wait(bars + PB::kPFull, gi & 1);
+          tc_fence_after();
+          if (it == 0) PT_STAMP(3);
+          if (it == 1) PT_STAMP(9);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_ts_lo(tm + kColDV, tm + kColS + (ks >> 2) * 64 + (ks & 3) * 8, m_lo,
+                         (S::kdO + ks * 2048) >> 4, m_hi, id_tv, (acc | (ks > 0)) ? 1u : 0u);
+          }
+          commit(PB::kDoEmpty);
+          // S^T(i+1)
+          if (it + 1 < n_it) {
+            mbar_wait(bars + PB::kQFull + (s ^ 1), ((gi + 1) >> 1) & 1);
+            tc_fence_after();
+            mma_kk(kColS, S::kK, S::kQ + static_cast<uint32_t>((s ^ 1) * S::kTile));
+            commit(PB::kSFull);
+          }
+          // dQ_i = dS K_j
+          mbar_wait(bars + PB::kDsFull, gi & 1);
+          tc_fence_after();
+          if (it == 0) PT_STAMP(4);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_ss_lo(tm + kColDP, m_lo, (S::kdS + ks * 2048) >> 4, m_hi, m_lo, (S::kK + ks * 2048) >> 4,
+                         m_hi, id_mm, ks > 0 ? 1u : 0u);
+          }
+          commit(PB::kDqFull);
+          if (it + 1 == n_it) commit(PB::kKEmpty);  // K_j is not read again
+          // dK += dS^T Q_i
+          if (it == 0) {
+            mbar_wait(bars + PB::kDkEmpty, (tl & 1) ^ 1);  // previous tile's dK read out
+            tc_fence_after();
+            PT_STAMP(5);
+          }
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t off = (ks >> 2) * S::kBox + (ks & 3) * 32;
+              umma_ss_lo(tm + kColDK, k_lo, (S::kdS + off) >> 4, k_hi, m_lo, (S::kQ + qoff + ks * 2048) >> 4,
+                         m_hi, id_tv, (acc | (ks > 0)) ? 1u : 0u);
+            }
+          }
+          commit(PB::kQEmpty + s);
+          // dP^T(i+1)
+          if (it + 1 < n_it) {
+            mbar_wait(bars + PB::kDoFull, (gi + 1) & 1);
+            mbar_wait(bars + PB::kDqEmpty, gi & 1);
+            tc_fence_after();
+            mma_kk(kColDP, S::kV, S::kdO);
+            commit(PB::kDpFull);
+            if (it + 2 == n_it) commit(PB::kVEmpty);  // V_j is not read again
+          }
+        }
+        commit(PB::kDkDvFull);
+        PT_STAMP(6);
+#ifdef NNOP_BWD_TRACE
+        if (blockIdx.x == 0 && lane == 0 && tl < 1024) {
+          g_bwd_cta_log[tl * 16 + 7] = n_it;
+          g_bwd_cta_log[tl * 16 + 8] = j;
+          g_bwd_cta_n = tl + 1;
+        }
+#endif
+        gs += n_it;
+      }
+    }
+  } else if (warp < 12) {
+    // ================================ compute warpgroups ===============================
+    setmaxnreg_inc<136>();
+    const int half = (warp - 4) >> 2;  // which 64 q columns
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;    // key row within the block
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const int c0 = half * 64;
+    const float sl2 = p.scale_log2;
+    int gs = 0;
+    for (int tl = 0;; ++tl) {
+      const int t = next_tile(tl);
+      if (t < 0) break;
+      const int j = t % nkv;
+      const int i0 = p.causal ? j : 0;
+      const int nqi = nq - i0;
+      const int n_it = nqi * g;
+      for (int it = 0; it < n_it; ++it) {
+        const int gi = gs + it;
+        const int s = gi & 1;
+        const int i = i0 + it % nqi;
+        // ---- P^T ----
+        mbar_wait(bars + PB::kQFull + s, (gi >> 1) & 1);  // lse2 / delta of this stage have landed
+        mbar_wait(bars + PB::kSFull, gi & 1);
+        tc_fence_after();
+        if (it == 0 && warp == 4) PT_STAMP(13);
+        uint32_t sr[2][32];
+        tmem_ld_x32(tmem_base + lane_off + kColS + c0, sr[0]);
+        tmem_ld_x32(tmem_base + lane_off + kColS + c0 + 32, sr[1]);
+        tmem_ld_wait();
+        float pf[64];
+        const float4* l4 = reinterpret_cast<const float4*>(s_lse + s * 128 + c0);
+#pragma unroll
+        for (int u4 = 0; u4 < 16; ++u4) {
+          const float4 l = l4[u4];
+          pf[4 * u4 + 0] = fast_exp2(fmaf(__uint_as_float(sr[u4 >> 3][(4 * u4 + 0) & 31]), sl2, -l.x));
+          pf[4 * u4 + 1] = fast_exp2(fmaf(__uint_as_float(sr[u4 >> 3][(4 * u4 + 1) & 31]), sl2, -l.y));
+          pf[4 * u4 + 2] = fast_exp2(fmaf(__uint_as_float(sr[u4 >> 3][(4 * u4 + 2) & 31]), sl2, -l.z));
+          pf[4 * u4 + 3] = fast_exp2(fmaf(__uint_as_float(sr[u4 >> 3][(4 * u4 + 3) & 31]), sl2, -l.w));
+        }
+        if (p.causal && i == j) {  // diagonal block: key k0+row is visible to query q0+c iff row <= c
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (row > c0 + c) pf[c] = 0.f;
+        }
+        {
+          uint32_t pk[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) pk[c] = pack2<T>(pf[2 * c], pf[2 * c + 1]);
+          tmem_st_x32(tmem_base + lane_off + kColS + half * 64, pk);  // inside this half's own S^T columns
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + PB::kPFull);
+        if (it == 0 && warp == 4) PT_STAMP(12);
+        // ---- dS^T ----
+        mbar_wait(bars + PB::kDpFull, gi & 1);
+        tc_fence_after();
+        tmem_ld_x32(tmem_base + lane_off + kColDP + c0, sr[0]);
+        tmem_ld_x32(tmem_base + lane_off + kColDP + c0 + 32, sr[1]);
+        tmem_ld_wait();
+        const float4* d4 = reinterpret_cast<const float4*>(s_del + s * 128 + c0);
+        uint8_t* drow = sdS + half * S::kBox + row * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {  // 8 columns = one 16-byte chunk
+          const float4 da = d4[2 * ch], db = d4[2 * ch + 1];
+          const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+          float ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = 8 * ch + e;
+            ds[e] = pf[c] * (__uint_as_float(sr[c >> 5][c & 31]) - dl[e]);
+          }
+          uint4 v;
+          v.x = pack2<T>(ds[0], ds[1]);
+          v.y = pack2<T>(ds[2], ds[3]);
+          v.z = pack2<T>(ds[4], ds[5]);
+          v.w = pack2<T>(ds[6], ds[7]);
+          *reinterpret_cast<uint4*>(drow + ((ch ^ (row & 7)) << 4)) = v;
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + PB::kDsFull);
+      }
+      gs += n_it;
+    }
+  } else {
+    // ========================= dQ drain + dK / dV epilogue warpgroup ====================
+    setmaxnreg_inc<152>();
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;  // query row (dQ) / key row (dK, dV) within the block
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const bool issuer = (warp == 12 && lane == 0);
+    int nred = 0;
+    int gs = 0;
+    for (int tl = 0;; ++tl) {
+      const int t = next_tile(tl);
+      if (t < 0) break;
+      const int j = t % nkv, u = t / nkv;
+      const int hk = u % p.KH, b = u / p.KH;
+      const int k0 = j * 128, bh_kv = b * p.KH + hk;
+      const int i0 = p.causal ? j : 0;
+      const int nqi = nq - i0;
+      const int n_it = nqi * g;
+      for (int it = 0; it < n_it; ++it) {
+        const int gi = gs + it;
+        const int bh_q = b * p.QH + hk * g + it / nqi;
+        const int q0 = (i0 + it % nqi) * 128;
+        mbar_wait(bars + PB::kDqFull, gi & 1);
+        tc_fence_after();
+        uint32_t r[D / 32][32];
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) tmem_ld_x32(tmem_base + lane_off + kColDP + c * 32, r[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + PB::kDqEmpty);
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint8_t* stage = sdQ + (nred & 1) * 16384;
+          if (issuer) {
+            // the bulk op that last read this buffer has finished (after an epilogue: the dK store,
+            // which reads both buffers)
+            if (it == 0 && c == 0) bulk_wait_read<0>(); else bulk_wait_read<1>();
+          }
+          named_bar_sync(3, 128);
+#pragma unroll
+          for (int u4 = 0; u4 < 8; ++u4) {
+            const uint4 v = make_uint4(r[c][4 * u4], r[c][4 * u4 + 1], r[c][4 * u4 + 2], r[c][4 * u4 + 3]);
+            *reinterpret_cast<uint4*>(stage + row * 128 + ((u4 ^ (row & 7)) << 4)) = v;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(3, 128);
+          if (issuer) {
+            tma_reduce_add_3d(&tm_dqa, stage, c * 32, q0, bh_q);
+            bulk_commit();
+          }
+          ++nred;
+        }
+      }
+      gs += n_it;
+      // ---- epilogue: dV then dK -> 16-bit -> swizzled staging (the dQ buffers) -> TMA store ----
+      // Each accumulator is pulled into registers in one go and released at once: the next tile's
+      // first dV / dK MMAs wait on dv_empty / dk_empty, the staging and the store do not.
+      if (warp == 12) PT_STAMP(14);
+      mbar_wait(bars + PB::kDkDvFull, tl & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t tsrc = tmem_base + lane_off + (which ? kColDK : kColDV);
+        const float mul = which ? p.scale : 1.f;
+        uint32_t r[D / 32][32];
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) tmem_ld_x32(tsrc + c * 32, r[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + (which ? PB::kDkEmpty : PB::kDvEmpty));
+        if (warp == 12) PT_STAMP(10 + which);
+        if (issuer) bulk_wait_read<0>();  // staging free: earlier dQ reduces / the dV store have been read
+        named_bar_sync(3, 128);
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) {
+            uint4 v;
+            v.x = pack2<T>(__uint_as_float(r[c][8 * u4 + 0]) * mul, __uint_as_float(r[c][8 * u4 + 1]) * mul);
+            v.y = pack2<T>(__uint_as_float(r[c][8 * u4 + 2]) * mul, __uint_as_float(r[c][8 * u4 + 3]) * mul);
+            v.z = pack2<T>(__uint_as_float(r[c][8 * u4 + 4]) * mul, __uint_as_float(r[c][8 * u4 + 5]) * mul);
+            v.w = pack2<T>(__uint_as_float(r[c][8 * u4 + 6]) * mul, __uint_as_float(r[c][8 * u4 + 7]) * mul);
+            const int chunk = c * 4 + u4;
+            const int bx = chunk >> 3, cin = chunk & 7;
+            *reinterpret_cast<uint4*>(sdQ + bx * S::kBox + row * 128 + ((cin ^ (row & 7)) << 4)) = v;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (issuer) {
+#pragma unroll
+          for (int bx = 0; bx < S::kNBox; ++bx)
+            tma_store_3d(which ? &tm_dk : &tm_dv, sdQ + bx * S::kBox, bx * 64, k0, bh_kv);
+          bulk_commit();
+        }
+      }
+    }
+    if (issuer) bulk_wait<0>();
+  }
+
+  // ---- teardown -------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -1026,9 +1529,10 @@ __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(float* __restrict__ deltap, float* __restrict__ lse2p,
                      float* __restrict__ dq_accum, const T* __restrict__ dO,
                      const T* __restrict__ o, const float* __restrict__ lse, int QL, int QLp,
-                     int64_t n_rows_p) {
+                     int64_t n_rows_p, int* __restrict__ tile_counter) {
   constexpr int LPR = D / 8;
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (gid == 0) *tile_counter = 0;  // tile queue of the persistent main kernel
   const int64_t rowp = gid / LPR;  // padded row index: bh * QLp + q
   const int li = static_cast<int>(gid % LPR);
   if (rowp >= n_rows_p) return;  // LPR divides 32 and 256: whole row groups exit together
@@ -1133,6 +1637,9 @@ int launch_bwd(const AttnParams& a) {
   float* deltap = reinterpret_cast<float*>(ws);
   float* lse2p = reinterpret_cast<float*>(ws + stat_bytes);
   float* dqa = reinterpret_cast<float*>(ws + 2 * stat_bytes);
+  // dense mode: the persistent kernel's tile counter sits behind the dQ accumulator
+  int* tile_counter = reinterpret_cast<int*>(
+      ws + 2 * stat_bytes + align256(static_cast<size_t>(BH) * rows_q * D * sizeof(float)));
 
   if (packed) {
     constexpr int kRows = 256 / (D / 8);
@@ -1146,7 +1653,7 @@ int launch_bwd(const AttnParams& a) {
     const int64_t threads = n_rows_p * (D / 8);
     attn_bwd_prep_kernel<T, D><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, a.stream>>>(
         deltap, lse2p, dqa, static_cast<const T*>(a.dO), static_cast<const T*>(a.o), a.lse, a.QL,
-        static_cast<int>(QLp), n_rows_p);
+        static_cast<int>(QLp), n_rows_p, tile_counter);
     NNOP_LAUNCH_CHECK();
   }
   alignas(64) CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdqa;
@@ -1167,8 +1674,24 @@ int launch_bwd(const AttnParams& a) {
   bp.cu_q = a.cu_q; bp.cu_k = a.cu_k; bp.dk_ptr = a.dk; bp.dv_ptr = a.dv; bp.total_k = a.total_k;
   bp.kpad = packed ? nullptr : a.kpad;
   const int nkv = (a.KL + 127) / 128;
+  // kernel variant (nnop_set_bwd_pair_mode / NNOP_BWD_PAIR): 0 = automatic (persistent kernel when the
+  // tile queue is at least two rounds deep, else one CTA per tile), 1 = CTA pairs (experiment),
+  // 2 = one CTA per tile, 3 = persistent, 100+n = persistent on n CTAs (tests)
+  const int mode = bwd_pair_mode();
   bool use_pair = false;
-  if constexpr (D == 128) use_pair = !packed && nkv >= 2 && bwd_pair_mode() != 0;
+  if constexpr (D == 128) use_pair = !packed && nkv >= 2 && mode == 1;
+  const int nq_blocks = (a.QL + 127) / 128;
+  const int64_t n_tiles = static_cast<int64_t>(nkv) * a.KH * a.B;
+  int num_sms = 148;
+  {
+    int dev = 0;
+    NNOP_CUDA_CHECK(cudaGetDevice(&dev));
+    NNOP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const bool persist_ok = !packed && a.kpad == nullptr && (!a.causal || nq_blocks >= nkv) &&
+                          n_tiles < (1LL << 30);
+  const bool use_persist = !use_pair && persist_ok &&
+                           (mode == 3 || mode >= 100 || (mode == 0 && n_tiles >= 2LL * num_sms));
   if (use_pair) {
     if constexpr (D == 128) {
       alignas(64) CUtensorMap tq64, tdo64;
@@ -1182,6 +1705,16 @@ int launch_bwd(const AttnParams& a) {
       timing_end(1, a.stream);
       NNOP_LAUNCH_CHECK();
     }
+  } else if (use_persist) {
+    auto kern = attn_bwd_sm100_persist_kernel<T, D>;
+    NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    const int ctas = mode >= 100 ? (mode - 100 < 1 ? 1 : mode - 100) : num_sms;
+    const int grid = static_cast<int>(n_tiles < ctas ? n_tiles : ctas);
+    timing_begin(1, a.stream);
+    kern<<<grid, kBwdThreads, S::kTotal, a.stream>>>(tq, tk, tv, tdo, tdk, tdv, tdqa, bp, tile_counter,
+                                                     static_cast<int>(n_tiles), nkv);
+    timing_end(1, a.stream);
+    NNOP_LAUNCH_CHECK();
   } else {
     auto kern = attn_bwd_sm100_kernel<T, D>;
     NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -1223,7 +1756,7 @@ void attn_sm100_set_bwd_pair_mode(int mode) { g_bwd_pair_mode.store(mode); }
 size_t attn_sm100_bwd_workspace_bytes(int E, int QL, int QH, int B) {
   const size_t QLp = static_cast<size_t>((QL + 127) / 128) * 128;
   const size_t BH = static_cast<size_t>(B) * QH;
-  return 2 * align256(BH * QLp * sizeof(float)) + BH * static_cast<size_t>(QL) * E * sizeof(float);
+  return 2 * align256(BH * QLp * sizeof(float)) + align256(BH * static_cast<size_t>(QL) * E * sizeof(float)) + 256;
 }
 
 size_t attn_sm100_bwd_packed_workspace_bytes(int E, int64_t total_q, int nseq, int QH) {

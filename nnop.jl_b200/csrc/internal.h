@@ -91,7 +91,7 @@ size_t attn_f32_bwd_workspace_bytes(int QL, int KL, int QH, int KH, int B);
 int attn_f32_bwd(const AttnParams& p);
 int attn_sm100_bwd(const AttnParams& p);
 bool attn_sm100_bwd_available();
-void attn_sm100_set_bwd_pair_mode(int mode);  // 0: single-CTA backward, 1: CTA pairs where eligible
+void attn_sm100_set_bwd_pair_mode(int mode);  // 0 auto, 1 CTA pairs, 2 one CTA per tile, 3 persistent, 100+n persistent on n CTAs
 size_t attn_sm100_bwd_workspace_bytes(int E, int QL, int QH, int B);
 size_t attn_sm100_bwd_packed_workspace_bytes(int E, int64_t total_q, int nseq, int QH);
 

@@ -67,7 +67,8 @@ def last_attention_path() -> int:
 
 
 def set_bwd_pair_mode(mode: int) -> None:
-    """0 (default): one CTA per kv block; 1: experimental CTA-pair backward (cta_group::2) for E = 128."""
+    """Backward kernel variant on the tcgen05 path: 0 automatic (persistent kernel for deep tile queues),
+    1 experimental CTA pairs (E = 128), 2 one CTA per tile, 3 persistent, 100+n persistent on n CTAs."""
     check(lib.nnop_set_bwd_pair_mode(int(mode)))
 
 

@@ -369,3 +369,31 @@ def test_host_pipeline_matches_device_call(nnop, chunk, kv_heads):
         assert torch.equal(out[name], ref.cpu()), name
     nbytes = lambda *ts: sum(t.numel() * t.element_size() for t in ts)
     assert pipe.h2d_bytes == nbytes(q, k, v, dO) and pipe.d2h_bytes == nbytes(q, q, k, k)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("E", [64, 128])
+def test_persistent_backward_matches_one_cta_per_tile(nnop, causal, E):
+    """The persistent backward (dynamic tile queue, dK / dV epilogue overlapped with the next tile) keeps
+    the per-tile summation order of the one-CTA-per-tile kernel: dK / dV bit for bit, dQ up to the
+    order of its fp32 reduce-adds.  Run on all SMs (mode 3) and squeezed onto 1 and 3 CTAs (modes
+    101, 103) so that every CTA walks many tiles of different lengths back to back."""
+    try:
+        for trial, (B, QH, KH, QL, KL) in enumerate([(1, 1, 1, 512, 256), (2, 4, 2, 1024, 1024), (1, 2, 2, 300, 700),
+                                                     (1, 2, 1, 1000, 1000), (3, 2, 2, 640, 640), (1, 1, 1, 128, 128),
+                                                     (2, 3, 3, 129, 129), (1, 6, 2, 2048, 2048)]):
+            if causal and QL != KL:
+                continue
+            dtype = torch.bfloat16 if trial % 2 == 0 else torch.float16
+            q, k, v, dO, _, _ = _inputs(B, QH, KH, QL, KL, E, dtype, 100 + trial)
+            qd, kd, vd, dOd = q.cuda(), k.cuda(), v.cuda(), dO.cuda()
+            o, lse = nnop._flash_attention(qd, kd, vd, causal=causal)
+            nnop.set_bwd_pair_mode(2)
+            ref = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=causal)
+            for mode in (3, 101, 103, 3):
+                nnop.set_bwd_pair_mode(mode)
+                got = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=causal)
+                assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]), (mode, B, QH, KH, QL, KL)
+                assert max_abs(got[0], ref[0]) <= 2 ** -7 * max(1.0, ref[0].abs().max().item())
+    finally:
+        nnop.set_bwd_pair_mode(0)
