@@ -93,10 +93,19 @@ int nnop_flash_attn_fwd(void* o, float* lse, const void* q, const void* k, const
 
 /* Forward with an optional caller-owned workspace.  With a workspace of at least
  * nnop_flash_attn_fwd_workspace_bytes(...) bytes (256-byte aligned), Float32 problems with E = 64
- * and no `pair` run on the tensor cores: q, k, v are split into two bf16 terms each (x ~ hi + lo,
- * 16 mantissa bits), S = Qh Kh^T + Qh Kl^T + Ql Kh^T and O = (Ph + Pl)(Vh + Vl) accumulate in fp32;
+ * run on the tensor cores: q, k, v are split into two fp16 terms each (x ~ hi + lo,
+ * 22 significant bits), S = Qh Kh^T + Qh Kl^T + Ql Kh^T and O = (Ph + Pl)(Vh + Vl) accumulate in fp32;
  * max abs error vs an fp64 evaluation stays below 1e-4.  Without it (or for other shapes) the call
- * is identical to nnop_flash_attn_fwd.  The size query returns 0 where no workspace is used. */
+ * is identical to nnop_flash_attn_fwd.  The size query returns 0 where no workspace is used.
+ *
+ * `pair` (the additive bias, (QH,QL,KL,B) column-major, src/attention.jl:55-62) runs on the tensor
+ * cores when the workspace is additionally extended by nnop_flash_attn_pair_workspace_bytes(...,
+ * backward = 0) bytes: total = round_up(fwd_workspace_bytes, 256) + pair_workspace_bytes.  The
+ * library then keeps a head-major copy of pair there (its layout has the head as the fastest axis,
+ * which no tile load can fetch).  Same rule for nnop_flash_attn_bwd with backward = 1 (copy of pair
+ * plus the staging area dpair is produced in): total = round_up(bwd_workspace_bytes, 256) +
+ * pair_workspace_bytes(..., 1).  With a smaller workspace `pair` is served by the SIMT kernels. */
+size_t nnop_flash_attn_pair_workspace_bytes(int dtype, int QL, int KL, int QH, int B, int backward);
 size_t nnop_flash_attn_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B);
 int nnop_flash_attn_fwd_ws(void* o, float* lse, const void* q, const void* k, const void* v,
                            const void* pair, const uint8_t* kpad_mask, int dtype, int E, int QL,

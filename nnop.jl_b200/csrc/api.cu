@@ -140,6 +140,14 @@ extern "C" size_t nnop_flash_attn_fwd_workspace_bytes(int dtype, int E, int QL, 
   return attn_sm100_fwd_workspace_bytes(dtype, E, QL, KL, QH, KH, B);
 }
 
+extern "C" size_t nnop_flash_attn_pair_workspace_bytes(int dtype, int QL, int KL, int QH, int B,
+                                                       int backward) {
+  if (dtype != NNOP_F32 && dtype != NNOP_F16 && dtype != NNOP_BF16) return 0;
+  return attn_pair_workspace_bytes(dtype, QL, KL, QH, B, backward != 0);
+}
+
+static inline size_t up256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
 extern "C" int nnop_flash_attn_fwd(void* o, float* lse, const void* q, const void* k, const void* v,
                                    const void* pair, const uint8_t* kpad_mask, int dtype, int E,
                                    int QL, int KL, int QH, int KH, int B, int causal, float scale,
@@ -166,6 +174,14 @@ extern "C" int nnop_flash_attn_fwd_ws(void* o, float* lse, const void* q, const 
       workspace_bytes >= attn_sm100_fwd_workspace_bytes(dtype, E, QL, KL, QH, KH, B) &&
       attn_sm100_fwd_workspace_bytes(dtype, E, QL, KL, QH, KH, B) > 0)
     p.fwd_ws = workspace;  // enables the tensor-core Float32 forward (E = 64)
+  if (pair && workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && KL > 0) {
+    // pair bias on the tensor cores: its head-major copy lives behind the base workspace
+    const size_t base = up256(attn_sm100_fwd_workspace_bytes(dtype, E, QL, KL, QH, KH, B));
+    if (workspace_bytes >= base + attn_pair_workspace_bytes(dtype, QL, KL, QH, B, false)) {
+      p.pair_t = static_cast<char*>(workspace) + base;
+      p.KLp = pair_klp(KL);
+    }
+  }
   const int mode = g_path_mode.load();
   const bool fast_ok = attn_sm100_supported(p, false);
   if (mode == 2 && !fast_ok)
@@ -220,13 +236,23 @@ extern "C" int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, co
   p.dtype = dtype; p.E = E; p.QL = QL; p.KL = KL; p.QH = QH; p.KH = KH; p.B = B;
   p.causal = causal ? 1 : 0; p.scale = scale;
   p.stream = static_cast<cudaStream_t>(stream);
+  if (pair && KL > 0 && QL > 0) {
+    // pair bias on the tensor cores: head-major pair and dpair staging behind the base workspace
+    const size_t base = up256(need);
+    const size_t one = attn_pair_workspace_bytes(dtype, QL, KL, QH, B, false);
+    if (workspace_bytes >= base + 2 * one) {
+      p.pair_t = static_cast<char*>(workspace) + base;
+      p.dpair_t = static_cast<char*>(workspace) + base + one;
+      p.KLp = pair_klp(KL);
+    }
+  }
   const int mode = g_path_mode.load();
-  // Float32, E = 64, no pair bias: split-bf16 tensor-core backward (attn_bwd_f32_sm100.cu)
+  // Float32, E = 64: split-fp16 tensor-core backward (attn_bwd_f32_sm100.cu)
   const bool al16 = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                       reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dO) |
                       reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
                       reinterpret_cast<uintptr_t>(dv)) & 15) == 0;
-  const bool f32_tc = dtype == NNOP_F32 && E == 64 && !pair && QL > 0 && KL > 0 && al16 &&
+  const bool f32_tc = dtype == NNOP_F32 && E == 64 && (!pair || p.pair_t) && QL > 0 && KL > 0 && al16 &&
                       QH <= 65535 && B <= 65535;
   const bool fast_ok = f32_tc || attn_sm100_supported(p, true);
   if (mode == 2 && !fast_ok)

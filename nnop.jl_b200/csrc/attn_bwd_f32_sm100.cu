@@ -39,6 +39,10 @@ struct Params {
   int QL, KL, QH, KH, QLp, causal;
   float scale, scale_log2;
   const uint8_t* kpad;
+  // additive bias (BIAS kernel): head-major fp32 copies (B, QH, QL, KLp), see attn_pair.cu
+  const float* pair_t;
+  float* dpair_t;
+  int KLp;
 };
 
 struct Smem {
@@ -60,6 +64,9 @@ struct Smem {
 __device__ __forceinline__ float bf_lo(uint32_t packed) { return unpack_lo<T>(packed); }
 __device__ __forceinline__ float bf_hi(uint32_t packed) { return unpack_hi<T>(packed); }
 
+// BIAS = true: S^T gets pair^T added before the exponential and dpair = dS is written out, both through
+// the head-major copies with lanes along the key axis (coalesced), as in attn_bwd_sm100.cu.
+template <bool BIAS>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -277,6 +284,27 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const float sl2 = p.scale_log2;
     for (int it = 0; it < n_it; ++it) {
       const int i = i0 + it % nqi;
+      float pf[64];
+      int64_t boff = 0;       // (BIAS) element offset of this thread's first bias / dpair entry
+      int nqv = 0;            // (BIAS) valid q columns of this half
+      if constexpr (BIAS) {
+        // bias of this step, parked in pf (dead here) while S^T is still being computed
+        const int bh_q = b * p.QH + hk * g + it / nqi;
+        const int qb = i * 128 + c0;
+        boff = (static_cast<int64_t>(bh_q) * QL + qb) * p.KLp + k0 + row;
+        nqv = min(64, QL - qb);
+        // unconditional loads (64 in flight per thread): out-of-range rows / keys re-read a valid
+        // entry instead of being predicated -- their P is zeroed or never used further down
+        const float* bb = p.pair_t + static_cast<int64_t>(bh_q) * QL * p.KLp + min(k0 + row, p.KLp - 1);
+        if (nqv == 64) {
+          const float* bp = bb + static_cast<int64_t>(qb) * p.KLp;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) pf[c] = bp[static_cast<int64_t>(c) * p.KLp];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) pf[c] = bb[static_cast<int64_t>(min(qb + c, QL - 1)) * p.KLp];
+        }
+      }
       mbar_wait(q_full, it & 1);   // lse2 / delta of this q block have landed
       mbar_wait(s_full, it & 1);
       tc_fence_after();
@@ -284,15 +312,19 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tmem_ld_x32(tmem_base + lane_off + kColS + c0, sr[0]);
       tmem_ld_x32(tmem_base + lane_off + kColS + c0 + 32, sr[1]);
       tmem_ld_wait();
-      float pf[64];
       const float4* l4 = reinterpret_cast<const float4*>(s_lse + c0);
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const float4 l = l4[u];
-        pf[4 * u + 0] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 0) & 31]), sl2, -l.x));
-        pf[4 * u + 1] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 1) & 31]), sl2, -l.y));
-        pf[4 * u + 2] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 2) & 31]), sl2, -l.z));
-        pf[4 * u + 3] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 3) & 31]), sl2, -l.w));
+        // with a bias: pf holds pair^T; (pair * log2e - lse2) replaces -lse2
+        const float b0 = BIAS ? fmaf(pf[4 * u + 0], kLog2e, -l.x) : -l.x;
+        const float b1 = BIAS ? fmaf(pf[4 * u + 1], kLog2e, -l.y) : -l.y;
+        const float b2 = BIAS ? fmaf(pf[4 * u + 2], kLog2e, -l.z) : -l.z;
+        const float b3 = BIAS ? fmaf(pf[4 * u + 3], kLog2e, -l.w) : -l.w;
+        pf[4 * u + 0] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 0) & 31]), sl2, b0));
+        pf[4 * u + 1] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 1) & 31]), sl2, b1));
+        pf[4 * u + 2] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 2) & 31]), sl2, b2));
+        pf[4 * u + 3] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 3) & 31]), sl2, b3));
       }
       if (p.causal && i == j) {
 #pragma unroll
@@ -344,6 +376,14 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         vh.w = pack2<T>(ds[6], ds[7]); vl.w = pack2<T>(ds[6] - bf_lo(vh.w), ds[7] - bf_hi(vh.w));
         *reinterpret_cast<uint4*>(drow_h + ((ch ^ (row & 7)) << 4)) = vh;
         *reinterpret_cast<uint4*>(drow_l + ((ch ^ (row & 7)) << 4)) = vl;
+        if constexpr (BIAS) {  // dpair = dS (before the 1/sqrt(E) that dQ / dK carry)
+          if (k0 + row < KL) {
+            float* dp = p.dpair_t + boff;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (8 * ch + e < nqv) dp[static_cast<int64_t>(8 * ch + e) * p.KLp] = ds[e];
+          }
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -553,17 +593,24 @@ int attn_f32_bwd(const AttnParams& a) {
   if (int rc = make_tmap_3d(&tdk, a.dk, NNOP_F32, 64, a.KL, bhk, 32, 128)) return rc;
   if (int rc = make_tmap_3d(&tdv, a.dv, NNOP_F32, 64, a.KL, bhk, 32, 128)) return rc;
   if (int rc = make_tmap_3d(&tdq, a.dq, NNOP_F32, 64, a.QL, bhq, 32, 128)) return rc;
-  NNOP_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  const bool bias = a.pair != nullptr;
+  auto kern = bias ? attn_bwd_f32_kernel<true> : attn_bwd_f32_kernel<false>;
+  NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  if (bias)
+    if (int rc = attn_pair_to_head_major(a)) return rc;
   Params bp;
   bp.lse2p = lse2p; bp.deltap = deltap;
   bp.QL = a.QL; bp.KL = a.KL; bp.QH = a.QH; bp.KH = a.KH; bp.QLp = QLp; bp.causal = a.causal;
   bp.scale = a.scale; bp.scale_log2 = a.scale * kLog2e;
   bp.kpad = a.kpad;
+  bp.pair_t = static_cast<const float*>(a.pair_t); bp.dpair_t = static_cast<float*>(a.dpair_t); bp.KLp = a.KLp;
   dim3 grid((a.KL + 127) / 128, a.KH, a.B);
   timing_begin(1, a.stream);
-  attn_bwd_f32_kernel<<<grid, kThreads, S::kTotal, a.stream>>>(tq, tk, tv, tdo, tdk, tdv, tdq, bp);
+  kern<<<grid, kThreads, S::kTotal, a.stream>>>(tq, tk, tv, tdo, tdk, tdv, tdq, bp);
   timing_end(1, a.stream);
   NNOP_LAUNCH_CHECK();
+  if (bias)
+    if (int rc = attn_dpair_from_head_major(a)) return rc;
   return NNOP_OK;
 }
 

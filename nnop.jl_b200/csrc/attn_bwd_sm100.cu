@@ -79,6 +79,10 @@ struct BwdParams {
   void* dv_ptr;
   int64_t total_k;
   const uint8_t* kpad;  // (B, KL) key padding mask, 1 = attend, or nullptr (dense mode only)
+  // additive bias (dense mode, BIAS kernels): head-major copies (B, QH, QL, KLp), see attn_pair.cu
+  const void* pair_t;
+  void* dpair_t;
+  int KLp;
 };
 
 // first padded-statistics row of packed sequence z (each sequence is padded to whole 128-row blocks)
@@ -101,7 +105,9 @@ struct BwdSmem {
   static constexpr int kTotal = kBar + kNumBars * 8 + 16;
 };
 
-template <typename T, int D>
+// BIAS = true: S^T gets pair^T added before the exponential and dpair = dS (src/attention_bwd.jl:120-131)
+// is written out, both through the head-major copies with lanes along the key axis (coalesced).
+template <typename T, int D, bool BIAS = false>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
                       const __grid_constant__ CUtensorMap tm_k,
@@ -363,6 +369,29 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
       const int i = i0 + it % nqi;
+      float pf[64];
+      int64_t boff = 0;       // (BIAS) element offset of this thread's first bias / dpair entry
+      int nqv = 0;            // (BIAS) valid q columns of this half
+      if constexpr (BIAS) {
+        // bias of this step, parked in pf (dead here) while S^T is still being computed:
+        // pair_t[bh_q][q][k] with lanes along k -> one 128-byte line per warp and q column
+        const int bh_q = b * p.QH + hk * g + it / nqi;
+        const int qb = i * 128 + c0;
+        boff = (static_cast<int64_t>(bh_q) * QL + qb) * p.KLp + k0 + row;
+        nqv = min(64, QL - qb);
+        // unconditional loads (64 in flight per thread): out-of-range rows / keys re-read a valid
+        // entry instead of being predicated -- their P is zeroed or never used further down
+        const T* bb = static_cast<const T*>(p.pair_t) + static_cast<int64_t>(bh_q) * QL * p.KLp +
+                      min(k0 + row, p.KLp - 1);
+        if (nqv == 64) {
+          const T* bp = bb + static_cast<int64_t>(qb) * p.KLp;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) pf[c] = to_f32<T>(bp[static_cast<int64_t>(c) * p.KLp]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) pf[c] = to_f32<T>(bb[static_cast<int64_t>(min(qb + c, QL - 1)) * p.KLp]);
+        }
+      }
       // ---- P^T ----
       mbar_wait(&q_full[s], (it >> 1) & 1);  // lse2 / delta of this stage have landed
       mbar_wait(s_full, it & 1);
@@ -372,15 +401,19 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       tmem_ld_x32(tmem_base + lane_off + kColS + c0, sr[0]);
       tmem_ld_x32(tmem_base + lane_off + kColS + c0 + 32, sr[1]);
       tmem_ld_wait();
-      float pf[64];
       const float4* l4 = reinterpret_cast<const float4*>(s_lse + s * 128 + c0);
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const float4 l = l4[u];
-        pf[4 * u + 0] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 0) & 31]), sl2, -l.x));
-        pf[4 * u + 1] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 1) & 31]), sl2, -l.y));
-        pf[4 * u + 2] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 2) & 31]), sl2, -l.z));
-        pf[4 * u + 3] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 3) & 31]), sl2, -l.w));
+        // with a bias: pf holds pair^T; (pair * log2e - lse2) replaces -lse2
+        const float b0 = BIAS ? fmaf(pf[4 * u + 0], kLog2e, -l.x) : -l.x;
+        const float b1 = BIAS ? fmaf(pf[4 * u + 1], kLog2e, -l.y) : -l.y;
+        const float b2 = BIAS ? fmaf(pf[4 * u + 2], kLog2e, -l.z) : -l.z;
+        const float b3 = BIAS ? fmaf(pf[4 * u + 3], kLog2e, -l.w) : -l.w;
+        pf[4 * u + 0] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 0) & 31]), sl2, b0));
+        pf[4 * u + 1] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 1) & 31]), sl2, b1));
+        pf[4 * u + 2] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 2) & 31]), sl2, b2));
+        pf[4 * u + 3] = fast_exp2(fmaf(__uint_as_float(sr[u >> 3][(4 * u + 3) & 31]), sl2, b3));
       }
       if (p.causal && i == j) {  // diagonal block: key k0+row is visible to query q0+c iff row <= c
 #pragma unroll
@@ -427,6 +460,14 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         v.z = pack2<T>(ds[4], ds[5]);
         v.w = pack2<T>(ds[6], ds[7]);
         *reinterpret_cast<uint4*>(drow + ((ch ^ (row & 7)) << 4)) = v;
+        if constexpr (BIAS) {  // dpair = dS (before the 1/sqrt(E) that dQ / dK carry)
+          if (k0 + row < KL) {
+            T* dp = static_cast<T*>(p.dpair_t) + boff;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (8 * ch + e < nqv) dp[static_cast<int64_t>(8 * ch + e) * p.KLp] = from_f32<T>(ds[e]);
+          }
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -1673,13 +1714,17 @@ int launch_bwd(const AttnParams& a) {
   bp.scale = a.scale; bp.scale_log2 = a.scale * kLog2e;
   bp.cu_q = a.cu_q; bp.cu_k = a.cu_k; bp.dk_ptr = a.dk; bp.dv_ptr = a.dv; bp.total_k = a.total_k;
   bp.kpad = packed ? nullptr : a.kpad;
+  bp.pair_t = a.pair_t; bp.dpair_t = a.dpair_t; bp.KLp = a.KLp;
+  const bool bias = a.pair != nullptr;
+  if (bias)
+    if (int rc = attn_pair_to_head_major(a)) return rc;
   const int nkv = (a.KL + 127) / 128;
   // kernel variant (nnop_set_bwd_pair_mode / NNOP_BWD_PAIR): 0 = automatic (persistent kernel when the
   // tile queue is at least two rounds deep, else one CTA per tile), 1 = CTA pairs (experiment),
   // 2 = one CTA per tile, 3 = persistent, 100+n = persistent on n CTAs (tests)
   const int mode = bwd_pair_mode();
   bool use_pair = false;
-  if constexpr (D == 128) use_pair = !packed && nkv >= 2 && mode == 1;
+  if constexpr (D == 128) use_pair = !packed && nkv >= 2 && mode == 1 && !bias;
   const int nq_blocks = (a.QL + 127) / 128;
   const int64_t n_tiles = static_cast<int64_t>(nkv) * a.KH * a.B;
   int num_sms = 148;
@@ -1688,7 +1733,7 @@ int launch_bwd(const AttnParams& a) {
     NNOP_CUDA_CHECK(cudaGetDevice(&dev));
     NNOP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const bool persist_ok = !packed && a.kpad == nullptr && (!a.causal || nq_blocks >= nkv) &&
+  const bool persist_ok = !packed && !bias && a.kpad == nullptr && (!a.causal || nq_blocks >= nkv) &&
                           n_tiles < (1LL << 30);
   const bool use_persist = !use_pair && persist_ok &&
                            (mode == 3 || mode >= 100 || (mode == 0 && n_tiles >= 2LL * num_sms));
@@ -1716,7 +1761,7 @@ int launch_bwd(const AttnParams& a) {
     timing_end(1, a.stream);
     NNOP_LAUNCH_CHECK();
   } else {
-    auto kern = attn_bwd_sm100_kernel<T, D>;
+    auto kern = bias ? attn_bwd_sm100_kernel<T, D, true> : attn_bwd_sm100_kernel<T, D, false>;
     NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     dim3 grid(nkv, a.KH, packed ? a.nseq : a.B);
     timing_begin(1, a.stream);
@@ -1730,6 +1775,8 @@ int launch_bwd(const AttnParams& a) {
         static_cast<T*>(a.dq), dqa, n8, a.scale);
     NNOP_LAUNCH_CHECK();
   }
+  if (bias)
+    if (int rc = attn_dpair_from_head_major(a)) return rc;
   return NNOP_OK;
 }
 

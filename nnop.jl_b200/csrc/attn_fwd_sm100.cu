@@ -19,6 +19,8 @@
 //
 // Ragged sizes: TMA zero-fills rows past QL / KL (per head: the tensor maps are 3-D), key
 // columns >= KL are masked to -inf, and the TMA store clips rows >= QL.
+#include <type_traits>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -26,7 +28,6 @@ namespace nnop {
 namespace {
 
 constexpr int kFwdThreads = 384;
-constexpr int kNStage = 4;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
@@ -65,15 +66,18 @@ struct FwdParams {
   const uint8_t* kpad;  // (B, KL) key padding mask, 1 = attend, or nullptr (dense mode only)
 };
 
-template <int D>
+// NS = stages of the K/V ring; BIASB = bytes of additive-bias staging (pair: 4 x 16 KB, ring of 3)
+template <int D, int NS = 4, int BIASB = 0>
 struct FwdSmem {
+  static constexpr int kNStage = NS;
   static constexpr int kTileBytes = 128 * D * 2;   // one Q tile / K block / V block
   static constexpr int kBoxBytes = 128 * 64 * 2;   // one 64-column TMA box (16 KB)
   static constexpr int kNBox = D / 64;
   static constexpr int kQOff = 0;
   static constexpr int kKVOff = 2 * kTileBytes;
-  static constexpr int kBarOff = kKVOff + kNStage * kTileBytes;
-  static constexpr int kNumBars = 2 + 2 * kNStage + 10;
+  static constexpr int kBiasOff = kKVOff + kNStage * kTileBytes;  // [2 tiles][2 buffers] x 16 KB
+  static constexpr int kBarOff = kBiasOff + BIASB;
+  static constexpr int kNumBars = 2 + 2 * kNStage + 10 + 8;
   static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
   static constexpr int kDynBytes = kTotal + 1024;  // slack for manual 1024-byte alignment
 };
@@ -84,13 +88,24 @@ struct FwdSmem {
 // into Ph + Pl (two TMEM operands), O' = (Ph + Pl) [Vh | Vl] accumulates both V terms side by side
 // and the epilogue adds the two halves and writes fp32.  Same tiles, barriers and shared-memory /
 // TMEM footprint as the bf16 E = 128 kernel; 1.75x its tensor time for half its FLOPs.
-template <typename T, int D, bool SPLIT = false>
+//
+// BIAS = true adds the `pair` term (src/attention.jl:55-62): S' = S * scale + pair[h, q, k, b].  The
+// launcher first transposes pair into head-major (B, QH, QL, KLp) rows (attn_pair.cu) so that a
+// (128 query) x (128-byte) box of it is one TMA load; warp 3 streams those boxes through two 16 KB
+// buffers per tile (the K/V ring gives up one stage for them) and the softmax warpgroups fold them
+// into the logits (in log2 units) before the mask / max / exp steps.
+template <typename T, int D, bool SPLIT = false, bool BIAS = false>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
                       const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v,
-                      const __grid_constant__ CUtensorMap tm_o, const FwdParams p) {
-  using S = FwdSmem<D>;
+                      const __grid_constant__ CUtensorMap tm_o,
+                      const __grid_constant__ CUtensorMap tm_bias, const FwdParams p) {
+  using S = FwdSmem<D, BIAS ? 3 : 4, BIAS ? 65536 : 0>;
+  constexpr int kNStage = S::kNStage;
+  using BT = typename std::conditional<SPLIT, float, T>::type;  // element type of the bias
+  constexpr int kBiasCols = 128 / static_cast<int>(sizeof(BT));  // keys per 128-byte box row
+  constexpr int kBiasChunks = 128 / kBiasCols;                   // boxes per 128-key block
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -104,6 +119,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   uint64_t* s_read = s_full + 2;               // [2]  S_t now lives in registers (columns 64.. reusable)
   uint64_t* p_half = s_full + 4;               // [2][2]  P_t keys 0..63 / 64..127 written
   uint64_t* o_full = s_full + 8;               // [2]
+  uint64_t* bias_full = s_full + 10;           // [2 tiles][2 buffers]
+  uint64_t* bias_empty = s_full + 14;          // [2 tiles][2 buffers]
+  uint8_t* sBias = smem + S::kBiasOff;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S::kNumBars);
 
   const int warp = threadIdx.x >> 5;
@@ -168,7 +186,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       mbar_init(&p_half[2 * t], 4);
       mbar_init(&p_half[2 * t + 1], 4);
       mbar_init(&o_full[t], 1);
+      for (int u = 0; u < 2; ++u) {
+        mbar_init(&bias_full[2 * t + u], 1);
+        mbar_init(&bias_empty[2 * t + u], 4);  // one arrival per softmax warp
+      }
     }
+    if constexpr (BIAS) tma_prefetch_desc(&tm_bias);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -210,6 +233,21 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         load_kv(&tm_k, i);
         load_kv(&tm_v, i);
       }
+    } else if (BIAS && warp == 3 && lane == 0 && nblk > 0) {
+      // ================================ bias producer ================================
+      // box c of block i of tile t -> buffer (i * kBiasChunks + c) & 1 of that tile, in the order the
+      // softmax warpgroups consume them (the two tiles interleaved)
+      for (int i = 0; i < nblk; ++i)
+        for (int c = 0; c < kBiasChunks; ++c)
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (i >= (t ? nb1 : nb0)) continue;
+            const int n = i * kBiasChunks + c;
+            const int u = 2 * t + (n & 1);
+            mbar_wait(&bias_empty[u], ((n >> 1) & 1) ^ 1);
+            mbar_arrive_expect_tx(&bias_full[u], 16384);
+            tma_load_3d(sBias + u * 16384, &tm_bias, &bias_full[u], i * 128 + c * kBiasCols, q0 + t * 128, bh_q);
+          }
     } else if (warp == 1 && nblk > 0) {
       // ================================ MMA issuer ===================================
       // The whole warp runs the (uniform) control flow and the barrier waits; one elected lane
@@ -351,7 +389,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
       const uint32_t tS = tmem_base + lane_off + t * 128;
       const uint32_t tO = tmem_base + lane_off + 256 + t * D;
-      const float sl2 = p.scale_log2;
+      // with a bias the logits are moved to log2 units as they are folded, so the rest runs unscaled
+      const float sl2 = BIAS ? 1.f : p.scale_log2;
       float m_used = -1e30f;  // reference max in scaled log2 units (finite: see the speculation note)
       float l = 0.f;
 
@@ -382,6 +421,42 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_read[t]);
+        }
+        if constexpr (BIAS) {
+          // S <- S * scale * log2e + pair * log2e, one 128-byte box row (this thread's query) at a time
+          const float sraw = p.scale_log2;
+#pragma unroll
+          for (int c = 0; c < kBiasChunks; ++c) {
+            const int n = i * kBiasChunks + c;
+            const int u = 2 * t + (n & 1);
+            mbar_wait(&bias_full[u], (n >> 1) & 1);
+            const uint8_t* brow = sBias + u * 16384 + row * 128;
+#pragma unroll
+            for (int u16 = 0; u16 < 8; ++u16) {
+              const uint4 bv = *reinterpret_cast<const uint4*>(brow + ((u16 ^ (row & 7)) << 4));
+              if constexpr (sizeof(BT) == 4) {
+                const int col = c * 32 + u16 * 4;
+                const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  uint32_t& sv = sr[(col + e) >> 5][(col + e) & 31];
+                  sv = __float_as_uint(fmaf(__uint_as_float(sv), sraw, __uint_as_float(w[e]) * kLog2e));
+                }
+              } else {
+                const int col = c * 64 + u16 * 8;
+                const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  uint32_t& s0 = sr[(col + 2 * e) >> 5][(col + 2 * e) & 31];
+                  uint32_t& s1 = sr[(col + 2 * e + 1) >> 5][(col + 2 * e + 1) & 31];
+                  s0 = __float_as_uint(fmaf(__uint_as_float(s0), sraw, unpack_lo<T>(w[e]) * kLog2e));
+                  s1 = __float_as_uint(fmaf(__uint_as_float(s1), sraw, unpack_hi<T>(w[e]) * kLog2e));
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bias_empty[u]);
+          }
         }
 
         const int k0 = i * 128;
@@ -616,10 +691,11 @@ int launch_split(__half* out, const void* in, int64_t rows, cudaStream_t st) {
 }
 
 // Float32, E = 64: split q, k, v into [hi | lo] bf16 rows in the workspace, then the SPLIT kernel
+template <bool BIAS>
 int launch_fwd_f32(const AttnParams& a) {
   using T = __half;
   constexpr int D = 128;
-  using S = FwdSmem<D>;
+  using S = FwdSmem<D, BIAS ? 3 : 4, BIAS ? 65536 : 0>;
   const int64_t rq = static_cast<int64_t>(a.B) * a.QH * a.QL, rk = static_cast<int64_t>(a.B) * a.KH * a.KL;
   T* qs = static_cast<T*>(a.fwd_ws);
   T* ks = qs + rq * 128;
@@ -633,7 +709,10 @@ int launch_fwd_f32(const AttnParams& a) {
   if (int rc = make_tmap_3d(&tk, ks, NNOP_F16, D, a.KL, bhk, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&tv, vs, NNOP_F16, D, a.KL, bhk, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&to, a.o, NNOP_F32, 64, a.QL, bhq, 32, 128)) return rc;
-  auto kern = attn_fwd_sm100_kernel<T, D, true>;
+  alignas(64) CUtensorMap tb = to;  // unused without a bias
+  if constexpr (BIAS)
+    if (int rc = make_tmap_3d(&tb, a.pair_t, NNOP_F32, a.KLp, a.QL, bhq, 32, 128)) return rc;
+  auto kern = attn_fwd_sm100_kernel<T, D, true, BIAS>;
   NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynBytes));
   FwdParams fp;
   fp.lse = a.lse;
@@ -643,15 +722,15 @@ int launch_fwd_f32(const AttnParams& a) {
   fp.kpad = a.kpad;
   dim3 grid((a.QL + 255) / 256, a.QH, a.B);
   timing_begin(0, a.stream);
-  kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, fp);
+  kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, tb, fp);
   timing_end(0, a.stream);
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
 }
 
-template <typename T, int D>
+template <typename T, int D, bool BIAS = false>
 int launch_fwd(const AttnParams& a) {
-  using S = FwdSmem<D>;
+  using S = FwdSmem<D, BIAS ? 3 : 4, BIAS ? 65536 : 0>;
   alignas(64) CUtensorMap tq, tk, tv, to;
   const bool packed = a.cu_q != nullptr;
   // packed mode: the tensors are (QH, total_q, E) / (KH, total_k, E); a.QL / a.KL hold the maxima
@@ -663,7 +742,10 @@ int launch_fwd(const AttnParams& a) {
   if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&to, a.o, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
-  auto kern = attn_fwd_sm100_kernel<T, D>;
+  alignas(64) CUtensorMap tb = to;  // unused without a bias
+  if constexpr (BIAS)
+    if (int rc = make_tmap_3d(&tb, a.pair_t, a.dtype, a.KLp, a.QL, bhq, 64, 128)) return rc;
+  auto kern = attn_fwd_sm100_kernel<T, D, false, BIAS>;
   NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynBytes));
   FwdParams fp;
   fp.lse = a.lse;
@@ -673,7 +755,7 @@ int launch_fwd(const AttnParams& a) {
   fp.kpad = packed ? nullptr : a.kpad;
   dim3 grid((a.QL + 255) / 256, a.QH, packed ? a.nseq : a.B);
   timing_begin(0, a.stream);
-  kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, fp);
+  kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, tb, fp);
   timing_end(0, a.stream);
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
@@ -692,7 +774,10 @@ bool attn_sm100_supported(const AttnParams& a, bool backward) {
   const bool f32_split = a.dtype == NNOP_F32 && a.E == 64 && !backward && a.fwd_ws != nullptr && !a.cu_q;
   if (a.dtype != NNOP_F16 && a.dtype != NNOP_BF16 && !f32_split) return false;
   if (a.E != 64 && a.E != 128) return false;
-  if (a.pair) return false;  // the additive bias is served by the generic path
+  // the additive bias needs its head-major copy (and, backward, a dpair staging area) in the
+  // workspace (nnop_flash_attn_pair_workspace_bytes); without it the generic path serves it
+  if (a.pair && (a.pair_t == nullptr || a.cu_q != nullptr)) return false;
+  if (a.pair && backward && a.dpair_t == nullptr) return false;
   if (a.QL < 1 || a.KL < 1) return false;
   if (a.QH > 65535 || a.B > 65535 || a.nseq > 65535) return false;
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -711,7 +796,14 @@ size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, 
 }
 
 int attn_sm100_fwd(const AttnParams& a) {
-  if (a.dtype == NNOP_F32) return launch_fwd_f32(a);
+  if (a.pair) {
+    if (int rc = attn_pair_to_head_major(a)) return rc;
+    if (a.dtype == NNOP_F32) return launch_fwd_f32<true>(a);
+    if (a.dtype == NNOP_BF16)
+      return a.E == 128 ? launch_fwd<__nv_bfloat16, 128, true>(a) : launch_fwd<__nv_bfloat16, 64, true>(a);
+    return a.E == 128 ? launch_fwd<__half, 128, true>(a) : launch_fwd<__half, 64, true>(a);
+  }
+  if (a.dtype == NNOP_F32) return launch_fwd_f32<false>(a);
   if (a.dtype == NNOP_BF16)
     return a.E == 128 ? launch_fwd<__nv_bfloat16, 128>(a) : launch_fwd<__nv_bfloat16, 64>(a);
   return a.E == 128 ? launch_fwd<__half, 128>(a) : launch_fwd<__half, 64>(a);

@@ -68,6 +68,11 @@ struct AttnParams {
   int64_t total_q, total_k;
   // forward workspace (nnop_flash_attn_fwd_ws): [hi | lo] bf16 copies of q, k, v for the Float32 path
   void* fwd_ws;
+  // pair bias on the tcgen05 path: head-major copy of pair (B, QH, QL, KLp) and, backward, the staging
+  // area dpair is produced in (same layout); KLp = KL rounded up to 32 elements
+  void* pair_t;
+  void* dpair_t;
+  int KLp;
 };
 
 // one-shot timing hook (api.cu); which: 0 forward kernel, 1 backward main kernel
@@ -94,6 +99,12 @@ bool attn_sm100_bwd_available();
 void attn_sm100_set_bwd_pair_mode(int mode);  // 0 auto, 1 CTA pairs, 2 one CTA per tile, 3 persistent, 100+n persistent on n CTAs
 size_t attn_sm100_bwd_workspace_bytes(int E, int QL, int QH, int B);
 size_t attn_sm100_bwd_packed_workspace_bytes(int E, int64_t total_q, int nseq, int QH);
+
+// attn_pair.cu -- layout changes of the additive bias for the tcgen05 path
+inline int pair_klp(int KL) { return (KL + 31) & ~31; }
+size_t attn_pair_workspace_bytes(int dtype, int QL, int KL, int QH, int B, bool backward);
+int attn_pair_to_head_major(const AttnParams& p);    // pair (B,KL,QL,QH) -> pair_t (B,QH,QL,KLp)
+int attn_dpair_from_head_major(const AttnParams& p);  // dpair_t -> dpair, zero where masked
 
 // TMA descriptor helper (api.cu): 3-D map over a row-major (outer, rows, inner) tensor of
 // nnop_dtype_t elements, box (box_inner, box_rows, 1), 128-byte swizzle, zero OOB fill.

@@ -48,6 +48,7 @@ SIGNATURES = {
     "nnop_set_bwd_pair_mode": (_i, [_i]),
     "nnop_flash_attn_fwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, _vp]),
     "nnop_flash_attn_fwd_workspace_bytes": (_sz, [_i] * 7),
+    "nnop_flash_attn_pair_workspace_bytes": (_sz, [_i] * 6),
     "nnop_flash_attn_fwd_ws": (_i, [_vp] * 7 + [_i] * 8 + [_f, _vp, _sz, _vp]),
     "nnop_flash_attn_bwd_workspace_bytes": (_sz, [_i] * 7),
     "nnop_flash_attn_bwd": (_i, [_vp] * 12 + [_i] * 8 + [_f, _vp, _sz, _vp]),

@@ -105,6 +105,10 @@ def _attn_dims(q, k, v, pair, kpad_mask):
     return B, QH, QL, QE, KH, KL
 
 
+def _up256(n: int) -> int:
+    return (n + 255) & ~255
+
+
 def _flash_attention(q, k, v, pair=None, *, causal: bool, kpad_mask=None):
     """`_flash_attention` (src/attention.jl:133-177).  Returns ``(o, lse)``."""
     _req(q, k, v, pair, kpad_mask)
@@ -112,7 +116,9 @@ def _flash_attention(q, k, v, pair=None, *, causal: bool, kpad_mask=None):
     o = torch.empty_like(q)
     lse = torch.empty((B, QH, QL), dtype=torch.float32, device=q.device)
     scale = 1.0 / math.sqrt(E)
-    ws_bytes = lib.nnop_flash_attn_fwd_workspace_bytes(_dt(q), E, QL, KL, QH, KH, B) if pair is None else 0
+    ws_bytes = lib.nnop_flash_attn_fwd_workspace_bytes(_dt(q), E, QL, KL, QH, KH, B)
+    if pair is not None:  # head-major copy of the bias: keeps `pair` on the tensor-core path
+        ws_bytes = _up256(ws_bytes) + lib.nnop_flash_attn_pair_workspace_bytes(_dt(q), QL, KL, QH, B, 0)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if ws_bytes else None
     check(lib.nnop_flash_attn_fwd_ws(_p(o), _p(lse), _p(q), _p(k), _p(v), _p(pair), _p(kpad_mask),
                                      _dt(q), E, QL, KL, QH, KH, B, int(bool(causal)), scale,
@@ -131,6 +137,8 @@ def grad_flash_attention(dO, o, lse, q, k, v, pair=None, *, causal: bool, kpad_m
     dv = torch.empty_like(v)
     dpair = torch.empty_like(pair) if pair is not None else None
     ws_bytes = lib.nnop_flash_attn_bwd_workspace_bytes(_dt(q), E, QL, KL, QH, KH, B)
+    if pair is not None:  # head-major pair + dpair staging (tensor-core path)
+        ws_bytes = _up256(ws_bytes) + lib.nnop_flash_attn_pair_workspace_bytes(_dt(q), QL, KL, QH, B, 1)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=q.device)
     scale = 1.0 / math.sqrt(E)
     check(lib.nnop_flash_attn_bwd(_p(dq), _p(dk), _p(dv), _p(dpair), _p(dO), _p(o), _p(lse), _p(q),
