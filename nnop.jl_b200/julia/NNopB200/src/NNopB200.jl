@@ -34,6 +34,13 @@ within_gradient(x) = false                                                     #
 CRC.rrule(::typeof(within_gradient), x) = true, _ -> (CRC.NoTangent(), CRC.NoTangent())
 
 # ------------------------------------------------------------------ flash attention
+# workspace size with the pair extension: round_up(base, 256) + nnop_flash_attn_pair_workspace_bytes
+function pair_workspace(base, ::Type{T}, QL, KL, QH, B, backward::Bool) where T
+    extra = ccall((:nnop_flash_attn_pair_workspace_bytes, libnnop_b200), Csize_t,
+        (Cint, Cint, Cint, Cint, Cint, Cint), dtype_code(T), QL, KL, QH, B, backward)
+    return Csize_t((base + 255) & ~Csize_t(255)) + extra
+end
+
 # _flash_attention: src/attention.jl:133-177.  Residuals: (o, lse, nothing) -- one Float32
 # log-sum-exp replaces the reference's (ms, ls); they are private to the rrule closure.
 function _flash_attention(
@@ -50,9 +57,11 @@ function _flash_attention(
 
     o = similar(q)
     lse = CUDA.zeros(Float32, QL, QH, B)
-    # optional workspace: lets Float32 (E = 64, no pair) run on the tensor cores (split fp16 operands)
-    nbytes = isnothing(pair) ? ccall((:nnop_flash_attn_fwd_workspace_bytes, libnnop_b200), Csize_t,
-        (Cint, Cint, Cint, Cint, Cint, Cint, Cint), dtype_code(T), QE, QL, KL, QH, KH, B) : Csize_t(0)
+    # optional workspace: lets Float32 (E = 64) run on the tensor cores (split fp16 operands) and, with
+    # the pair extension, keeps the additive bias on the tensor-core path (head-major copy of `pair`)
+    nbytes = ccall((:nnop_flash_attn_fwd_workspace_bytes, libnnop_b200), Csize_t,
+        (Cint, Cint, Cint, Cint, Cint, Cint, Cint), dtype_code(T), QE, QL, KL, QH, KH, B)
+    isnothing(pair) || (nbytes = pair_workspace(nbytes, T, QL, KL, QH, B, false))
     ws = nbytes > 0 ? CuArray{UInt8}(undef, nbytes) : nothing
     check(ccall((:nnop_flash_attn_fwd_ws, libnnop_b200), Cint,
         (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
@@ -76,6 +85,7 @@ function ∇flash_attention(
     dpair = isnothing(pair) ? nothing : similar(pair)
     nbytes = ccall((:nnop_flash_attn_bwd_workspace_bytes, libnnop_b200), Csize_t,
         (Cint, Cint, Cint, Cint, Cint, Cint, Cint), dtype_code(T), QE, QL, KL, QH, KH, B)
+    isnothing(pair) || (nbytes = pair_workspace(nbytes, T, QL, KL, QH, B, true))
     ws = CuArray{UInt8}(undef, max(nbytes, 1))
     check(ccall((:nnop_flash_attn_bwd, libnnop_b200), Cint,
         (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
