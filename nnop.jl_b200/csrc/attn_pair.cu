@@ -17,11 +17,15 @@ constexpr int kTP = 64;  // tile edge: 16 independent loads per thread keep enou
 // in (B, KL, C) with C = QL * QH, c = q * QH + h  ->  out (B, QH, QL, KLp)
 template <typename T>
 __global__ void __launch_bounds__(256)
-pair_to_head_major_kernel(T* __restrict__ out, const T* __restrict__ in, int KL, int QL, int QH, int KLp) {
+pair_to_head_major_kernel(T* __restrict__ out, const T* __restrict__ in, int KL, int QL, int QH, int KLp,
+                          int causal) {
   __shared__ T tile[kTP][kTP + 1];
   const int b = blockIdx.z;
   const int C = QL * QH;
   const int k0 = blockIdx.x * kTP, c0 = blockIdx.y * kTP;
+  // causal: a query row q only ever sees keys below q + 256 (forward: its 256-row tile's diagonal
+  // blocks; backward: 128-row blocks), and everything above the diagonal is overwritten by the mask
+  if (causal && k0 >= (c0 + kTP - 1) / QH + 256) return;
   const T* src = in + static_cast<int64_t>(b) * KL * C;
 #pragma unroll
   for (int r = threadIdx.y; r < kTP; r += 8) {
@@ -58,6 +62,7 @@ dpair_from_head_major_kernel(T* __restrict__ out, const T* __restrict__ in, cons
   const int b = blockIdx.z;
   const int C = QL * QH;
   const int k0 = blockIdx.x * kTP, c0 = blockIdx.y * kTP;
+  const bool all_dead = causal && k0 > (c0 + kTP - 1) / QH;  // whole tile above the diagonal: zeros
   bool keep[kTP / 32];
 #pragma unroll
   for (int kk = 0; kk < kTP; kk += 32) {
@@ -72,7 +77,7 @@ dpair_from_head_major_kernel(T* __restrict__ out, const T* __restrict__ in, cons
 #pragma unroll
     for (int kk = 0; kk < kTP; kk += 32) {
       const int k = k0 + kk + threadIdx.x;
-      const bool live = c < C && keep[kk / 32] && !(causal && k > q);
+      const bool live = !all_dead && c < C && keep[kk / 32] && !(causal && k > q);
       tile[r][kk + threadIdx.x] = live ? src[k] : T(0);
     }
   }
@@ -105,10 +110,11 @@ int attn_pair_to_head_major(const AttnParams& a) {
   dim3 grid((a.KLp + kTP - 1) / kTP, (C + kTP - 1) / kTP, a.B), block(32, 8);
   if (a.dtype == NNOP_F32)
     pair_to_head_major_kernel<float><<<grid, block, 0, a.stream>>>(
-        static_cast<float*>(a.pair_t), static_cast<const float*>(a.pair), a.KL, a.QL, a.QH, a.KLp);
+        static_cast<float*>(a.pair_t), static_cast<const float*>(a.pair), a.KL, a.QL, a.QH, a.KLp, a.causal);
   else  // 16-bit payloads are moved bit for bit
     pair_to_head_major_kernel<uint16_t><<<grid, block, 0, a.stream>>>(
-        static_cast<uint16_t*>(a.pair_t), static_cast<const uint16_t*>(a.pair), a.KL, a.QL, a.QH, a.KLp);
+        static_cast<uint16_t*>(a.pair_t), static_cast<const uint16_t*>(a.pair), a.KL, a.QL, a.QH, a.KLp,
+        a.causal);
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
 }
