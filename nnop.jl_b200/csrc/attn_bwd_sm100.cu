@@ -79,6 +79,10 @@ struct BwdParams {
   void* dv_ptr;
   int64_t total_k;
   const uint8_t* kpad;  // (B, KL) key padding mask, 1 = attend, or nullptr (dense mode only)
+  // persistent kernel, packed mode: tile_pre[z] = number of (kv block, kv head) tiles of the
+  // sequences before z (nseq + 1 entries, built by packed_tile_prefix_kernel)
+  const int* tile_pre;
+  int nseq;
   // additive bias (dense mode, BIAS kernels): head-major copies (B, QH, QL, KLp), see attn_pair.cu
   const void* pair_t;
   void* dpair_t;
@@ -101,7 +105,7 @@ struct BwdSmem {
   static constexpr int kdQs = kdS + 2 * kBox;   // 2 x (128 rows x 32 fp32)
   static constexpr int kStat = kdQs + 2 * 16384;  // lse2[2][128], delta[2][128]
   static constexpr int kBar = kStat + 2048;
-  static constexpr int kNumBars = 24;  // 14 used by the plain kernel, 24 by the persistent one
+  static constexpr int kNumBars = 28;  // 14 used by the plain kernel, 24 (+ 32 bytes of tile ring) by the persistent one
   static constexpr int kTotal = kBar + kNumBars * 8 + 16;
 };
 
@@ -630,7 +634,7 @@ struct PersistBars {
     kCount = 24
   };
 };
-static_assert(PersistBars::kCount <= BwdSmem<128>::kNumBars, "barrier area too small");
+static_assert(PersistBars::kCount + 4 <= BwdSmem<128>::kNumBars, "barrier area too small for the tile ring");
 
 template <typename T, int D>
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -655,12 +659,38 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
   float* s_del = reinterpret_cast<float*>(smem + S::kStat + 1024);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S::kNumBars);
-  volatile int* s_tile = reinterpret_cast<volatile int*>(tmem_slot + 2);  // [2]
+  // tile ring: {batch element or packed sequence, kv block, kv head, 1 = tile / -1 = queue empty}
+  volatile int* s_tile = reinterpret_cast<volatile int*>(bars + PersistBars::kCount);  // [2][4]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int g = p.QH / p.KH;
-  const int nq = (p.QL + 127) >> 7;
+  const bool packed = p.cu_q != nullptr;
+
+  // everything a role needs to know about a tile, derived from its ring record
+  struct Tile {
+    int b, j, hk, k0, QL, KL, q_off, k_off, st_off, i0, nqi, n_it, bh_kv;
+  };
+  auto make_tile = [&](int zb, int j, int hk) -> Tile {
+    Tile t;
+    t.j = j; t.hk = hk; t.k0 = j * 128;
+    if (packed) {
+      t.q_off = p.cu_q[zb];
+      t.QL = p.cu_q[zb + 1] - t.q_off;
+      t.k_off = p.cu_k[zb];
+      t.KL = p.cu_k[zb + 1] - t.k_off;
+      t.st_off = packed_stat_row(t.q_off, zb);
+      t.b = 0;
+    } else {
+      t.b = zb; t.QL = p.QL; t.KL = p.KL; t.q_off = 0; t.k_off = 0; t.st_off = 0;
+    }
+    const int nq = (t.QL + 127) >> 7;
+    t.i0 = p.causal ? j : 0;
+    t.nqi = nq > t.i0 ? nq - t.i0 : 0;
+    t.n_it = t.nqi * g;
+    t.bh_kv = t.b * p.KH + hk;
+    return t;
+  };
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -690,32 +720,74 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 256 + D;
 
-  // every consumer role fetches the n-th tile id the same way
-  auto next_tile = [&](int n) -> int {
+  // every consumer role fetches the n-th tile record the same way (false = queue empty)
+  auto next_tile = [&](int n, Tile& t) -> bool {
     const int slot = n & 1;
     mbar_wait(bars + PB::kTileFull + slot, (n >> 1) & 1);
-    const int t = s_tile[slot];
+    const int zb = s_tile[4 * slot], j = s_tile[4 * slot + 1], hk = s_tile[4 * slot + 2];
+    const int flag = s_tile[4 * slot + 3];
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + PB::kTileEmpty + slot);
-    return t;
+    if (flag < 0) return false;
+    t = make_tile(zb, j, hk);
+    return true;
   };
 
   if (warp < 4) {
     setmaxnreg_dec<88>();
     if (warp == 3) {
       // ================================ tile scheduler ===============================
-      if (lane == 0) {
-        for (int n = 0;; ++n) {
-          const int slot = n & 1;
-          // a tile is claimed only when this CTA is about to need it: tiles claimed early would sit
-          // in the ring while other CTAs run dry at the end of the queue
-          if (n > 0) mbar_wait(bars + PB::kSchedGo, (n - 1) & 1);
-          mbar_wait(bars + PB::kTileEmpty + slot, ((n >> 1) & 1) ^ 1);
-          const int t = atomicAdd(tile_counter, 1);
-          s_tile[slot] = t < n_tiles ? t : -1;
-          mbar_arrive(bars + PB::kTileFull + slot);
-          if (t >= n_tiles) break;
+      // The whole warp runs it (uniformly); lane 0 claims and publishes.  Dense: tile t = ((b * KH +
+      // hk) * nkv + j).  Packed: sequence z by binary search in tile_pre, then hk-major, j fastest.
+      const int total = packed ? p.tile_pre[p.nseq] : n_tiles;
+      for (int n = 0;; ++n) {
+        const int slot = n & 1;
+        // a tile is claimed only when this CTA is about to need it: tiles claimed early would sit
+        // in the ring while other CTAs run dry at the end of the queue
+        if (n > 0) mbar_wait(bars + PB::kSchedGo, (n - 1) & 1);
+        mbar_wait(bars + PB::kTileEmpty + slot, ((n >> 1) & 1) ^ 1);
+        int zb = 0, j = 0, hk = 0, flag = -1;
+        for (;;) {
+          int t = 0;
+          if (lane == 0) t = atomicAdd(tile_counter, 1);
+          t = __shfl_sync(0xffffffffu, t, 0);
+          if (t >= total) break;
+          if (packed) {
+            int lo = 0, hi = p.nseq;  // largest z with tile_pre[z] <= t
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              if (p.tile_pre[mid] <= t) lo = mid; else hi = mid;
+            }
+            zb = lo;
+            const int tl = t - p.tile_pre[zb];
+            const int nkv_z = (p.tile_pre[zb + 1] - p.tile_pre[zb]) / p.KH;
+            hk = tl / nkv_z;
+            j = tl - hk * nkv_z;
+          } else {
+            j = t % nkv;
+            const int u = t / nkv;
+            hk = u % p.KH;
+            zb = u / p.KH;
+          }
+          const Tile ti = make_tile(zb, j, hk);
+          if (ti.n_it > 0) { flag = 1; break; }
+          // no visible query for this kv block (packed sequence without queries): dK = dV = 0, written
+          // here with plain stores; the tile is not published
+          {
+            const int rows = min(128, ti.KL - ti.k0);
+            constexpr int kCPR = D / 8;
+            const int64_t base = (static_cast<int64_t>(hk) * p.total_k + ti.k_off + ti.k0) * D;
+            for (int idx = lane; idx < rows * kCPR; idx += 32) {
+              reinterpret_cast<uint4*>(static_cast<T*>(p.dk_ptr) + base)[idx] = make_uint4(0u, 0u, 0u, 0u);
+              reinterpret_cast<uint4*>(static_cast<T*>(p.dv_ptr) + base)[idx] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
         }
+        if (lane == 0) {
+          s_tile[4 * slot] = zb; s_tile[4 * slot + 1] = j; s_tile[4 * slot + 2] = hk; s_tile[4 * slot + 3] = flag;
+          mbar_arrive(bars + PB::kTileFull + slot);
+        }
+        if (flag < 0) break;
       }
     } else if (warp == 0) {
       // ================================ TMA producer =================================
@@ -724,15 +796,13 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
         for (int tl = 0;; ++tl) {
           const int slot = tl & 1;
           mbar_wait(bars + PB::kTileFull + slot, (tl >> 1) & 1);
-          const int t = s_tile[slot];
+          const int zb = s_tile[4 * slot], tj = s_tile[4 * slot + 1], thk = s_tile[4 * slot + 2];
+          const int flag = s_tile[4 * slot + 3];
           mbar_arrive(bars + PB::kTileEmpty + slot);
-          if (t < 0) break;
-          const int j = t % nkv, u = t / nkv;
-          const int hk = u % p.KH, b = u / p.KH;
-          const int k0 = j * 128, bh_kv = b * p.KH + hk;
-          const int i0 = p.causal ? j : 0;
-          const int nqi = nq - i0;
-          const int n_it = nqi * g;
+          if (flag < 0) break;
+          const Tile ti = make_tile(zb, tj, thk);
+          const int hk = ti.hk, b = ti.b, k0 = ti.k0, bh_kv = ti.bh_kv, i0 = ti.i0, nqi = ti.nqi, n_it = ti.n_it;
+          const int q_off = ti.q_off, k_off = ti.k_off, st_off = ti.st_off;
           auto load_q = [&](int it) {
             const int gi = gs + it;
             const int s = gi & 1;
@@ -742,8 +812,8 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
             mbar_arrive_expect_tx(bars + PB::kQFull + s, S::kTile + 1024);
 #pragma unroll
             for (int bx = 0; bx < S::kNBox; ++bx)
-              tma_load_3d(sQ + s * S::kTile + bx * S::kBox, &tm_q, bars + PB::kQFull + s, bx * 64, q0, bh_q);
-            const int64_t soff = static_cast<int64_t>(bh_q) * p.QLp + q0;
+              tma_load_3d(sQ + s * S::kTile + bx * S::kBox, &tm_q, bars + PB::kQFull + s, bx * 64, q_off + q0, bh_q);
+            const int64_t soff = static_cast<int64_t>(bh_q) * p.QLp + st_off + q0;
             bulk_load_1d(s_lse + s * 128, p.lse2p + soff, 512, bars + PB::kQFull + s);
             bulk_load_1d(s_del + s * 128, p.deltap + soff, 512, bars + PB::kQFull + s);
           };
@@ -755,7 +825,7 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
             mbar_arrive_expect_tx(bars + PB::kDoFull, S::kTile);
 #pragma unroll
             for (int bx = 0; bx < S::kNBox; ++bx)
-              tma_load_3d(sdO + bx * S::kBox, &tm_do, bars + PB::kDoFull, bx * 64, q0, bh_q);
+              tma_load_3d(sdO + bx * S::kBox, &tm_do, bars + PB::kDoFull, bx * 64, q_off + q0, bh_q);
           };
           const int go_at = n_it > 2 ? n_it - 2 : 0;  // step whose loads trigger the next claim
           if (go_at == 0) mbar_arrive(bars + PB::kSchedGo);
@@ -764,14 +834,14 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
           mbar_arrive_expect_tx(bars + PB::kVFull, S::kTile);
 #pragma unroll
           for (int bx = 0; bx < S::kNBox; ++bx)
-            tma_load_3d(sV + bx * S::kBox, &tm_v, bars + PB::kVFull, bx * 64, k0, bh_kv);
+            tma_load_3d(sV + bx * S::kBox, &tm_v, bars + PB::kVFull, bx * 64, k_off + k0, bh_kv);
           load_q(0);
           load_do(0);
           mbar_wait(bars + PB::kKEmpty, (tl & 1) ^ 1);
           mbar_arrive_expect_tx(bars + PB::kKFull, S::kTile);
 #pragma unroll
           for (int bx = 0; bx < S::kNBox; ++bx)
-            tma_load_3d(sK + bx * S::kBox, &tm_k, bars + PB::kKFull, bx * 64, k0, bh_kv);
+            tma_load_3d(sK + bx * S::kBox, &tm_k, bars + PB::kKFull, bx * 64, k_off + k0, bh_kv);
           if (n_it > 1) load_q(1);
           for (int it = 1; it < n_it; ++it) {
             if (it == go_at) mbar_arrive(bars + PB::kSchedGo);
@@ -808,10 +878,9 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
       };
       int gs = 0;
       for (int tl = 0;; ++tl) {
-        const int t = next_tile(tl);
-        if (t < 0) break;
-        const int j = t % nkv;
-        const int n_it = (nq - (p.causal ? j : 0)) * g;
+        Tile ti;
+        if (!next_tile(tl, ti)) break;
+        const int j = ti.j, n_it = ti.n_it;
         PT_STAMP(0);
         // dP^T(0) = V dO_0^T: its TMEM columns hold the previous tile's last dQ until drained
         mbar_wait(bars + PB::kVFull, tl & 1);
@@ -914,12 +983,10 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
     const float sl2 = p.scale_log2;
     int gs = 0;
     for (int tl = 0;; ++tl) {
-      const int t = next_tile(tl);
-      if (t < 0) break;
-      const int j = t % nkv;
-      const int i0 = p.causal ? j : 0;
-      const int nqi = nq - i0;
-      const int n_it = nqi * g;
+      Tile ti;
+      if (!next_tile(tl, ti)) break;
+      const int j = ti.j, i0 = ti.i0, nqi = ti.nqi, n_it = ti.n_it;
+      const bool key_dead = packed && ti.k0 + row >= ti.KL;  // this row belongs to the next packed sequence
       for (int it = 0; it < n_it; ++it) {
         const int gi = gs + it;
         const int s = gi & 1;
@@ -947,6 +1014,10 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
 #pragma unroll
           for (int c = 0; c < 64; ++c)
             if (row > c0 + c) pf[c] = 0.f;
+        }
+        if (key_dead) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) pf[c] = 0.f;
         }
         {
           uint32_t pk[32];
@@ -1001,14 +1072,10 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
     int nred = 0;
     int gs = 0;
     for (int tl = 0;; ++tl) {
-      const int t = next_tile(tl);
-      if (t < 0) break;
-      const int j = t % nkv, u = t / nkv;
-      const int hk = u % p.KH, b = u / p.KH;
-      const int k0 = j * 128, bh_kv = b * p.KH + hk;
-      const int i0 = p.causal ? j : 0;
-      const int nqi = nq - i0;
-      const int n_it = nqi * g;
+      Tile ti;
+      if (!next_tile(tl, ti)) break;
+      const int hk = ti.hk, b = ti.b, k0 = ti.k0, bh_kv = ti.bh_kv, i0 = ti.i0, nqi = ti.nqi, n_it = ti.n_it;
+      const int q_off = ti.q_off, k_off = ti.k_off;
       for (int it = 0; it < n_it; ++it) {
         const int gi = gs + it;
         const int bh_q = b * p.QH + hk * g + it / nqi;
@@ -1039,7 +1106,7 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
           fence_proxy_async_smem();
           named_bar_sync(3, 128);
           if (issuer) {
-            tma_reduce_add_3d(&tm_dqa, stage, c * 32, q0, bh_q);
+            tma_reduce_add_3d(&tm_dqa, stage, c * 32, q_off + q0, bh_q);
             bulk_commit();
           }
           ++nred;
@@ -1080,13 +1147,29 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
             *reinterpret_cast<uint4*>(sdQ + bx * S::kBox + row * 128 + ((cin ^ (row & 7)) << 4)) = v;
           }
         }
-        fence_proxy_async_smem();
-        named_bar_sync(3, 128);
-        if (issuer) {
+        const int rows_left = ti.KL - k0;
+        if (packed && rows_left < 128) {
+          // partial last block of a packed sequence: copy only its own rows (coalesced 16-byte stores);
+          // the barrier that opens the next use of the staging buffer also closes these reads
+          named_bar_sync(3, 128);
+          constexpr int kCPR = D / 8;
+          T* obase = static_cast<T*>(which ? p.dk_ptr : p.dv_ptr) +
+                     (static_cast<int64_t>(hk) * p.total_k + k_off + k0) * D;
+          for (int idx = row; idx < rows_left * kCPR; idx += 128) {
+            const int r2 = idx / kCPR, chunk = idx % kCPR;
+            const int bx = chunk >> 3, cin = chunk & 7;
+            const uint4 v = *reinterpret_cast<const uint4*>(sdQ + bx * S::kBox + r2 * 128 + ((cin ^ (r2 & 7)) << 4));
+            *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(r2) * D + chunk * 8) = v;
+          }
+        } else {
+          fence_proxy_async_smem();
+          named_bar_sync(3, 128);
+          if (issuer) {
 #pragma unroll
-          for (int bx = 0; bx < S::kNBox; ++bx)
-            tma_store_3d(which ? &tm_dk : &tm_dv, sdQ + bx * S::kBox, bx * 64, k0, bh_kv);
-          bulk_commit();
+            for (int bx = 0; bx < S::kNBox; ++bx)
+              tma_store_3d(which ? &tm_dk : &tm_dv, sdQ + bx * S::kBox, bx * 64, k_off + k0, bh_kv);
+            bulk_commit();
+          }
         }
       }
     }
@@ -1656,6 +1739,32 @@ attn_bwd_post_kernel(T* __restrict__ dq, const float* __restrict__ dq_accum, int
   reinterpret_cast<uint4*>(dq)[i] = v;
 }
 
+// packed mode, persistent kernel: tile_pre[z] = sum over sequences before z of ceil(KL_z / 128) * KH
+// (one block; each thread scans a contiguous chunk of sequences), and the tile counter is reset
+__global__ void __launch_bounds__(256)
+packed_tile_prefix_kernel(int* __restrict__ tile_pre, int* __restrict__ tile_counter,
+                          const int* __restrict__ cu_k, int nseq, int KH) {
+  __shared__ int part[256];
+  const int per = (nseq + 255) / 256;
+  const int z0 = min(nseq, static_cast<int>(threadIdx.x) * per), z1 = min(nseq, z0 + per);
+  int sum = 0;
+  for (int z = z0; z < z1; ++z) sum += ((cu_k[z + 1] - cu_k[z] + 127) >> 7) * KH;
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < 256; ++i) { const int v = part[i]; part[i] = run; run += v; }
+    tile_pre[nseq] = run;
+    *tile_counter = 0;
+  }
+  __syncthreads();
+  int run = part[threadIdx.x];
+  for (int z = z0; z < z1; ++z) {
+    tile_pre[z] = run;
+    run += ((cu_k[z + 1] - cu_k[z] + 127) >> 7) * KH;
+  }
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 // rows of the padded per-row statistics: dense (QL rounded up to 128) or packed (every sequence
@@ -1678,9 +1787,11 @@ int launch_bwd(const AttnParams& a) {
   float* deltap = reinterpret_cast<float*>(ws);
   float* lse2p = reinterpret_cast<float*>(ws + stat_bytes);
   float* dqa = reinterpret_cast<float*>(ws + 2 * stat_bytes);
-  // dense mode: the persistent kernel's tile counter sits behind the dQ accumulator
+  // the persistent kernel's tile counter (and, packed, the per-sequence tile prefix) sit behind the
+  // dQ accumulator
   int* tile_counter = reinterpret_cast<int*>(
       ws + 2 * stat_bytes + align256(static_cast<size_t>(BH) * rows_q * D * sizeof(float)));
+  int* tile_pre = tile_counter + 64;
 
   if (packed) {
     constexpr int kRows = 256 / (D / 8);
@@ -1715,6 +1826,7 @@ int launch_bwd(const AttnParams& a) {
   bp.cu_q = a.cu_q; bp.cu_k = a.cu_k; bp.dk_ptr = a.dk; bp.dv_ptr = a.dv; bp.total_k = a.total_k;
   bp.kpad = packed ? nullptr : a.kpad;
   bp.pair_t = a.pair_t; bp.dpair_t = a.dpair_t; bp.KLp = a.KLp;
+  bp.tile_pre = tile_pre; bp.nseq = a.nseq;
   const bool bias = a.pair != nullptr;
   if (bias)
     if (int rc = attn_pair_to_head_major(a)) return rc;
@@ -1726,14 +1838,15 @@ int launch_bwd(const AttnParams& a) {
   bool use_pair = false;
   if constexpr (D == 128) use_pair = !packed && nkv >= 2 && mode == 1 && !bias;
   const int nq_blocks = (a.QL + 127) / 128;
-  const int64_t n_tiles = static_cast<int64_t>(nkv) * a.KH * a.B;
+  // packed: the exact tile count is only known on the device; this is its upper bound
+  const int64_t n_tiles = packed ? (a.total_k / 128 + a.nseq) * a.KH : static_cast<int64_t>(nkv) * a.KH * a.B;
   int num_sms = 148;
   {
     int dev = 0;
     NNOP_CUDA_CHECK(cudaGetDevice(&dev));
     NNOP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const bool persist_ok = !packed && !bias && a.kpad == nullptr && (!a.causal || nq_blocks >= nkv) &&
+  const bool persist_ok = !bias && a.kpad == nullptr && (packed || !a.causal || nq_blocks >= nkv) &&
                           n_tiles < (1LL << 30);
   const bool use_persist = !use_pair && persist_ok &&
                            (mode == 3 || mode >= 100 || (mode == 0 && n_tiles >= 2LL * num_sms));
@@ -1755,6 +1868,10 @@ int launch_bwd(const AttnParams& a) {
     NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     const int ctas = mode >= 100 ? (mode - 100 < 1 ? 1 : mode - 100) : num_sms;
     const int grid = static_cast<int>(n_tiles < ctas ? n_tiles : ctas);
+    if (packed) {
+      packed_tile_prefix_kernel<<<1, 256, 0, a.stream>>>(tile_pre, tile_counter, a.cu_k, a.nseq, a.KH);
+      NNOP_LAUNCH_CHECK();
+    }
     timing_begin(1, a.stream);
     kern<<<grid, kBwdThreads, S::kTotal, a.stream>>>(tq, tk, tv, tdo, tdk, tdv, tdqa, bp, tile_counter,
                                                      static_cast<int>(n_tiles), nkv);
@@ -1809,7 +1926,8 @@ size_t attn_sm100_bwd_workspace_bytes(int E, int QL, int QH, int B) {
 size_t attn_sm100_bwd_packed_workspace_bytes(int E, int64_t total_q, int nseq, int QH) {
   const size_t QLp = static_cast<size_t>(stat_rows(0, total_q, nseq, true));
   return 2 * align256(static_cast<size_t>(QH) * QLp * sizeof(float)) +
-         static_cast<size_t>(QH) * static_cast<size_t>(total_q) * E * sizeof(float);
+         align256(static_cast<size_t>(QH) * static_cast<size_t>(total_q) * E * sizeof(float)) +
+         align256((static_cast<size_t>(nseq) + 2 + 64) * sizeof(int));
 }
 
 int attn_sm100_bwd(const AttnParams& a) {

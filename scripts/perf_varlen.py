@@ -24,6 +24,13 @@ def timeit(fn, n=10):
     return a.elapsed_time(b) / n
 o, lse = nn._flash_attention_varlen(q, k, v, cu, cu, mx, mx, causal=True)
 tf = timeit(lambda: nn._flash_attention_varlen(q, k, v, cu, cu, mx, mx, causal=True))
+tbs = {}
+for mode in (2, 3, 2, 3):   # backward variants: one CTA per tile / persistent, alternating
+    nn.set_bwd_pair_mode(mode)
+    t_ = timeit(lambda: nn.grad_flash_attention_varlen(dO, o, lse, q, k, v, cu, cu, mx, mx, causal=True))
+    tbs[mode] = min(tbs.get(mode, 1e9), t_)
+nn.set_bwd_pair_mode(0)
+print("backward: " + "  ".join(f"mode {m}: {t:.3f} ms {2.5*f/t/1e9:.0f} TF/s" for m, t in tbs.items()), flush=True)
 tb = timeit(lambda: nn.grad_flash_attention_varlen(dO, o, lse, q, k, v, cu, cu, mx, mx, causal=True))
 print(f"C4: 64 seqs, sum L = {T}, sum L^2 = {sum(l*l for l in lens):.3e}, max L = {mx}, min L = {min(lens)}: "
       f"fwd {tf:.3f} ms {f/tf/1e9:.0f} TF/s | bwd {tb:.3f} ms {2.5*f/tb/1e9:.0f} TF/s | fwd+bwd {3.5*f/(tf+tb)/1e9:.0f} TF/s", flush=True)

@@ -157,3 +157,33 @@ def test_varlen_errors(nnop):
     qh = torch.randn(2, 64, 32, device="cuda").bfloat16()
     with pytest.raises(nnop.NNopError, match="64 and 128"):
         nnop._flash_attention_varlen(qh, qh, qh, cu, cu, 64, 64, causal=False)
+
+
+@pytest.mark.parametrize("mode", [3, 101, 103])
+def test_varlen_persistent_backward(nnop, mode):
+    """The persistent backward on packed batches (dynamic tile queue over (sequence, kv head, kv block),
+    sequence found by binary search in a device-built tile prefix): oracle parity on every scenario
+    of this file, and dK / dV bit-identical to the one-CTA-per-tile kernel.  Modes 101 / 103 squeeze
+    the queue onto 1 / 3 CTAs so that tiles of different sequences follow each other in one CTA."""
+    cases = [([255, 1, 128, 513, 256, 129, 64, 511], None, 4, 4, 128, True),
+             ([255, 1, 128, 513, 256, 129, 64, 511], None, 4, 4, 64, False),
+             ([300, 77, 1024, 5], None, 8, 2, 128, True),
+             ([100, 257, 31], [513, 64, 200], 2, 2, 128, False),
+             ([130, 0, 64, 0], None, 2, 1, 64, True),
+             ([40, 200], [0, 200], 2, 2, 128, False),
+             ([0, 200, 64], [300, 200, 64], 2, 2, 128, False)]   # keys without queries: dK = dV = 0
+    try:
+        for lens_q, lens_k, QH, KH, E, causal in cases:
+            lens_k = lens_k or lens_q
+            nnop.set_bwd_pair_mode(mode)
+            _check(nnop, lens_q, lens_k, QH, KH, E, torch.bfloat16, causal, seed=len(lens_q))
+            q, k, v, dO, cu_q, cu_k = (t.cuda() for t in _packed(lens_q, lens_k, QH, KH, E, torch.bfloat16, 11))
+            mq, mk = max(lens_q), max(lens_k)
+            o, lse = nnop._flash_attention_varlen(q, k, v, cu_q, cu_k, mq, mk, causal=causal)
+            got = nnop.grad_flash_attention_varlen(dO, o, lse, q, k, v, cu_q, cu_k, mq, mk, causal=causal)
+            nnop.set_bwd_pair_mode(2)
+            ref = nnop.grad_flash_attention_varlen(dO, o, lse, q, k, v, cu_q, cu_k, mq, mk, causal=causal)
+            assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]), (lens_q, lens_k)
+            assert max_abs(got[0], ref[0]) <= 2 ** -7 * max(1.0, ref[0].abs().max().item())
+    finally:
+        nnop.set_bwd_pair_mode(0)
