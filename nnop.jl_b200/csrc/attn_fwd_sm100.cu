@@ -64,6 +64,7 @@ struct FwdParams {
   void* o_ptr;       // raw output pointer for partial tiles (a TMA store would spill into the next sequence)
   int64_t total_q;
   const uint8_t* kpad;  // (B, KL) key padding mask, 1 = attend, or nullptr (dense mode only)
+  int nseq;             // packed mode: number of sequences
 };
 
 // NS = stages of the K/V ring; BIASB = bytes of additive-bias staging (pair: 4 x 16 KB, ring of 3)
@@ -131,19 +132,47 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
 #endif
 
   // ---- work assignment ----------------------------------------------------------------
-  const int qt = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heaviest first
-  const int q0 = qt * 256;
-  const int h = blockIdx.y;
   const bool packed = p.cu_q != nullptr;
+  int qt = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heaviest first
+  const int h = blockIdx.y;
   int QL = p.QL, KL = p.KL, q_off = 0, k_off = 0, b = blockIdx.z;
   if (packed) {
-    q_off = p.cu_q[blockIdx.z];
-    QL = p.cu_q[blockIdx.z + 1] - q_off;
-    k_off = p.cu_k[blockIdx.z];
-    KL = p.cu_k[blockIdx.z + 1] - k_off;
+    // The grid has one CTA per 256-row q tile of the packed batch (upper bound total_q / 256 + nseq,
+    // no CTAs for tiles a shorter sequence does not have).  Tile e = blockIdx.x belongs to the
+    // sequence z whose tile range contains it: every thread counts the tiles of a chunk of
+    // sequences, then all walk the per-thread counts (scratch: the not yet used Q buffer).
+    int* scratch = reinterpret_cast<int*>(smem);
+    const int e = blockIdx.x;
+    const int per = (p.nseq + kFwdThreads - 1) / kFwdThreads;
+    auto tiles_of = [&](int z) { return (p.cu_q[z + 1] - p.cu_q[z] + 255) >> 8; };
+    {
+      const int z0 = min(p.nseq, static_cast<int>(threadIdx.x) * per), z1 = min(p.nseq, z0 + per);
+      int cnt = 0;
+      for (int z = z0; z < z1; ++z) cnt += tiles_of(z);
+      scratch[threadIdx.x] = cnt;
+    }
+    __syncthreads();
+    int run = 0, c = 0;
+    for (; c < kFwdThreads; ++c) {
+      const int v = scratch[c];
+      if (e < run + v) break;
+      run += v;
+    }
+    __syncthreads();   // scratch is the Q buffer from here on
+    if (c == kFwdThreads) return;  // past the last tile of the batch (whole CTA exits together)
+    int z = c * per, nt = tiles_of(z);
+    while (e >= run + nt) {
+      run += nt;
+      nt = tiles_of(++z);
+    }
+    qt = p.causal ? nt - 1 - (e - run) : e - run;  // heaviest tile of a sequence first
+    q_off = p.cu_q[z];
+    QL = p.cu_q[z + 1] - q_off;
+    k_off = p.cu_k[z];
+    KL = p.cu_k[z + 1] - k_off;
     b = 0;
-    if (q0 >= QL) return;  // the grid is sized for the longest sequence (whole CTA exits together)
   }
+  const int q0 = qt * 256;
   const int bh_q = b * p.QH + h;
   const int bh_kv = b * p.KH + h / (p.QH / p.KH);
   // key padding mask (src/attention.jl:73-79): keys past the last attended one are never loaded
@@ -718,7 +747,7 @@ int launch_fwd_f32(const AttnParams& a) {
   fp.lse = a.lse;
   fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
   fp.scale_log2 = a.scale * kLog2e;
-  fp.cu_q = nullptr; fp.cu_k = nullptr; fp.o_ptr = a.o; fp.total_q = 0;
+  fp.cu_q = nullptr; fp.cu_k = nullptr; fp.o_ptr = a.o; fp.total_q = 0; fp.nseq = 0;
   fp.kpad = a.kpad;
   dim3 grid((a.QL + 255) / 256, a.QH, a.B);
   timing_begin(0, a.stream);
@@ -753,7 +782,8 @@ int launch_fwd(const AttnParams& a) {
   fp.scale_log2 = a.scale * kLog2e;
   fp.cu_q = a.cu_q; fp.cu_k = a.cu_k; fp.o_ptr = a.o; fp.total_q = a.total_q;
   fp.kpad = packed ? nullptr : a.kpad;
-  dim3 grid((a.QL + 255) / 256, a.QH, packed ? a.nseq : a.B);
+  fp.nseq = a.nseq;
+  dim3 grid(packed ? static_cast<unsigned>(a.total_q / 256 + a.nseq) : (a.QL + 255) / 256, a.QH, packed ? 1 : a.B);
   timing_begin(0, a.stream);
   kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, tb, fp);
   timing_end(0, a.stream);
