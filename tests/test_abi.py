@@ -50,3 +50,23 @@ def test_product_package_never_imports_oracle():
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.jl")):
         txt = f.read_text()
         assert "oracle" not in txt.lower() or f.name == "build.py", f
+
+
+def test_workspace_queries_need_no_gpu(nnop):
+    """Pure host arithmetic of the size queries: the pair extension is one (backward: two) head-major
+    copies of the bias with the key axis padded to 32, and the backward workspace covers the padded
+    statistics, the fp32 dQ accumulator and the persistent kernel's tile counter."""
+    from nnop_b200 import _lib
+    lib = _lib.lib
+    up = lambda n: (n + 255) & ~255
+    for dtype, s in ((0, 4), (1, 2), (2, 2)):
+        one = up(3 * 4 * 300 * 320 * s)          # B=3, QH=4, QL=300, KL=300 -> KLp=320
+        assert lib.nnop_flash_attn_pair_workspace_bytes(dtype, 300, 300, 4, 3, 0) == one
+        assert lib.nnop_flash_attn_pair_workspace_bytes(dtype, 300, 300, 4, 3, 1) == 2 * one
+    assert lib.nnop_flash_attn_pair_workspace_bytes(9, 300, 300, 4, 3, 0) == 0
+    assert lib.nnop_flash_attn_pair_workspace_bytes(0, 0, 300, 4, 3, 0) == 0
+    # bf16, E=128, QL=KL=1000, QH=8, KH=2, B=2: delta + 2 x padded stats + dQ accumulator + counter
+    need = lib.nnop_flash_attn_bwd_workspace_bytes(2, 128, 1000, 1000, 8, 2, 2)
+    assert need == up(2 * 8 * 1000 * 4) + 2 * up(2 * 8 * 1024 * 4) + up(2 * 8 * 1000 * 128 * 4) + 256
+    assert lib.nnop_set_bwd_pair_mode(4) != 0 and lib.nnop_set_bwd_pair_mode(103) == 0
+    assert lib.nnop_set_bwd_pair_mode(0) == 0
