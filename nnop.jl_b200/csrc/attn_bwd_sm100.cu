@@ -90,6 +90,9 @@ struct BwdParams {
 };
 
 // first padded-statistics row of packed sequence z (each sequence is padded to whole 128-row blocks)
+#ifdef NNOP_BWD_NO_EXP   // (timing experiments: knock out the MUFU work)
+#define fast_exp2(x) (x)
+#endif
 __device__ __forceinline__ int packed_stat_row(int cu, int z) { return ((cu >> 7) + z) << 7; }
 
 template <int D>
@@ -1004,7 +1007,11 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
         const float4* l4 = reinterpret_cast<const float4*>(s_lse + s * 128 + c0);
 #pragma unroll
         for (int u4 = 0; u4 < 16; ++u4) {
+#ifdef NNOP_BWD_NO_STATS   // timing experiment only: what do the broadcast LDS of lse2 / delta cost?
+          const float4 l = make_float4(sl2, sl2, sl2, sl2);
+#else
           const float4 l = l4[u4];
+#endif
           pf[4 * u4 + 0] = fast_exp2(fmaf(__uint_as_float(sr[u4 >> 3][(4 * u4 + 0) & 31]), sl2, -l.x));
           pf[4 * u4 + 1] = fast_exp2(fmaf(__uint_as_float(sr[u4 >> 3][(4 * u4 + 1) & 31]), sl2, -l.y));
           pf[4 * u4 + 2] = fast_exp2(fmaf(__uint_as_float(sr[u4 >> 3][(4 * u4 + 2) & 31]), sl2, -l.z));
@@ -1040,7 +1047,11 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
         uint8_t* drow = sdS + half * S::kBox + row * 128;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {  // 8 columns = one 16-byte chunk
+#ifdef NNOP_BWD_NO_STATS
+          const float4 da = make_float4(sl2, sl2, sl2, sl2), db = da;
+#else
           const float4 da = d4[2 * ch], db = d4[2 * ch + 1];
+#endif
           const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
           float ds[8];
 #pragma unroll
@@ -1053,7 +1064,11 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
           v.y = pack2<T>(ds[2], ds[3]);
           v.z = pack2<T>(ds[4], ds[5]);
           v.w = pack2<T>(ds[6], ds[7]);
+#ifndef NNOP_BWD_NO_DS   // (timing experiments: knock out the dS^T shared-memory stores)
           *reinterpret_cast<uint4*>(drow + ((ch ^ (row & 7)) << 4)) = v;
+#else
+          if (v.x == 0x12345678u) *reinterpret_cast<uint4*>(drow) = v;
+#endif
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -1089,6 +1104,7 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + PB::kDqEmpty);
+#ifndef NNOP_BWD_NO_DQ   // (timing experiments: knock out the dQ staging + bulk reduce)
 #pragma unroll
         for (int c = 0; c < D / 32; ++c) {
           uint8_t* stage = sdQ + (nred & 1) * 16384;
@@ -1101,16 +1117,23 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
 #pragma unroll
           for (int u4 = 0; u4 < 8; ++u4) {
             const uint4 v = make_uint4(r[c][4 * u4], r[c][4 * u4 + 1], r[c][4 * u4 + 2], r[c][4 * u4 + 3]);
+#ifndef NNOP_BWD_NO_DQ_STS
             *reinterpret_cast<uint4*>(stage + row * 128 + ((u4 ^ (row & 7)) << 4)) = v;
+#else
+            if (v.x == 0x12345678u) *reinterpret_cast<uint4*>(stage) = v;
+#endif
           }
           fence_proxy_async_smem();
           named_bar_sync(3, 128);
+#ifndef NNOP_BWD_NO_DQ_RED
           if (issuer) {
             tma_reduce_add_3d(&tm_dqa, stage, c * 32, q_off + q0, bh_q);
             bulk_commit();
           }
+#endif
           ++nred;
         }
+#endif
       }
       gs += n_it;
       // ---- epilogue: dV then dK -> 16-bit -> swizzled staging (the dQ buffers) -> TMA store ----

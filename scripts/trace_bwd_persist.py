@@ -3,7 +3,7 @@ development aid):  python scripts/build_variants.py attn_bwd_sm100.cu btrace:-DN
 import ctypes, os, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
-os.environ["NNOP_B200_LIB"] = str(ROOT / "nnop.jl_b200" / "lib" / "variants" / "libnnop_b200_btrace.so")
+os.environ.setdefault("NNOP_B200_LIB", str(ROOT / "nnop.jl_b200" / "lib" / "variants" / "libnnop_b200_btrace.so"))
 sys.path.insert(0, str(ROOT / "nnop.jl_b200"))
 import torch, nnop_b200 as nn
 causal = "--noncausal" not in sys.argv
