@@ -520,8 +520,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
             if (kPolyEvery > 0 && (j % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
               exp2_poly2(x0, x1, pf[2 * j], pf[2 * j + 1]);
             } else {
+#ifdef NNOP_FWD_NO_EXP   // timing experiment only (wrong results): what do the MUFU exponentials cost?
+              pf[2 * j] = x0;
+              pf[2 * j + 1] = x1;
+#else
               pf[2 * j] = fast_exp2(x0);
               pf[2 * j + 1] = fast_exp2(x1);
+#endif
             }
           }
         };
