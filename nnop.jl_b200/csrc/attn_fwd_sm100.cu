@@ -362,6 +362,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         commit(&s_full[1]);
       }
       commit(&kv_empty[0]);
+      // One issuer walks both tiles in turn.  That serialisation is what keeps the two tiles half a
+      // step apart (one tile's softmax under the other's MMAs): with one issuer warp per tile
+      // (tried) both chains fall into lockstep -- both softmaxes contend for the same issue slots
+      // and then both MMA groups queue on the pipe -- and the step grows from 3 200 to 4 490 clk.
       // Per step and tile the tensor pipe sees PV_lo(i), PV_hi(i) (as each half of P lands) and
       // QK(i+1) (its columns alias P, so it follows PV in the in-order pipe).  With kSplitQK the
       // upper half of S(i+1) is issued as soon as the softmax warpgroup holds S(i) in registers.
@@ -379,6 +383,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
             qk_half(t, knext, 1);
           }
           mbar_wait(&p_half[2 * t], i & 1);
+          if (t == 0) FWD_STAMP(i, 14);
           slot_wait(vslot);
           tc_fence_after();
           FWD_STAMP(i, 10 + 2 * t);
@@ -386,6 +391,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           if (kSplitPV) {
             mbar_wait(&p_half[2 * t + 1], i & 1);
             tc_fence_after();
+            if (t == 0) FWD_STAMP(i, 15);
           }
           pv_half(t, vslot, 1, true);
           if (has_next) {

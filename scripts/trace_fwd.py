@@ -16,9 +16,9 @@ buf = (ctypes.c_longlong * n)()
 rc = nn.lib.nnop_debug_fwd_trace(buf, n)
 assert rc == 0, rc
 rows = [list(buf[i * 16:(i + 1) * 16]) for i in range(64)]
-names = ["0:S", "0:ld", "0:max", "0:p0", "0:p1", "1:S", "1:ld", "1:max", "1:p0", "1:p1", "M0:w", "M0:i", "M1:w", "M1:i"]
+names = ["0:S", "0:ld", "0:max", "0:p0", "0:p1", "1:S", "1:ld", "1:max", "1:p0", "1:p1", "M0:w", "M0:i", "M1:w", "M1:i", "M0:p0", "M0:p1"]
 t0 = rows[20][0]
 print("it " + " ".join(f"{x:>7s}" for x in names))
 for i in range(20, 30):
-    print(f"{i:2d} " + " ".join(f"{rows[i][j] - t0:7d}" for j in range(14)))
+    print(f"{i:2d} " + " ".join(f"{rows[i][j] - t0:7d}" for j in range(16)))
 print("clk/step:", (rows[50][0] - rows[20][0]) / 30)
