@@ -71,6 +71,15 @@ int nnop_last_attention_path(void);
  * (tcgen05 cta_group::2; same results, currently slower); 2: always one CTA per tile; 3: persistent
  * wherever eligible; 100+n: persistent on n CTAs (tests).  dK / dV are bit-identical across modes. */
 int nnop_set_bwd_pair_mode(int mode);
+/* Forward kernel selection on the tcgen05 path (diagnostics / A-B timing), process-wide; env
+ * NNOP_FWD_MODE gives the initial value.  0 (default): automatic -- dense 16-bit problems without
+ * key padding mask or pair bias whose queue of (256-row q tile, head, batch) tiles is at least two
+ * rounds deep and whose tiles are short enough for the per-tile fixed cost to matter (E = 64, or
+ * QL <= 2048) run the persistent kernel (one CTA per SM, dynamic tile queue, Q / K / V of the next
+ * tile loaded under the current one, O stored through private staging); 1: always one CTA per q
+ * tile; 2: persistent wherever eligible; 100+n: persistent on n CTAs (tests).  O and lse are
+ * bit-identical across modes. */
+int nnop_set_fwd_mode(int mode);
 
 /* ---------------------------------------------------------------------------------------
  * flash attention forward.  Replaces `_flash_attention` + kernel `_flash_attention_fwd!`

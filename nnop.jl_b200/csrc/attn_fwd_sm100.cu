@@ -19,6 +19,9 @@
 //
 // Ragged sizes: TMA zero-fills rows past QL / KL (per head: the tensor maps are 3-D), key
 // columns >= KL are masked to -inf, and the TMA store clips rows >= QL.
+#include <stdlib.h>
+
+#include <atomic>
 #include <type_traits>
 
 #include "common.cuh"
@@ -703,6 +706,440 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   }
 }
 
+// =========================================================================================
+// Persistent forward (dense layout, bf16 / f16, no key padding mask, no bias): one CTA per SM walks a
+// dynamic queue of (256-row q tile, q head, batch) work tiles, heaviest q tile of a head first and
+// the q tiles of one head next to each other (they share K / V through L2).  The one-tile kernel
+// above pays ~7 K clk per CTA outside its steady state (launch gap, barrier / TMEM setup, the Q and
+// first K load, the epilogue) and with one CTA per SM nothing overlaps it; here
+//   * the K / V ring, the barrier phases and TMEM run on across tiles: the producer loads the next
+//     tile's Q_t as soon as the last QK of the current tile has read Q_t, and its first K / V blocks
+//     behind the current tile's last ones;
+//   * the next tile's first QK is issued right behind the last PV; only its first PV waits for the
+//     softmax warpgroup to have pulled O out of TMEM (o_empty);
+//   * each softmax warpgroup stores its O tile through a private 16 KB staging buffer (one 64-column
+//     box at a time), so Q never waits for a store;
+//   * warp 3 claims tiles with atomicAdd on a per-launch counter slot (see launch_fwd_persist) and
+//     publishes them through a two-slot ring, late, as in the persistent backward.
+// The softmax code is the one-tile kernel's, so O and lse are bit-identical (test).
+// =========================================================================================
+template <int D>
+struct FwdPersistSmem {
+  static constexpr int kNStage = 4;
+  static constexpr int kTileBytes = 128 * D * 2;
+  static constexpr int kBoxBytes = 128 * 64 * 2;
+  static constexpr int kNBox = D / 64;
+  static constexpr int kQOff = 0;
+  static constexpr int kKVOff = 2 * kTileBytes;
+  static constexpr int kStageOff = kKVOff + kNStage * kTileBytes;  // 2 x 16 KB: O staging per warpgroup
+  static constexpr int kBarOff = kStageOff + 2 * kBoxBytes;
+  enum : int {
+    kQFull = 0,      // [2]
+    kQEmpty = 2,     // [2]
+    kKVFull = 4,     // [4]
+    kKVEmpty = 8,    // [4]
+    kSFull = 12,     // [2]
+    kPHalf = 14,     // [2][2]
+    kOFull = 18,     // [2]
+    kOEmpty = 20,    // [2]
+    kTileFull = 22,  // [2]
+    kTileEmpty = 24, // [2]
+    kSchedGo = 26,
+    kNumBars = 27
+  };
+  static constexpr int kTileRing = kBarOff + kNumBars * 8;   // [2][4] ints
+  static constexpr int kTmemSlot = kTileRing + 32;
+  static constexpr int kTotal = kTmemSlot + 16;
+  static constexpr int kDynBytes = kTotal + 1024;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
+                              const __grid_constant__ CUtensorMap tm_k,
+                              const __grid_constant__ CUtensorMap tm_v,
+                              const __grid_constant__ CUtensorMap tm_o, const FwdParams p,
+                              int* __restrict__ tile_counter, const int n_tiles, const int nqt, const int B) {
+  using S = FwdPersistSmem<D>;
+  constexpr int kNStage = S::kNStage;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem + S::kQOff;
+  uint8_t* sKV = smem + S::kKVOff;
+  uint8_t* sStage = smem + S::kStageOff;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  volatile int* s_tile = reinterpret_cast<volatile int*>(smem + S::kTileRing);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int QL = p.QL, KL = p.KL;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_o);
+    for (int i = 0; i < S::kNumBars; ++i) {
+      uint32_t cnt = 1;
+      if (i >= S::kPHalf && i < S::kPHalf + 4) cnt = 4;     // one arrival per softmax warp
+      if (i >= S::kOEmpty && i < S::kOEmpty + 2) cnt = 4;
+      if (i >= S::kTileEmpty && i < S::kTileEmpty + 2) cnt = 10;  // producer + issuer + 8 softmax warps
+      mbar_init(bars + i, cnt);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work tile geometry, derived from a ring record by every role the same way
+  struct Tile {
+    int bh_q, bh_kv, q0, act1, nb0, nb1, nblk;
+  };
+  auto make_tile = [&](int b, int h, int qt) -> Tile {
+    Tile t;
+    t.q0 = qt * 256;
+    t.bh_q = b * p.QH + h;
+    t.bh_kv = b * p.KH + h / (p.QH / p.KH);
+    t.act1 = t.q0 + 128 < QL;
+    t.nb0 = ((p.causal ? min(KL, t.q0 + 128) : KL) + 127) >> 7;
+    t.nb1 = t.act1 ? (((p.causal ? min(KL, t.q0 + 256) : KL) + 127) >> 7) : 0;
+    t.nblk = t.act1 ? t.nb1 : t.nb0;
+    return t;
+  };
+  auto next_tile = [&](int n, Tile& t) -> bool {
+    const int slot = n & 1;
+    mbar_wait(bars + S::kTileFull + slot, (n >> 1) & 1);
+    const int b = s_tile[4 * slot], h = s_tile[4 * slot + 1], qt = s_tile[4 * slot + 2];
+    const int flag = s_tile[4 * slot + 3];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + S::kTileEmpty + slot);
+    if (flag < 0) return false;
+    t = make_tile(b, h, qt);
+    return true;
+  };
+
+  if (warp < 4) {
+    setmaxnreg_dec<80>();
+    if (warp == 3) {
+      // ================================ tile scheduler ===============================
+      if (lane == 0) {
+        for (int n = 0;; ++n) {
+          const int slot = n & 1;
+          if (n > 0) mbar_wait(bars + S::kSchedGo, (n - 1) & 1);   // claim late (see the backward)
+          mbar_wait(bars + S::kTileEmpty + slot, ((n >> 1) & 1) ^ 1);
+          const int t = atomicAdd(tile_counter, 1);
+          const bool ok = t < n_tiles;
+          const int bh = ok ? t / nqt : 0;
+          const int r = ok ? t % nqt : 0;
+          s_tile[4 * slot] = bh / p.QH;                       // batch element
+          s_tile[4 * slot + 1] = bh % p.QH;                   // q head
+          s_tile[4 * slot + 2] = p.causal ? nqt - 1 - r : r;  // heaviest q tile of a head first
+          s_tile[4 * slot + 3] = ok ? 1 : -1;
+          mbar_arrive(bars + S::kTileFull + slot);
+          if (!ok) break;
+        }
+      }
+    } else if (warp == 0) {
+      // ================================ TMA producer =================================
+      if (lane == 0) {
+        int n = 0;        // K / V loads issued so far (ring position)
+        int cq[2] = {0, 0};  // uses of Q buffer t so far
+        for (int tl = 0;; ++tl) {
+          const int slot = tl & 1;
+          mbar_wait(bars + S::kTileFull + slot, (tl >> 1) & 1);
+          const int tb = s_tile[4 * slot], th = s_tile[4 * slot + 1], tqt = s_tile[4 * slot + 2];
+          const int flag = s_tile[4 * slot + 3];
+          mbar_arrive(bars + S::kTileEmpty + slot);
+          if (flag < 0) break;
+          const Tile ti = make_tile(tb, th, tqt);
+          auto load_q = [&](int t) {
+            mbar_wait(bars + S::kQEmpty + t, (cq[t] & 1) ^ 1);
+            mbar_arrive_expect_tx(bars + S::kQFull + t, S::kTileBytes);
+#pragma unroll
+            for (int bx = 0; bx < S::kNBox; ++bx)
+              tma_load_3d(sQ + t * S::kTileBytes + bx * S::kBoxBytes, &tm_q, bars + S::kQFull + t, bx * 64,
+                          ti.q0 + t * 128, ti.bh_q);
+            ++cq[t];
+          };
+          auto load_kv = [&](const CUtensorMap* tm, int blk) {
+            const int st = n % kNStage;
+            const uint32_t ph = (n / kNStage) & 1;
+            mbar_wait(bars + S::kKVEmpty + st, ph ^ 1);
+            mbar_arrive_expect_tx(bars + S::kKVFull + st, S::kTileBytes);
+#pragma unroll
+            for (int bx = 0; bx < S::kNBox; ++bx)
+              tma_load_3d(sKV + st * S::kTileBytes + bx * S::kBoxBytes, tm, bars + S::kKVFull + st, bx * 64,
+                          blk * 128, ti.bh_kv);
+            ++n;
+          };
+          const int go_at = ti.nblk > 2 ? ti.nblk - 2 : 0;  // block whose loads trigger the next claim
+          if (go_at == 0) mbar_arrive(bars + S::kSchedGo);
+          load_q(0);
+          load_kv(&tm_k, 0);
+          if (ti.act1) load_q(1);
+          load_kv(&tm_v, 0);
+          for (int i = 1; i < ti.nblk; ++i) {
+            if (i == go_at) mbar_arrive(bars + S::kSchedGo);
+            load_kv(&tm_k, i);
+            load_kv(&tm_v, i);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ================================ MMA issuer ===================================
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, is_bf16<T>::value, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, D, is_bf16<T>::value, false, true);
+      const uint32_t tm = uniform_u32(tmem_base);
+      const uint32_t q_base = uniform_u32(smem_u32(sQ));
+      const uint32_t kv_base = uniform_u32(smem_u32(sKV));
+      const uint64_t dq0 = make_smem_desc_sw128(q_base, 16, 1024);
+      const uint64_t dk0 = make_smem_desc_sw128(kv_base, 16, 1024);
+      const uint64_t dv0 = make_smem_desc_sw128(kv_base, S::kBoxBytes, 1024);
+      auto slot_wait = [&](int slot) {
+        mbar_wait(bars + S::kKVFull + slot % kNStage, (slot / kNStage) & 1);
+      };
+      auto qk = [&](int t, int slot) {
+        const uint64_t a0 = dq0 + static_cast<uint64_t>((t * S::kTileBytes) >> 4);
+        const uint64_t b0 = dk0 + static_cast<uint64_t>(((slot % kNStage) * S::kTileBytes) >> 4);
+        const uint32_t d = tm + t * 128;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t off = ((ks >> 2) * S::kBoxBytes + (ks & 3) * 32) >> 4;
+            umma_ss(d, a0 + off, b0 + off, idesc_qk, ks > 0 ? 1u : 0u);
+          }
+        }
+      };
+      auto pv_half = [&](int t, int slot, int hf, bool acc) {
+        const uint64_t b0 = dv0 + static_cast<uint64_t>(((slot % kNStage) * S::kTileBytes) >> 4);
+        const uint32_t d = tm + 256 + t * D;
+        const uint32_t a = tm + t * 128;  // P aliases S columns [0, 64)
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 4 * hf; j < 4 * hf + 4; ++j)
+            umma_ts(d, a + j * 8, b0 + ((j * 2048) >> 4), idesc_pv, (acc || j > 0) ? 1u : 0u);
+        }
+      };
+      auto commit = [&](int bar) {
+        if (elect_one()) tc_commit(bars + bar);
+      };
+      int nbase = 0;          // ring position of this tile's K_0
+      int cq[2] = {0, 0};     // tiles processed on q slot t
+      int cs[2] = {0, 0};     // key blocks processed on q slot t (phases of s_full / p_half)
+      for (int tl = 0;; ++tl) {
+        Tile ti;
+        if (!next_tile(tl, ti)) break;
+        const int nbt[2] = {ti.nb0, ti.nb1};
+        mbar_wait(bars + S::kQFull + 0, cq[0] & 1);
+        slot_wait(nbase);
+        tc_fence_after();
+        qk(0, nbase);
+        commit(S::kSFull + 0);
+        if (ti.nb0 == 1) commit(S::kQEmpty + 0);   // Q_0 is not read again in this tile
+        if (ti.act1) {
+          mbar_wait(bars + S::kQFull + 1, cq[1] & 1);
+          tc_fence_after();
+          qk(1, nbase);
+          commit(S::kSFull + 1);
+          if (ti.nb1 == 1) commit(S::kQEmpty + 1);
+        }
+        commit(S::kKVEmpty + nbase % kNStage);
+        for (int i = 0; i < ti.nblk; ++i) {
+          const int vslot = nbase + 2 * i + 1, knext = nbase + 2 * i + 2;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (i >= nbt[t]) continue;
+            const bool has_next = i + 1 < nbt[t];
+            const int ph = (cs[t] + i) & 1;
+            mbar_wait(bars + S::kPHalf + 2 * t, ph);
+            slot_wait(vslot);
+            if (i == 0) mbar_wait(bars + S::kOEmpty + t, (cq[t] & 1) ^ 1);  // previous tile's O_t read out
+            tc_fence_after();
+            pv_half(t, vslot, 0, i > 0);
+            mbar_wait(bars + S::kPHalf + 2 * t + 1, ph);
+            tc_fence_after();
+            pv_half(t, vslot, 1, true);
+            if (has_next) {
+              slot_wait(knext);
+              tc_fence_after();
+              qk(t, knext);
+              commit(S::kSFull + t);
+              if (i + 2 == nbt[t]) commit(S::kQEmpty + t);   // that was the last QK on Q_t
+            } else {
+              commit(S::kOFull + t);
+            }
+          }
+          commit(S::kKVEmpty + vslot % kNStage);
+          if (i + 1 < ti.nblk) commit(S::kKVEmpty + knext % kNStage);
+        }
+        nbase += 2 * ti.nblk;
+        cq[0] += 1; cs[0] += ti.nb0;
+        if (ti.act1) { cq[1] += 1; cs[1] += ti.nb1; }
+      }
+    }
+  } else {
+    // ================================ softmax warpgroups ===============================
+    setmaxnreg_inc<208>();
+    const int t = (warp - 4) >> 2;
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + t * 128;
+    const uint32_t tO = tmem_base + lane_off + 256 + t * D;
+    const float sl2 = p.scale_log2;
+    const uint64_t sl2x2 = pack_f2(sl2, sl2);
+    uint8_t* stage = sStage + t * S::kBoxBytes;
+    int cqt = 0, cst = 0;   // tiles / key blocks this warpgroup has processed
+    for (int tl = 0;; ++tl) {
+      Tile ti;
+      if (!next_tile(tl, ti)) break;
+      const int nbt = t ? ti.nb1 : ti.nb0;
+      if (nbt == 0) continue;   // this tile has no second half
+      const int q0 = ti.q0;
+      const int q_row = q0 + t * 128 + row;
+      float m_used = -1e30f;
+      float l = 0.f;
+      for (int i = 0; i < nbt; ++i) {
+        mbar_wait(bars + S::kSFull + t, (cst + i) & 1);
+        tc_fence_after();
+        uint32_t sr[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, sr[c]);
+        tmem_ld_wait();
+        const int k0 = i * 128;
+        const bool need_mask = (k0 + 128 > KL) || (p.causal && (k0 + 127 > q0 + t * 128));
+        if (need_mask) {
+          const int lim = p.causal ? min(KL - 1, q_row) : (KL - 1);  // last visible key
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (k0 + c * 32 + j > lim) sr[c][j] = 0xff800000u;  // -inf
+        }
+        auto exp_chunk = [&](int c, float (&pf)[32]) {
+          const uint64_t negm2 = pack_f2(-m_used, -m_used);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint64_t x2 = ffma2(pack_f2(__uint_as_float(sr[c][2 * j]), __uint_as_float(sr[c][2 * j + 1])),
+                                      sl2x2, negm2);
+            float x0, x1;
+            unpack_f2(x2, x0, x1);
+            pf[2 * j] = fast_exp2(x0);
+            pf[2 * j + 1] = fast_exp2(x1);
+          }
+        };
+        float pf[32];
+        exp_chunk(0, pf);   // speculative against the running reference max (see the one-tile kernel)
+        float mx8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mx8[u] = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            mx8[j & 7] = fmax3(mx8[j & 7], __uint_as_float(sr[c][2 * j]), __uint_as_float(sr[c][2 * j + 1]));
+        const float mx = fmax3(fmax3(mx8[0], mx8[1], mx8[2]), fmax3(mx8[3], mx8[4], mx8[5]),
+                               fmaxf(mx8[6], mx8[7]));
+        const float mx_s = mx * sl2;
+        const bool grow = mx_s > m_used + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = grow ? mx_s : m_used;
+          const float alpha = fast_exp2(m_used - m_new);
+          m_used = m_new;
+          l *= alpha;
+          if (i > 0) {
+#pragma unroll
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t orow[32];
+              tmem_ld_x32(tO + c * 32, orow);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) orow[j] = __float_as_uint(__uint_as_float(orow[j]) * alpha);
+              tmem_st_x32(tO + c * 32, orow);
+            }
+          }
+          exp_chunk(0, pf);
+        }
+        uint64_t sum2 = pack_f2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c > 0) exp_chunk(c, pf);
+          uint32_t pr[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            sum2 = fadd2(sum2, pack_f2(pf[2 * j], pf[2 * j + 1]));
+            pr[j] = pack2<T>(pf[2 * j], pf[2 * j + 1]);
+          }
+          tmem_st_x16(tS + c * 16, pr);
+          if (c & 1) {  // half of the keys are in TMEM: release the tensor pipe
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + S::kPHalf + 2 * t + (c >> 1));
+          }
+        }
+        float s0, s1;
+        unpack_f2(sum2, s0, s1);
+        l += s0 + s1;
+      }
+      cst += nbt;
+      // ---- epilogue: O / l -> 16-bit -> private staging, one 64-column box at a time -> TMA store
+      mbar_wait(bars + S::kOFull + t, cqt & 1);
+      tc_fence_after();
+      ++cqt;
+      const float inv_l = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+      for (int bx = 0; bx < S::kNBox; ++bx) {
+        uint32_t o2[2][32];
+        tmem_ld_x32(tO + bx * 64, o2[0]);
+        tmem_ld_x32(tO + bx * 64 + 32, o2[1]);
+        tmem_ld_wait();
+        if (bx == S::kNBox - 1) {   // O_t is in registers: the next tile's first PV may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars + S::kOEmpty + t);
+        }
+        if (wq == 0 && lane == 0) bulk_wait_read<0>();   // the previous store has read the staging box
+        named_bar_sync(1 + t, 128);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 v;
+            v.x = pack2<T>(__uint_as_float(o2[c][8 * u + 0]) * inv_l, __uint_as_float(o2[c][8 * u + 1]) * inv_l);
+            v.y = pack2<T>(__uint_as_float(o2[c][8 * u + 2]) * inv_l, __uint_as_float(o2[c][8 * u + 3]) * inv_l);
+            v.z = pack2<T>(__uint_as_float(o2[c][8 * u + 4]) * inv_l, __uint_as_float(o2[c][8 * u + 5]) * inv_l);
+            v.w = pack2<T>(__uint_as_float(o2[c][8 * u + 6]) * inv_l, __uint_as_float(o2[c][8 * u + 7]) * inv_l);
+            const int cin = c * 4 + u;  // 16-byte chunk within the 128-byte box row
+            *reinterpret_cast<uint4*>(stage + row * 128 + ((cin ^ (row & 7)) << 4)) = v;
+          }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + t, 128);
+        if (wq == 0 && lane == 0) {
+          tma_store_3d(&tm_o, stage, bx * 64, q0 + t * 128, ti.bh_q);
+          bulk_commit();
+        }
+      }
+      if (q_row < QL)
+        p.lse[static_cast<int64_t>(ti.bh_q) * QL + q_row] = l > 0.f ? (m_used + fast_log2(l)) * kLn2 : -INFINITY;
+    }
+    if (wq == 0 && lane == 0) bulk_wait<0>();
+  }
+
+  // ---- teardown -------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // x (rows, 64) fp32 -> (rows, 128) fp16 = [hi(64) | lo(64)], hi = fp16(x), lo = fp16(x - hi): 22
 // significant bits (bf16 terms would give 16, not enough for 1e-4 absolute on gradients of
 // magnitude ~5).  |x| must stay below 65504 -- the reference itself stages Q and K as Float16 in
@@ -802,7 +1239,56 @@ int launch_fwd(const AttnParams& a) {
   return NNOP_OK;
 }
 
+// per-launch tile counters of the persistent forward: a launch takes the next slot round-robin and
+// zeroes it on its own stream first, so stream-ordered launches never share a live slot (launches
+// on different streams would have to be 256 launches apart and still running to collide)
+__device__ int g_fwd_tile_counters[256];
+std::atomic<unsigned> g_fwd_slot{0};
+std::atomic<int> g_fwd_mode{-1};
+
+inline int fwd_mode() {
+  int m = g_fwd_mode.load();
+  if (m < 0) {
+    const char* e = getenv("NNOP_FWD_MODE");
+    m = e ? atoi(e) : 0;
+    g_fwd_mode.store(m);
+  }
+  return m;
+}
+
+template <typename T, int D>
+int launch_fwd_persist(const AttnParams& a, int ctas) {
+  using S = FwdPersistSmem<D>;
+  alignas(64) CUtensorMap tq, tk, tv, to;
+  const uint64_t bhq = static_cast<uint64_t>(a.B) * a.QH, bhk = static_cast<uint64_t>(a.B) * a.KH;
+  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, D, a.QL, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&to, a.o, a.dtype, D, a.QL, bhq, 64, 128)) return rc;
+  auto kern = attn_fwd_sm100_persist_kernel<T, D>;
+  NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynBytes));
+  FwdParams fp;
+  fp.lse = a.lse;
+  fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
+  fp.scale_log2 = a.scale * kLog2e;
+  fp.cu_q = nullptr; fp.cu_k = nullptr; fp.o_ptr = a.o; fp.total_q = 0; fp.kpad = nullptr; fp.nseq = 0;
+  int* counters = nullptr;
+  NNOP_CUDA_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&counters), g_fwd_tile_counters));
+  int* counter = counters + (g_fwd_slot.fetch_add(1) & 255u);
+  NNOP_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), a.stream));
+  const int nqt = (a.QL + 255) / 256;
+  const int64_t n_tiles = static_cast<int64_t>(nqt) * a.QH * a.B;
+  const int grid = static_cast<int>(n_tiles < ctas ? n_tiles : ctas);
+  timing_begin(0, a.stream);
+  kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, fp, counter, static_cast<int>(n_tiles), nqt, a.B);
+  timing_end(0, a.stream);
+  NNOP_LAUNCH_CHECK();
+  return NNOP_OK;
+}
+
 }  // namespace
+
+void attn_sm100_set_fwd_mode(int mode) { g_fwd_mode.store(mode); }
 
 #ifdef NNOP_FWD_TRACE
 extern "C" int nnop_debug_fwd_trace(long long* host_out, int n) {
@@ -845,6 +1331,21 @@ int attn_sm100_fwd(const AttnParams& a) {
     return a.E == 128 ? launch_fwd<__half, 128, true>(a) : launch_fwd<__half, 64, true>(a);
   }
   if (a.dtype == NNOP_F32) return launch_fwd_f32<false>(a);
+  // forward variant (nnop_set_fwd_mode / NNOP_FWD_MODE): 0 automatic, 1 one CTA per q tile, 2 persistent,
+  // 100+n persistent on n CTAs
+  const int mode = fwd_mode();
+  const int64_t n_tiles = static_cast<int64_t>((a.QL + 255) / 256) * a.QH * a.B;
+  const bool persist_ok = a.cu_q == nullptr && a.kpad == nullptr && a.KL >= 1 && n_tiles < (1LL << 30);
+  // automatic choice, from measurement (profiles/r01d_perf_fwd_modes.txt): the persistent kernel wins
+  // where the per-tile fixed cost matters -- E = 64 (+15 %) and short sequences (L = 2 048: +6 %) --
+  // and is neutral (bench.py regime) to slower (back-to-back launches) on long E = 128 tiles
+  const bool persist_pays = a.E == 64 || a.QL <= 2048;
+  if (persist_ok && (mode == 2 || mode >= 100 || (mode == 0 && persist_pays && n_tiles >= 2LL * sm_count()))) {
+    const int ctas = mode >= 100 ? (mode - 100 < 1 ? 1 : mode - 100) : sm_count();
+    if (a.dtype == NNOP_BF16)
+      return a.E == 128 ? launch_fwd_persist<__nv_bfloat16, 128>(a, ctas) : launch_fwd_persist<__nv_bfloat16, 64>(a, ctas);
+    return a.E == 128 ? launch_fwd_persist<__half, 128>(a, ctas) : launch_fwd_persist<__half, 64>(a, ctas);
+  }
   if (a.dtype == NNOP_BF16)
     return a.E == 128 ? launch_fwd<__nv_bfloat16, 128>(a) : launch_fwd<__nv_bfloat16, 64>(a);
   return a.E == 128 ? launch_fwd<__half, 128>(a) : launch_fwd<__half, 64>(a);

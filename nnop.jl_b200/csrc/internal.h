@@ -88,6 +88,7 @@ int attn_bwd_preprocess(const AttnParams& p);
 // attn_fwd_sm100.cu / attn_bwd_sm100.cu -- tcgen05 + TMA path (bf16/f16, E in {64,128})
 bool attn_sm100_supported(const AttnParams& p, bool backward);
 int attn_sm100_fwd(const AttnParams& p);
+void attn_sm100_set_fwd_mode(int mode);  // 0 auto, 1 one CTA per q tile, 2 persistent, 100+n persistent on n CTAs
 size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B);
 // (rows, 64) fp32 -> (rows, 128) bf16 rows [hi(64) | lo(64)] with x ~ hi + lo (Float32 tensor-core path)
 int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, cudaStream_t st);

@@ -14,7 +14,7 @@ from .ops import (  # noqa: F401
     rms_norm, _rms_norm, grad_rms_norm,
     layer_norm, _layer_norm, grad_layer_norm,
     llama_rope, grad_llama_rope, LlamaRotaryEmbedding,
-    device_info, set_attention_path, last_attention_path, selftest_umma, set_bwd_pair_mode,
+    device_info, set_attention_path, last_attention_path, selftest_umma, set_bwd_pair_mode, set_fwd_mode,
     set_timing_events, HostAttentionPipeline,
 )
 from .sharding import shard_slices, shard_attention_inputs  # noqa: F401
@@ -30,7 +30,7 @@ __all__ = [
     "device_info", "set_attention_path", "last_attention_path", "selftest_umma",
     "shard_slices", "shard_attention_inputs", "NNopError", "set_timing_events",
     "HostAttentionPipeline", "flash_attention_varlen", "_flash_attention_varlen",
-    "grad_flash_attention_varlen", "set_bwd_pair_mode", "ring_flash_attention", "ring_attention_forward",
+    "grad_flash_attention_varlen", "set_bwd_pair_mode", "set_fwd_mode", "ring_flash_attention", "ring_attention_forward",
     "ring_attention_backward", "ring_schedule", "zigzag_shard", "zigzag_unshard", "contiguous_shard",
 ]
 # the reference spells its pullbacks with a nabla; reachable via getattr(nnop_b200, "∇flash_attention")

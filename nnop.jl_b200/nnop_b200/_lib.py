@@ -46,6 +46,7 @@ SIGNATURES = {
     "nnop_set_attention_path": (_i, [_i]),
     "nnop_last_attention_path": (_i, []),
     "nnop_set_bwd_pair_mode": (_i, [_i]),
+    "nnop_set_fwd_mode": (_i, [_i]),
     "nnop_flash_attn_fwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, _vp]),
     "nnop_flash_attn_fwd_workspace_bytes": (_sz, [_i] * 7),
     "nnop_flash_attn_pair_workspace_bytes": (_sz, [_i] * 6),

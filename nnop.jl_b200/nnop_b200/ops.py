@@ -72,6 +72,12 @@ def set_bwd_pair_mode(mode: int) -> None:
     check(lib.nnop_set_bwd_pair_mode(int(mode)))
 
 
+def set_fwd_mode(mode: int) -> None:
+    """Forward kernel variant on the tcgen05 path: 0 automatic (persistent kernel for deep tile queues),
+    1 one CTA per q tile, 2 persistent, 100+n persistent on n CTAs."""
+    check(lib.nnop_set_fwd_mode(int(mode)))
+
+
 def selftest_umma(a: torch.Tensor, b: torch.Tensor, which: int) -> torch.Tensor:
     _req(a, b)
     out = torch.empty(128, 128, dtype=torch.float32, device=a.device)

@@ -445,3 +445,30 @@ def test_persistent_backward_matches_one_cta_per_tile(nnop, causal, E):
                 assert max_abs(got[0], ref[0]) <= 2 ** -7 * max(1.0, ref[0].abs().max().item())
     finally:
         nnop.set_bwd_pair_mode(0)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("E", [64, 128])
+def test_persistent_forward_matches_one_cta_per_tile(nnop, causal, E):
+    """The persistent forward (dynamic queue of (q tile, head, batch) work tiles, next tile's Q / K / V
+    loaded under the current one, O stored through private staging) runs the same softmax code as the
+    one-CTA-per-tile kernel: O and lse bit for bit.  On all SMs (mode 2) and squeezed onto 1 / 3 CTAs
+    (modes 101 / 103) so that every CTA walks many tiles of different lengths back to back."""
+    try:
+        for trial, (B, QH, KH, QL, KL) in enumerate([(1, 1, 1, 512, 256), (2, 4, 2, 1024, 1024), (1, 2, 2, 300, 700),
+                                                     (1, 2, 1, 1000, 1000), (3, 2, 2, 640, 640), (1, 1, 1, 128, 128),
+                                                     (2, 3, 3, 129, 129), (1, 6, 2, 2048, 2048), (2, 2, 2, 257, 257),
+                                                     (1, 1, 1, 1, 1), (1, 2, 2, 255, 64)]):
+            if causal and QL != KL:
+                continue
+            dtype = torch.bfloat16 if trial % 2 == 0 else torch.float16
+            q, k, v, dO, _, _ = _inputs(B, QH, KH, QL, KL, E, dtype, 200 + trial)
+            qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
+            nnop.set_fwd_mode(1)
+            o_ref, lse_ref = nnop._flash_attention(qd, kd, vd, causal=causal)
+            for mode in (2, 101, 103, 2):
+                nnop.set_fwd_mode(mode)
+                o, lse = nnop._flash_attention(qd, kd, vd, causal=causal)
+                assert torch.equal(o, o_ref) and torch.equal(lse, lse_ref), (mode, B, QH, KH, QL, KL)
+    finally:
+        nnop.set_fwd_mode(0)
