@@ -137,6 +137,17 @@ int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, const void* d
                         const void* v, const void* pair, const uint8_t* kpad_mask, int dtype,
                         int E, int QL, int KL, int QH, int KH, int B, int causal, float scale,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Same, for callers that kept the forward's workspace alive: `pair_head_major` is the head-major copy
+ * of `pair` that nnop_flash_attn_fwd_ws left at offset round_up(nnop_flash_attn_fwd_workspace_bytes,
+ * 256) of its workspace (same dims, same dtype).  The backward then skips its own layout change of
+ * pair and its workspace only needs round_up(bwd_workspace_bytes, 256) + pair_workspace_bytes(..., 0)
+ * (the dpair staging area).  NULL = nnop_flash_attn_bwd. */
+int nnop_flash_attn_bwd_reuse_pair(void* dq, void* dk, void* dv, void* dpair, const void* dO,
+                                   const void* o, const float* lse, const void* q, const void* k,
+                                   const void* v, const void* pair, const uint8_t* kpad_mask,
+                                   int dtype, int E, int QL, int KL, int QH, int KH, int B,
+                                   int causal, float scale, void* workspace, size_t workspace_bytes,
+                                   void* stream, const void* pair_head_major);
 
 /* ---------------------------------------------------------------------------------------
  * Packed variable-length flash attention (additive: the reference only has the dense Bool

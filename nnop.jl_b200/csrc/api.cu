@@ -213,12 +213,12 @@ extern "C" size_t nnop_flash_attn_bwd_workspace_bytes(int dtype, int E, int QL, 
   return delta + rest;
 }
 
-extern "C" int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, const void* dO,
-                                   const void* o, const float* lse, const void* q, const void* k,
-                                   const void* v, const void* pair, const uint8_t* kpad_mask,
-                                   int dtype, int E, int QL, int KL, int QH, int KH, int B,
-                                   int causal, float scale, void* workspace, size_t workspace_bytes,
-                                   void* stream) {
+static int flash_attn_bwd_impl(void* dq, void* dk, void* dv, void* dpair, const void* dO,
+                               const void* o, const float* lse, const void* q, const void* k,
+                               const void* v, const void* pair, const uint8_t* kpad_mask,
+                               int dtype, int E, int QL, int KL, int QH, int KH, int B,
+                               int causal, float scale, void* workspace, size_t workspace_bytes,
+                               void* stream, const void* pair_head_major) {
   clear_error();
   if (int rc = validate(dtype, E, QL, KL, QH, KH, B)) return rc;
   if (static_cast<int64_t>(B) * QL == 0 && static_cast<int64_t>(B) * KL == 0) return NNOP_OK;
@@ -246,7 +246,14 @@ extern "C" int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, co
     // pair bias on the tensor cores: head-major pair and dpair staging behind the base workspace
     const size_t base = up256(need);
     const size_t one = attn_pair_workspace_bytes(dtype, QL, KL, QH, B, false);
-    if (workspace_bytes >= base + 2 * one) {
+    if (pair_head_major && (reinterpret_cast<uintptr_t>(pair_head_major) & 255) == 0 &&
+        workspace_bytes >= base + one) {
+      // the forward's head-major copy is still alive: no second layout change of pair
+      p.pair_t = const_cast<void*>(pair_head_major);
+      p.pair_t_ready = 1;
+      p.dpair_t = static_cast<char*>(workspace) + base;
+      p.KLp = pair_klp(KL);
+    } else if (workspace_bytes >= base + 2 * one) {
       p.pair_t = static_cast<char*>(workspace) + base;
       p.dpair_t = static_cast<char*>(workspace) + base + one;
       p.KLp = pair_klp(KL);
@@ -302,6 +309,27 @@ static int validate_varlen(int dtype, int E, int nseq, int max_q, int max_k, int
     return fail(NNOP_ERR_SHAPE, "Invalid packed shape nseq=%d total_q=%lld total_k=%lld.", nseq,
                 static_cast<long long>(total_q), static_cast<long long>(total_k));
   return NNOP_OK;
+}
+
+extern "C" int nnop_flash_attn_bwd(void* dq, void* dk, void* dv, void* dpair, const void* dO,
+                                   const void* o, const float* lse, const void* q, const void* k,
+                                   const void* v, const void* pair, const uint8_t* kpad_mask,
+                                   int dtype, int E, int QL, int KL, int QH, int KH, int B,
+                                   int causal, float scale, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  return flash_attn_bwd_impl(dq, dk, dv, dpair, dO, o, lse, q, k, v, pair, kpad_mask, dtype, E, QL, KL, QH,
+                             KH, B, causal, scale, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int nnop_flash_attn_bwd_reuse_pair(void* dq, void* dk, void* dv, void* dpair, const void* dO,
+                                              const void* o, const float* lse, const void* q,
+                                              const void* k, const void* v, const void* pair,
+                                              const uint8_t* kpad_mask, int dtype, int E, int QL, int KL,
+                                              int QH, int KH, int B, int causal, float scale,
+                                              void* workspace, size_t workspace_bytes, void* stream,
+                                              const void* pair_head_major) {
+  return flash_attn_bwd_impl(dq, dk, dv, dpair, dO, o, lse, q, k, v, pair, kpad_mask, dtype, E, QL, KL, QH,
+                             KH, B, causal, scale, workspace, workspace_bytes, stream, pair_head_major);
 }
 
 extern "C" int nnop_flash_attn_varlen_fwd(void* o, float* lse, const void* q, const void* k,

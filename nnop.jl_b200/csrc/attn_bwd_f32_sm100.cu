@@ -596,7 +596,7 @@ int attn_f32_bwd(const AttnParams& a) {
   const bool bias = a.pair != nullptr;
   auto kern = bias ? attn_bwd_f32_kernel<true> : attn_bwd_f32_kernel<false>;
   NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-  if (bias)
+  if (bias && !a.pair_t_ready)
     if (int rc = attn_pair_to_head_major(a)) return rc;
   Params bp;
   bp.lse2p = lse2p; bp.deltap = deltap;

@@ -1851,7 +1851,7 @@ int launch_bwd(const AttnParams& a) {
   bp.pair_t = a.pair_t; bp.dpair_t = a.dpair_t; bp.KLp = a.KLp;
   bp.tile_pre = tile_pre; bp.nseq = a.nseq;
   const bool bias = a.pair != nullptr;
-  if (bias)
+  if (bias && !a.pair_t_ready)
     if (int rc = attn_pair_to_head_major(a)) return rc;
   const int nkv = (a.KL + 127) / 128;
   // kernel variant (nnop_set_bwd_pair_mode / NNOP_BWD_PAIR): 0 = automatic (persistent kernel when the

@@ -73,6 +73,7 @@ struct AttnParams {
   void* pair_t;
   void* dpair_t;
   int KLp;
+  int pair_t_ready;  // backward: pair_t already holds the copy (made by the forward)
 };
 
 // one-shot timing hook (api.cu); which: 0 forward kernel, 1 backward main kernel

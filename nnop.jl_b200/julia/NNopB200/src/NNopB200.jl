@@ -59,17 +59,22 @@ function _flash_attention(
     lse = CUDA.zeros(Float32, QL, QH, B)
     # optional workspace: lets Float32 (E = 64) run on the tensor cores (split fp16 operands) and, with
     # the pair extension, keeps the additive bias on the tensor-core path (head-major copy of `pair`)
-    nbytes = ccall((:nnop_flash_attn_fwd_workspace_bytes, libnnop_b200), Csize_t,
+    base = ccall((:nnop_flash_attn_fwd_workspace_bytes, libnnop_b200), Csize_t,
         (Cint, Cint, Cint, Cint, Cint, Cint, Cint), dtype_code(T), QE, QL, KL, QH, KH, B)
-    isnothing(pair) || (nbytes = pair_workspace(nbytes, T, QL, KL, QH, B, false))
+    nbytes = isnothing(pair) ? base : pair_workspace(base, T, QL, KL, QH, B, false)
     ws = nbytes > 0 ? CuArray{UInt8}(undef, nbytes) : nothing
     check(ccall((:nnop_flash_attn_fwd_ws, libnnop_b200), Cint,
         (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
          Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cfloat, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
         ptr(o), ptr(lse), ptr(q), ptr(k), ptr(v), ptr(pair), ptr(kpad_mask),
         dtype_code(T), QE, QL, KL, QH, KH, B, causal, Float32(inv(sqrt(QE))), ptr(ws), nbytes, stream()))
-    isnothing(ws) || CUDA.unsafe_free!(ws)
-    return o, lse, nothing
+    # third residual (the reference's `ls` slot): with a pair bias, the workspace that now holds the
+    # head-major copy of `pair`, and its offset -- the backward takes it instead of making its own
+    if isnothing(pair)
+        isnothing(ws) || CUDA.unsafe_free!(ws)
+        return o, lse, nothing
+    end
+    return o, lse, (ws, Int((base + 255) & ~Csize_t(255)))
 end
 
 # ∇flash_attention: src/attention_bwd.jl:199-275 (`ms` carries lse, `ls` is unused)
@@ -85,15 +90,20 @@ function ∇flash_attention(
     dpair = isnothing(pair) ? nothing : similar(pair)
     nbytes = ccall((:nnop_flash_attn_bwd_workspace_bytes, libnnop_b200), Csize_t,
         (Cint, Cint, Cint, Cint, Cint, Cint, Cint), dtype_code(T), QE, QL, KL, QH, KH, B)
-    isnothing(pair) || (nbytes = pair_workspace(nbytes, T, QL, KL, QH, B, true))
+    # `ls` carries the forward's (workspace, offset) when a pair bias was given: its head-major copy of
+    # `pair` is reused and this workspace only needs the dpair staging area
+    reuse = !isnothing(pair) && ls isa Tuple
+    isnothing(pair) || (nbytes = pair_workspace(nbytes, T, QL, KL, QH, B, !reuse))
+    pair_hm = reuse ? ptr(ls[1]) + ls[2] : ptr(nothing)
     ws = CuArray{UInt8}(undef, max(nbytes, 1))
-    check(ccall((:nnop_flash_attn_bwd, libnnop_b200), Cint,
+    check(ccall((:nnop_flash_attn_bwd_reuse_pair, libnnop_b200), Cint,
         (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
          CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
-         Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cfloat, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+         Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cfloat, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid},
+         CuPtr{Cvoid}),
         ptr(dq), ptr(dk), ptr(dv), ptr(dpair), ptr(Δ), ptr(o), ptr(ms), ptr(q), ptr(k), ptr(v),
         ptr(pair), ptr(kpad_mask), dtype_code(T), QE, QL, KL, QH, KH, B, causal,
-        Float32(inv(sqrt(QE))), ptr(ws), nbytes, stream()))
+        Float32(inv(sqrt(QE))), ptr(ws), nbytes, stream(), pair_hm))
     CUDA.unsafe_free!(ws)
     return dq, dk, dv, dpair
 end
@@ -107,10 +117,10 @@ end
 
 function CRC.rrule(::typeof(_flash_attention), q, k, v, pair::Maybe{AbstractArray{<:Real,4}} = nothing;
                    causal::Bool, kpad_mask::Maybe{AbstractMatrix{Bool}} = nothing)         # src/attention_crc.jl:16-31
-    o, lse, _ = _flash_attention(q, k, v, pair; causal, kpad_mask)
+    o, lse, ls = _flash_attention(q, k, v, pair; causal, kpad_mask)   # ls: forward workspace with the pair copy
     function _pullback(Δ)
         Δd = convert(typeof(o), CRC.unthunk(Δ))      # Zygote may hand a Fill / thunk: materialise
-        dq, dk, dv, dpair = ∇flash_attention(Δd, o, lse, nothing, q, k, v, pair; causal, kpad_mask)
+        dq, dk, dv, dpair = ∇flash_attention(Δd, o, lse, ls, q, k, v, pair; causal, kpad_mask)
         return CRC.NoTangent(), dq, dk, dv, (isnothing(dpair) ? CRC.NoTangent() : dpair)
     end
     return o, _pullback

@@ -53,6 +53,7 @@ SIGNATURES = {
     "nnop_flash_attn_fwd_ws": (_i, [_vp] * 7 + [_i] * 8 + [_f, _vp, _sz, _vp]),
     "nnop_flash_attn_bwd_workspace_bytes": (_sz, [_i] * 7),
     "nnop_flash_attn_bwd": (_i, [_vp] * 12 + [_i] * 8 + [_f, _vp, _sz, _vp]),
+    "nnop_flash_attn_bwd_reuse_pair": (_i, [_vp] * 12 + [_i] * 8 + [_f, _vp, _sz, _vp, _vp]),
     "nnop_flash_attn_varlen_fwd": (_i, [_vp] * 7 + [_i] * 3 + [_i64, _i64] + [_i] * 5 + [_f, _vp]),
     "nnop_flash_attn_varlen_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i64, _i]),
     "nnop_flash_attn_varlen_bwd": (_i, [_vp] * 11 + [_i] * 3 + [_i64, _i64] + [_i] * 5 + [_f, _vp, _sz, _vp]),

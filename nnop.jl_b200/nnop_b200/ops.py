@@ -115,8 +115,10 @@ def _up256(n: int) -> int:
     return (n + 255) & ~255
 
 
-def _flash_attention(q, k, v, pair=None, *, causal: bool, kpad_mask=None):
-    """`_flash_attention` (src/attention.jl:133-177).  Returns ``(o, lse)``."""
+def _flash_attention(q, k, v, pair=None, *, causal: bool, kpad_mask=None, keep_pair_copy: bool = False):
+    """`_flash_attention` (src/attention.jl:133-177).  Returns ``(o, lse)``; with ``keep_pair_copy`` a
+    third residual (the reference returns a 3-tuple too): the head-major copy of `pair` the library
+    made in its workspace (or None), which `grad_flash_attention` can take instead of making its own."""
     _req(q, k, v, pair, kpad_mask)
     B, QH, QL, E, KH, KL = _attn_dims(q, k, v, pair, kpad_mask)
     o = torch.empty_like(q)
@@ -129,11 +131,18 @@ def _flash_attention(q, k, v, pair=None, *, causal: bool, kpad_mask=None):
     check(lib.nnop_flash_attn_fwd_ws(_p(o), _p(lse), _p(q), _p(k), _p(v), _p(pair), _p(kpad_mask),
                                      _dt(q), E, QL, KL, QH, KH, B, int(bool(causal)), scale,
                                      _p(ws), ws_bytes, _stream()))
+    if keep_pair_copy:
+        hm = None
+        if pair is not None and last_attention_path() == 1:  # the copy sits behind the base workspace
+            hm = ws[_up256(lib.nnop_flash_attn_fwd_workspace_bytes(_dt(q), E, QL, KL, QH, KH, B)):]
+        return o, lse, hm
     return o, lse
 
 
-def grad_flash_attention(dO, o, lse, q, k, v, pair=None, *, causal: bool, kpad_mask=None):
-    """`∇flash_attention` (src/attention_bwd.jl:199-275).  Returns ``(dq, dk, dv, dpair|None)``."""
+def grad_flash_attention(dO, o, lse, q, k, v, pair=None, *, causal: bool, kpad_mask=None,
+                         pair_head_major=None):
+    """`∇flash_attention` (src/attention_bwd.jl:199-275).  Returns ``(dq, dk, dv, dpair|None)``.
+    ``pair_head_major``: the third residual of ``_flash_attention(..., keep_pair_copy=True)``."""
     _req(dO, o, lse, q, k, v, pair, kpad_mask)
     B, QH, QL, E, KH, KL = _attn_dims(q, k, v, pair, kpad_mask)
     if tuple(dO.shape) != tuple(q.shape) or dO.dtype != q.dtype:
@@ -143,13 +152,15 @@ def grad_flash_attention(dO, o, lse, q, k, v, pair=None, *, causal: bool, kpad_m
     dv = torch.empty_like(v)
     dpair = torch.empty_like(pair) if pair is not None else None
     ws_bytes = lib.nnop_flash_attn_bwd_workspace_bytes(_dt(q), E, QL, KL, QH, KH, B)
-    if pair is not None:  # head-major pair + dpair staging (tensor-core path)
-        ws_bytes = _up256(ws_bytes) + lib.nnop_flash_attn_pair_workspace_bytes(_dt(q), QL, KL, QH, B, 1)
+    if pair is not None:  # (head-major pair +) dpair staging (tensor-core path)
+        ws_bytes = _up256(ws_bytes) + lib.nnop_flash_attn_pair_workspace_bytes(
+            _dt(q), QL, KL, QH, B, 0 if pair_head_major is not None else 1)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=q.device)
     scale = 1.0 / math.sqrt(E)
-    check(lib.nnop_flash_attn_bwd(_p(dq), _p(dk), _p(dv), _p(dpair), _p(dO), _p(o), _p(lse), _p(q),
-                                  _p(k), _p(v), _p(pair), _p(kpad_mask), _dt(q), E, QL, KL, QH, KH,
-                                  B, int(bool(causal)), scale, _p(ws), ws_bytes, _stream()))
+    check(lib.nnop_flash_attn_bwd_reuse_pair(
+        _p(dq), _p(dk), _p(dv), _p(dpair), _p(dO), _p(o), _p(lse), _p(q), _p(k), _p(v), _p(pair),
+        _p(kpad_mask), _dt(q), E, QL, KL, QH, KH, B, int(bool(causal)), scale, _p(ws), ws_bytes, _stream(),
+        _p(pair_head_major) if pair is not None else None))
     return dq, dk, dv, dpair
 
 
@@ -158,16 +169,16 @@ class _FlashAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, pair, causal, kpad_mask):
-        o, lse = _flash_attention(q, k, v, pair, causal=causal, kpad_mask=kpad_mask)
-        ctx.save_for_backward(o, lse, q, k, v, pair, kpad_mask)
+        o, lse, hm = _flash_attention(q, k, v, pair, causal=causal, kpad_mask=kpad_mask, keep_pair_copy=True)
+        ctx.save_for_backward(o, lse, q, k, v, pair, kpad_mask, hm)
         ctx.causal = causal
         return o
 
     @staticmethod
     def backward(ctx, dO):
-        o, lse, q, k, v, pair, kpad_mask = ctx.saved_tensors
+        o, lse, q, k, v, pair, kpad_mask, hm = ctx.saved_tensors
         dq, dk, dv, dpair = grad_flash_attention(dO.contiguous(), o, lse, q, k, v, pair,
-                                                 causal=ctx.causal, kpad_mask=kpad_mask)
+                                                 causal=ctx.causal, kpad_mask=kpad_mask, pair_head_major=hm)
         return dq, dk, dv, dpair, None, None
 
 

@@ -472,3 +472,23 @@ def test_persistent_forward_matches_one_cta_per_tile(nnop, causal, E):
                 assert torch.equal(o, o_ref) and torch.equal(lse, lse_ref), (mode, B, QH, KH, QL, KL)
     finally:
         nnop.set_fwd_mode(0)
+
+
+@pytest.mark.parametrize("dtype,E", [(torch.float32, 64), (torch.bfloat16, 128)])
+def test_backward_reuses_forward_pair_copy(nnop, dtype, E):
+    """The head-major copy of `pair` the forward leaves in its workspace can be handed to the backward
+    (nnop_flash_attn_bwd_reuse_pair; the rrule keeps it as its third residual, where the reference
+    keeps `ls`): same gradients bit for bit (dQ up to its atomics), one layout change less."""
+    q, k, v, dO, pr, m = _inputs(2, 4, 2, 384, 384, E, dtype, 31, pair=True, mask=True)
+    qd, kd, vd, dOd, pd, md = (t.cuda() for t in (q, k, v, dO, pr, m))
+    o, lse, hm = nnop._flash_attention(qd, kd, vd, pd, causal=True, kpad_mask=md, keep_pair_copy=True)
+    assert hm is not None and nnop.last_attention_path() == 1
+    ref = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, pd, causal=True, kpad_mask=md)
+    got = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, pd, causal=True, kpad_mask=md, pair_head_major=hm)
+    assert nnop.last_attention_path() == 1
+    assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])
+    assert max_abs(got[0], ref[0]) <= 2 ** -7 * max(1.0, ref[0].abs().max().item())
+    # and through autograd (the public flash_attention)
+    qa, ka, va, pa = (t.clone().requires_grad_(True) for t in (qd, kd, vd, pd))
+    nnop.flash_attention(qa, ka, va, pa, causal=True, kpad_mask=md).backward(dOd)
+    assert torch.equal(ka.grad, ref[1]) and torch.equal(va.grad, ref[2]) and torch.equal(pa.grad, ref[3])
