@@ -759,7 +759,7 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
                               const __grid_constant__ CUtensorMap tm_k,
                               const __grid_constant__ CUtensorMap tm_v,
                               const __grid_constant__ CUtensorMap tm_o, const FwdParams p,
-                              int* __restrict__ tile_counter, const int n_tiles, const int nqt, const int B) {
+                              int* __restrict__ tile_counter, const int n_tiles, const int nqt) {
   using S = FwdPersistSmem<D>;
   constexpr int kNStage = S::kNStage;
   extern __shared__ uint8_t smem_raw[];
@@ -1280,7 +1280,7 @@ int launch_fwd_persist(const AttnParams& a, int ctas) {
   const int64_t n_tiles = static_cast<int64_t>(nqt) * a.QH * a.B;
   const int grid = static_cast<int>(n_tiles < ctas ? n_tiles : ctas);
   timing_begin(0, a.stream);
-  kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, fp, counter, static_cast<int>(n_tiles), nqt, a.B);
+  kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, fp, counter, static_cast<int>(n_tiles), nqt);
   timing_end(0, a.stream);
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
