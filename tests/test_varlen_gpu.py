@@ -187,3 +187,18 @@ def test_varlen_persistent_backward(nnop, mode):
             assert max_abs(got[0], ref[0]) <= 2 ** -7 * max(1.0, ref[0].abs().max().item())
     finally:
         nnop.set_bwd_pair_mode(0)
+
+
+def test_varlen_many_short_sequences(nnop):
+    """A thousand short sequences (more sequences than threads in a CTA): exercises the chunked
+    block-wide count of the forward's tile lookup and the chunked tile prefix + binary search of the
+    persistent backward, both of which see one sequence per thread in the other tests."""
+    import random
+    rng = random.Random(5)
+    lens = [rng.choice([0, 1, 7, 40, 128, 129, 200, 300]) for _ in range(1000)]
+    try:
+        for mode in (0, 3, 107):
+            nnop.set_bwd_pair_mode(mode)
+            _check(nnop, lens, lens, 4, 2, 64, torch.bfloat16, True, seed=9)
+    finally:
+        nnop.set_bwd_pair_mode(0)
