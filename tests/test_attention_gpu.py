@@ -492,3 +492,28 @@ def test_backward_reuses_forward_pair_copy(nnop, dtype, E):
     qa, ka, va, pa = (t.clone().requires_grad_(True) for t in (qd, kd, vd, pd))
     nnop.flash_attention(qa, ka, va, pa, causal=True, kpad_mask=md).backward(dOd)
     assert torch.equal(ka.grad, ref[1]) and torch.equal(va.grad, ref[2]) and torch.equal(pa.grad, ref[3])
+
+
+@pytest.mark.parametrize("E,L", [(64, 1024), (128, 2048), (64, 4096)])
+def test_automatic_kernel_choice_is_transparent(nnop, E, L):
+    """Shapes for which the automatic choice takes the persistent forward (E = 64 or QL <= 2048, tile queue
+    at least two rounds deep) and the persistent backward: results must not depend on the choice --
+    O, lse, dK, dV bit for bit against the one-CTA-per-tile kernels, dQ up to its fp32 reduce order."""
+    B, H = 8, 16
+    q, k, v, dO, _, _ = _inputs(B, H, H, L, L, E, torch.bfloat16, 300 + E)
+    qd, kd, vd, dOd = q.cuda(), k.cuda(), v.cuda(), dO.cuda()
+    try:
+        nnop.set_fwd_mode(1)
+        nnop.set_bwd_pair_mode(2)
+        o_ref, lse_ref = nnop._flash_attention(qd, kd, vd, causal=True)
+        ref = nnop.grad_flash_attention(dOd, o_ref, lse_ref, qd, kd, vd, causal=True)
+        nnop.set_fwd_mode(0)
+        nnop.set_bwd_pair_mode(0)
+        o, lse = nnop._flash_attention(qd, kd, vd, causal=True)
+        got = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=True)
+    finally:
+        nnop.set_fwd_mode(0)
+        nnop.set_bwd_pair_mode(0)
+    assert torch.equal(o, o_ref) and torch.equal(lse, lse_ref)
+    assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
+    assert max_abs(got[0], ref[0]) <= 2 ** -7 * max(1.0, ref[0].abs().max().item())
