@@ -20,8 +20,9 @@
 //             by two warpgroups (thread <-> key row, half of the q columns each).  A fourth
 //             warpgroup drains dQ_i from TMEM and adds it into the fp32 accumulator with TMA
 //             reduce-add (cp.reduce.async.bulk.tensor), 32 columns at a time.
-//             Issue order per step: dV(i), S^T(i+1), dQ(i), dK(i), dP^T(i+1) so the tensor pipe
-//             works on step i's products while the warpgroups exponentiate step i+1.
+//             Issue order per step: dV(i), S^T(i+1), dQ(i), dK(i), dP^T(i+1) (persistent kernel: dK(i)
+//             before dQ(i)) so the tensor pipe works on step i's products while the warpgroups
+//             exponentiate step i+1.
 //   3. post:  dQ = T(scale * dQ_accum).
 #include <stdlib.h>
 
@@ -329,18 +330,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           mma_kk(kColS, S::kK, S::kQ + static_cast<uint32_t>((s ^ 1) * S::kTile));
           commit(s_full);
         }
-        // dQ_i = dS K_j   (A: dS^T smem viewed MN-major; B: K_j MN-major)
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
         BWD_STAMP(it, 1);
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_ss_lo(tm + kColDP, m_lo, (S::kdS + ks * 2048) >> 4, m_hi, m_lo, (S::kK + ks * 2048) >> 4,
-                       m_hi, id_mm, ks > 0 ? 1u : 0u);
-        }
-        commit(dq_full);
-        // dK += dS^T Q_i  (A: dS^T K-major; B: Q_i MN-major)
+        // dK += dS^T Q_i  (A: dS^T K-major; B: Q_i MN-major) -- before dQ_i: it releases the Q stage,
+        // whose reload is on the S^T(i+2) critical path (see the persistent kernel)
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
@@ -350,6 +344,14 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           }
         }
         commit(&q_empty[s]);
+        // dQ_i = dS K_j   (A: dS^T smem viewed MN-major; B: K_j MN-major)
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ss_lo(tm + kColDP, m_lo, (S::kdS + ks * 2048) >> 4, m_hi, m_lo, (S::kK + ks * 2048) >> 4,
+                       m_hi, id_mm, ks > 0 ? 1u : 0u);
+        }
+        commit(dq_full);
         // dP^T(i+1) -- its TMEM columns hold dQ_i until the drain warpgroup has read them
         if (it + 1 < n_it) {
           mbar_wait(do_full, (it + 1) & 1);
@@ -926,6 +928,36 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
             mma_kk(kColS, S::kK, S::kQ + static_cast<uint32_t>((s ^ 1) * S::kTile));
             commit(PB::kSFull);
           }
+#ifndef NNOP_BWD_DQ_FIRST
+          // dK(i) before dQ(i): the Q stage is released one MMA earlier, and the load of Q_{i+2} into it
+          // sits on the S^T(i+2) critical path (measured: steady step 3 952 -> 3 870 clk); dQ(i), and
+          // with it dP^T(i+1), move back by one MMA, which the dS phase has the slack for
+          mbar_wait(bars + PB::kDsFull, gi & 1);
+          tc_fence_after();
+          if (it == 0) {
+            mbar_wait(bars + PB::kDkEmpty, (tl & 1) ^ 1);
+            tc_fence_after();
+            PT_STAMP(5);
+          }
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t off = (ks >> 2) * S::kBox + (ks & 3) * 32;
+              umma_ss_lo(tm + kColDK, k_lo, (S::kdS + off) >> 4, k_hi, m_lo, (S::kQ + qoff + ks * 2048) >> 4,
+                         m_hi, id_tv, (acc | (ks > 0)) ? 1u : 0u);
+            }
+          }
+          commit(PB::kQEmpty + s);
+          if (it == 0) PT_STAMP(4);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_ss_lo(tm + kColDP, m_lo, (S::kdS + ks * 2048) >> 4, m_hi, m_lo, (S::kK + ks * 2048) >> 4,
+                         m_hi, id_mm, ks > 0 ? 1u : 0u);
+          }
+          commit(PB::kDqFull);
+          if (it + 1 == n_it) commit(PB::kKEmpty);
+#else
           // dQ_i = dS K_j
           mbar_wait(bars + PB::kDsFull, gi & 1);
           tc_fence_after();
@@ -953,6 +985,7 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
             }
           }
           commit(PB::kQEmpty + s);
+#endif
           // dP^T(i+1)
           if (it + 1 < n_it) {
             mbar_wait(bars + PB::kDoFull, (gi + 1) & 1);
