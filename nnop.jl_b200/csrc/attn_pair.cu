@@ -96,6 +96,79 @@ dpair_from_head_major_kernel(T* __restrict__ out, const T* __restrict__ in, cons
   }
 }
 
+// 16-bit payloads, C even: the same tile transposes moving two elements per access (a 2-byte access
+// per lane only reaches half the bandwidth).  Pairs run along c on the (B, KL, C) side and along k on
+// the head-major side; rows of both sides are then 4-byte aligned (C even, KLp a multiple of 32).
+__global__ void __launch_bounds__(256)
+pair_to_head_major_16x2_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ in, int KL, int QL,
+                               int QH, int KLp, int causal) {
+  __shared__ __align__(4) uint16_t tile[kTP][kTP + 2];
+  const int b = blockIdx.z;
+  const int C = QL * QH;
+  const int k0 = blockIdx.x * kTP, c0 = blockIdx.y * kTP;
+  if (causal && k0 >= (c0 + kTP - 1) / QH + 256) return;
+  const uint16_t* src = in + static_cast<int64_t>(b) * KL * C;
+  const int c = c0 + 2 * threadIdx.x;  // this lane's pair of columns
+#pragma unroll
+  for (int r = threadIdx.y; r < kTP; r += 8) {
+    const int k = k0 + r;
+    uint32_t v = 0u;
+    if (k < KL && c < C) v = *reinterpret_cast<const uint32_t*>(src + static_cast<int64_t>(k) * C + c);
+    *reinterpret_cast<uint32_t*>(&tile[r][2 * threadIdx.x]) = v;
+  }
+  __syncthreads();
+  const int k = k0 + 2 * threadIdx.x;  // this lane's pair of keys
+#pragma unroll
+  for (int r = threadIdx.y; r < kTP; r += 8) {
+    const int cc = c0 + r;
+    if (cc < C && k < KLp) {
+      const int q = cc / QH, h = cc % QH;
+      const uint32_t v = static_cast<uint32_t>(tile[2 * threadIdx.x][r]) |
+                         (static_cast<uint32_t>(tile[2 * threadIdx.x + 1][r]) << 16);
+      *reinterpret_cast<uint32_t*>(out + ((static_cast<int64_t>(b) * QH + h) * QL + q) * KLp + k) = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dpair_from_head_major_16x2_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ in,
+                                  const uint8_t* __restrict__ kpad, int KL, int QL, int QH, int KLp, int causal) {
+  __shared__ __align__(4) uint16_t tile[kTP][kTP + 2];
+  const int b = blockIdx.z;
+  const int C = QL * QH;
+  const int k0 = blockIdx.x * kTP, c0 = blockIdx.y * kTP;
+  const bool all_dead = causal && k0 > (c0 + kTP - 1) / QH;
+  const int k = k0 + 2 * threadIdx.x;
+  bool keep0 = k < KL, keep1 = k + 1 < KL;
+  if (kpad) {
+    keep0 = keep0 && kpad[static_cast<int64_t>(b) * KL + k] != 0;
+    keep1 = keep1 && kpad[static_cast<int64_t>(b) * KL + k + 1] != 0;
+  }
+#pragma unroll
+  for (int r = threadIdx.y; r < kTP; r += 8) {
+    const int cc = c0 + r;
+    const int q = cc / QH, h = cc % QH;
+    uint32_t v = 0u;
+    if (!all_dead && cc < C && k < KLp)
+      v = *reinterpret_cast<const uint32_t*>(in + ((static_cast<int64_t>(b) * QH + h) * QL + q) * KLp + k);
+    if (!keep0 || (causal && k > q)) v &= 0xffff0000u;
+    if (!keep1 || (causal && k + 1 > q)) v &= 0x0000ffffu;
+    *reinterpret_cast<uint32_t*>(&tile[r][2 * threadIdx.x]) = v;   // tile[c][k]
+  }
+  __syncthreads();
+  uint16_t* dst = out + static_cast<int64_t>(b) * KL * C;
+  const int c = c0 + 2 * threadIdx.x;
+#pragma unroll
+  for (int r = threadIdx.y; r < kTP; r += 8) {
+    const int kk = k0 + r;
+    if (kk < KL && c < C) {
+      const uint32_t v = static_cast<uint32_t>(tile[2 * threadIdx.x][r]) |
+                         (static_cast<uint32_t>(tile[2 * threadIdx.x + 1][r]) << 16);
+      *reinterpret_cast<uint32_t*>(dst + static_cast<int64_t>(kk) * C + c) = v;
+    }
+  }
+}
+
 }  // namespace
 
 size_t attn_pair_workspace_bytes(int dtype, int QL, int KL, int QH, int B, bool backward) {
@@ -111,7 +184,11 @@ int attn_pair_to_head_major(const AttnParams& a) {
   if (a.dtype == NNOP_F32)
     pair_to_head_major_kernel<float><<<grid, block, 0, a.stream>>>(
         static_cast<float*>(a.pair_t), static_cast<const float*>(a.pair), a.KL, a.QL, a.QH, a.KLp, a.causal);
-  else  // 16-bit payloads are moved bit for bit
+  else if (C % 2 == 0 && (reinterpret_cast<uintptr_t>(a.pair) & 3) == 0)  // 16-bit payloads are moved bit for bit
+    pair_to_head_major_16x2_kernel<<<grid, block, 0, a.stream>>>(
+        static_cast<uint16_t*>(a.pair_t), static_cast<const uint16_t*>(a.pair), a.KL, a.QL, a.QH, a.KLp,
+        a.causal);
+  else
     pair_to_head_major_kernel<uint16_t><<<grid, block, 0, a.stream>>>(
         static_cast<uint16_t*>(a.pair_t), static_cast<const uint16_t*>(a.pair), a.KL, a.QL, a.QH, a.KLp,
         a.causal);
@@ -126,6 +203,10 @@ int attn_dpair_from_head_major(const AttnParams& a) {
     dpair_from_head_major_kernel<float><<<grid, block, 0, a.stream>>>(
         static_cast<float*>(a.dpair), static_cast<const float*>(a.dpair_t), a.kpad, a.KL, a.QL, a.QH, a.KLp,
         a.causal);
+  else if (C % 2 == 0 && (reinterpret_cast<uintptr_t>(a.dpair) & 3) == 0)
+    dpair_from_head_major_16x2_kernel<<<grid, block, 0, a.stream>>>(
+        static_cast<uint16_t*>(a.dpair), static_cast<const uint16_t*>(a.dpair_t), a.kpad, a.KL, a.QL, a.QH,
+        a.KLp, a.causal);
   else
     dpair_from_head_major_kernel<uint16_t><<<grid, block, 0, a.stream>>>(
         static_cast<uint16_t*>(a.dpair), static_cast<const uint16_t*>(a.dpair_t), a.kpad, a.KL, a.QL, a.QH,
