@@ -19,6 +19,10 @@
 //
 // Ragged sizes: TMA zero-fills rows past QL / KL (per head: the tensor maps are 3-D), key
 // columns >= KL are masked to -inf, and the TMA store clips rows >= QL.
+//
+// Variants in this file: attn_fwd_sm100_kernel<T, D, SPLIT, BIAS> (one CTA per 256-row q tile; SPLIT =
+// Float32 operands as two fp16 terms, BIAS = additive pair bias streamed by TMA) and
+// attn_fwd_sm100_persist_kernel<T, D> (one CTA per SM over a dynamic queue of q tiles; same softmax code).
 #include <stdlib.h>
 
 #include <atomic>
