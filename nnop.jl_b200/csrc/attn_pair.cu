@@ -15,6 +15,8 @@ namespace {
 constexpr int kTP = 64;  // tile edge: 16 independent loads per thread keep enough bytes in flight
 
 // in (B, KL, C) with C = QL * QH, c = q * QH + h  ->  out (B, QH, QL, KLp)
+// Tiles that lie fully inside the arrays (almost all of them) run without per-element predicates and
+// with the row bases hoisted: the generic form spent two thirds of its issue slots on index math.
 template <typename T>
 __global__ void __launch_bounds__(256)
 pair_to_head_major_kernel(T* __restrict__ out, const T* __restrict__ in, int KL, int QL, int QH, int KLp,
@@ -27,6 +29,30 @@ pair_to_head_major_kernel(T* __restrict__ out, const T* __restrict__ in, int KL,
   // blocks; backward: 128-row blocks), and everything above the diagonal is overwritten by the mask
   if (causal && k0 >= (c0 + kTP - 1) / QH + 256) return;
   const T* src = in + static_cast<int64_t>(b) * KL * C;
+  T* dst_b = out + static_cast<int64_t>(b) * QH * QL * KLp;
+  const bool interior = k0 + kTP <= KL && c0 + kTP <= C;
+  if (interior) {
+    const T* sp = src + static_cast<int64_t>(k0 + threadIdx.y) * C + c0 + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < kTP / 8; ++i) {
+      tile[threadIdx.y + 8 * i][threadIdx.x] = sp[0];
+      tile[threadIdx.y + 8 * i][threadIdx.x + 32] = sp[32];
+      sp += static_cast<int64_t>(8) * C;
+    }
+    __syncthreads();
+    int c = c0 + threadIdx.y;
+    int q = c / QH, h = c - q * QH;          // one division per thread; then c advances by 8
+    const int dq8 = 8 / QH, dh8 = 8 - dq8 * QH;
+#pragma unroll
+    for (int i = 0; i < kTP / 8; ++i) {
+      T* dp = dst_b + (static_cast<int64_t>(h) * QL + q) * KLp + k0 + threadIdx.x;
+      dp[0] = tile[threadIdx.x][threadIdx.y + 8 * i];
+      dp[32] = tile[threadIdx.x + 32][threadIdx.y + 8 * i];
+      q += dq8; h += dh8;
+      if (h >= QH) { h -= QH; ++q; }
+    }
+    return;
+  }
 #pragma unroll
   for (int r = threadIdx.y; r < kTP; r += 8) {
     const int k = k0 + r;
@@ -42,7 +68,7 @@ pair_to_head_major_kernel(T* __restrict__ out, const T* __restrict__ in, int KL,
     const int c = c0 + r;
     if (c < C) {
       const int q = c / QH, h = c % QH;
-      T* dst = out + ((static_cast<int64_t>(b) * QH + h) * QL + q) * KLp;
+      T* dst = dst_b + (static_cast<int64_t>(h) * QL + q) * KLp;
 #pragma unroll
       for (int kk = 0; kk < kTP; kk += 32) {
         const int k = k0 + kk + threadIdx.x;
@@ -68,6 +94,30 @@ dpair_from_head_major_kernel(T* __restrict__ out, const T* __restrict__ in, cons
   for (int kk = 0; kk < kTP; kk += 32) {
     const int k = k0 + kk + threadIdx.x;
     keep[kk / 32] = k < KL && (!kpad || kpad[static_cast<int64_t>(b) * KL + k] != 0);
+  }
+  // tiles fully inside the arrays and fully below the diagonal: no per-element predicates, hoisted bases
+  if (k0 + kTP <= KL && c0 + kTP <= C && (!causal || k0 + kTP - 1 <= c0 / QH)) {
+    int c = c0 + threadIdx.y;
+    int q = c / QH, h = c - q * QH;
+    const int dq8 = 8 / QH, dh8 = 8 - dq8 * QH;
+    const T* src_b = in + static_cast<int64_t>(b) * QH * QL * KLp;
+#pragma unroll
+    for (int i = 0; i < kTP / 8; ++i) {
+      const T* sp = src_b + (static_cast<int64_t>(h) * QL + q) * KLp + k0 + threadIdx.x;
+      tile[threadIdx.y + 8 * i][threadIdx.x] = keep[0] ? sp[0] : T(0);
+      tile[threadIdx.y + 8 * i][threadIdx.x + 32] = keep[1] ? sp[32] : T(0);
+      q += dq8; h += dh8;
+      if (h >= QH) { h -= QH; ++q; }
+    }
+    __syncthreads();
+    T* dp = out + static_cast<int64_t>(b) * KL * C + static_cast<int64_t>(k0 + threadIdx.y) * C + c0 + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < kTP / 8; ++i) {
+      dp[0] = tile[threadIdx.x][threadIdx.y + 8 * i];
+      dp[32] = tile[threadIdx.x + 32][threadIdx.y + 8 * i];
+      dp += static_cast<int64_t>(8) * C;
+    }
+    return;
   }
 #pragma unroll
   for (int r = threadIdx.y; r < kTP; r += 8) {
@@ -109,6 +159,29 @@ pair_to_head_major_16x2_kernel(uint16_t* __restrict__ out, const uint16_t* __res
   if (causal && k0 >= (c0 + kTP - 1) / QH + 256) return;
   const uint16_t* src = in + static_cast<int64_t>(b) * KL * C;
   const int c = c0 + 2 * threadIdx.x;  // this lane's pair of columns
+  if (k0 + kTP <= KL && c0 + kTP <= C) {   // interior tile: no predicates, hoisted bases
+    const uint16_t* sp = src + static_cast<int64_t>(k0 + threadIdx.y) * C + c;
+#pragma unroll
+    for (int i = 0; i < kTP / 8; ++i) {
+      *reinterpret_cast<uint32_t*>(&tile[threadIdx.y + 8 * i][2 * threadIdx.x]) = *reinterpret_cast<const uint32_t*>(sp);
+      sp += static_cast<int64_t>(8) * C;
+    }
+    __syncthreads();
+    int cc = c0 + threadIdx.y;
+    int q = cc / QH, h = cc - q * QH;
+    const int dq8 = 8 / QH, dh8 = 8 - dq8 * QH;
+    uint16_t* dst_b = out + static_cast<int64_t>(b) * QH * QL * KLp + k0 + 2 * threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < kTP / 8; ++i) {
+      const int r = threadIdx.y + 8 * i;
+      const uint32_t v = static_cast<uint32_t>(tile[2 * threadIdx.x][r]) |
+                         (static_cast<uint32_t>(tile[2 * threadIdx.x + 1][r]) << 16);
+      *reinterpret_cast<uint32_t*>(dst_b + (static_cast<int64_t>(h) * QL + q) * KLp) = v;
+      q += dq8; h += dh8;
+      if (h >= QH) { h -= QH; ++q; }
+    }
+    return;
+  }
 #pragma unroll
   for (int r = threadIdx.y; r < kTP; r += 8) {
     const int k = k0 + r;
@@ -143,6 +216,33 @@ dpair_from_head_major_16x2_kernel(uint16_t* __restrict__ out, const uint16_t* __
   if (kpad) {
     keep0 = keep0 && kpad[static_cast<int64_t>(b) * KL + k] != 0;
     keep1 = keep1 && kpad[static_cast<int64_t>(b) * KL + k + 1] != 0;
+  }
+  if (k0 + kTP <= KL && c0 + kTP <= C && (!causal || k0 + kTP - 1 <= c0 / QH)) {
+    // interior tile fully below the diagonal: only the key padding mask can kill an entry
+    const uint32_t keepm = (keep0 ? 0x0000ffffu : 0u) | (keep1 ? 0xffff0000u : 0u);
+    int cc = c0 + threadIdx.y;
+    int q = cc / QH, h = cc - q * QH;
+    const int dq8 = 8 / QH, dh8 = 8 - dq8 * QH;
+    const uint16_t* src_b = in + static_cast<int64_t>(b) * QH * QL * KLp + k;
+#pragma unroll
+    for (int i = 0; i < kTP / 8; ++i) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(src_b + (static_cast<int64_t>(h) * QL + q) * KLp);
+      *reinterpret_cast<uint32_t*>(&tile[threadIdx.y + 8 * i][2 * threadIdx.x]) = v & keepm;
+      q += dq8; h += dh8;
+      if (h >= QH) { h -= QH; ++q; }
+    }
+    __syncthreads();
+    uint16_t* dp = out + static_cast<int64_t>(b) * KL * C + static_cast<int64_t>(k0 + threadIdx.y) * C + c0 +
+                   2 * threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < kTP / 8; ++i) {
+      const int r = threadIdx.y + 8 * i;
+      const uint32_t v = static_cast<uint32_t>(tile[2 * threadIdx.x][r]) |
+                         (static_cast<uint32_t>(tile[2 * threadIdx.x + 1][r]) << 16);
+      *reinterpret_cast<uint32_t*>(dp) = v;
+      dp += static_cast<int64_t>(8) * C;
+    }
+    return;
   }
 #pragma unroll
   for (int r = threadIdx.y; r < kTP; r += 8) {
