@@ -78,7 +78,9 @@ int nnop_set_bwd_pair_mode(int mode);
  * QL <= 2048) run the persistent kernel (one CTA per SM, dynamic tile queue, Q / K / V of the next
  * tile loaded under the current one, O stored through private staging); 1: always one CTA per q
  * tile; 2: persistent wherever eligible; 100+n: persistent on n CTAs (tests).  O and lse are
- * bit-identical across modes. */
+ * bit-identical across modes.  The persistent forward keeps its tile counter in one of 256 library-owned
+ * device slots, taken round-robin and zeroed on the call's stream: calls on one stream never share a
+ * live slot; do not replay one captured CUDA graph containing it on several streams at once. */
 int nnop_set_fwd_mode(int mode);
 
 /* ---------------------------------------------------------------------------------------

@@ -1896,12 +1896,7 @@ int launch_bwd(const AttnParams& a) {
   const int nq_blocks = (a.QL + 127) / 128;
   // packed: the exact tile count is only known on the device; this is its upper bound
   const int64_t n_tiles = packed ? (a.total_k / 128 + a.nseq) * a.KH : static_cast<int64_t>(nkv) * a.KH * a.B;
-  int num_sms = 148;
-  {
-    int dev = 0;
-    NNOP_CUDA_CHECK(cudaGetDevice(&dev));
-    NNOP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = sm_count();
   const bool persist_ok = !bias && a.kpad == nullptr && (packed || !a.causal || nq_blocks >= nkv) &&
                           n_tiles < (1LL << 30);
   const bool use_persist = !use_pair && persist_ok &&
