@@ -231,19 +231,10 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
         }
         commit(do_empty);
-        // dQ' = (dSh + dSl) [Kh | Kl]   (A: dS^T tiles viewed MN-major; B: K' MN-major, N = 128)
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            umma_ss_lo(tm + kColDP, m_lo, (S::kdSh + ks * 2048) >> 4, m_hi, m_lo, (S::kK + ks * 2048) >> 4, m_hi,
-                       id_mm, ks > 0 ? 1u : 0u);
-            umma_ss_lo(tm + kColDP, m_lo, (S::kdSl + ks * 2048) >> 4, m_hi, m_lo, (S::kK + ks * 2048) >> 4, m_hi,
-                       id_mm, 1u);
-          }
-        }
-        commit(dq_full);
+        // dK' first: Q' is single-buffered here, so its reload (and with it S^T(i+1)) can only start when
+        // dK' has read it -- issued before dQ', the load runs under the dQ' MMAs instead of after them
         // dK' += (dSh + dSl)^T [Qh | Ql]   (A: dS^T K-major; B: Q' MN-major, N = 128)
         if (elect_one()) {
 #pragma unroll
@@ -255,6 +246,17 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
         }
         commit(q_empty);
+        // dQ' = (dSh + dSl) [Kh | Kl]   (A: dS^T tiles viewed MN-major; B: K' MN-major, N = 128)
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            umma_ss_lo(tm + kColDP, m_lo, (S::kdSh + ks * 2048) >> 4, m_hi, m_lo, (S::kK + ks * 2048) >> 4, m_hi,
+                       id_mm, ks > 0 ? 1u : 0u);
+            umma_ss_lo(tm + kColDP, m_lo, (S::kdSl + ks * 2048) >> 4, m_hi, m_lo, (S::kK + ks * 2048) >> 4, m_hi,
+                       id_mm, 1u);
+          }
+        }
+        commit(dq_full);
         if ((it + 1) % kFlushEvery == 0 && it + 1 < n_it) {
           commit(flush_full);
           ++nflush;
