@@ -41,8 +41,9 @@ function pair_workspace(base, ::Type{T}, QL, KL, QH, B, backward::Bool) where T
     return Csize_t((base + 255) & ~Csize_t(255)) + extra
 end
 
-# _flash_attention: src/attention.jl:133-177.  Residuals: (o, lse, nothing) -- one Float32
-# log-sum-exp replaces the reference's (ms, ls); they are private to the rrule closure.
+# _flash_attention: src/attention.jl:133-177.  Residuals: (o, lse, ls) -- one Float32 log-sum-exp
+# replaces the reference's `ms`; the `ls` slot is `nothing`, or with a pair bias the forward workspace
+# holding the head-major copy of `pair`.  They are private to the rrule closure.
 function _flash_attention(
     q::CuArray{T,4}, k::CuArray{T,4}, v::CuArray{T,4},
     pair::Maybe{CuArray{T,4}} = nothing;
@@ -77,7 +78,7 @@ function _flash_attention(
     return o, lse, (ws, Int((base + 255) & ~Csize_t(255)))
 end
 
-# ∇flash_attention: src/attention_bwd.jl:199-275 (`ms` carries lse, `ls` is unused)
+# ∇flash_attention: src/attention_bwd.jl:199-275 (`ms` carries lse, `ls` the forward's pair copy or nothing)
 function ∇flash_attention(
     Δ::CuArray{T,4}, o::CuArray{T,4}, ms, ls,
     q::CuArray{T,4}, k::CuArray{T,4}, v::CuArray{T,4},
