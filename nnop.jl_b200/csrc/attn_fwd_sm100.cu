@@ -753,7 +753,9 @@ struct FwdPersistSmem {
   };
   static constexpr int kTileRing = kBarOff + kNumBars * 8;   // [2][4] ints
   static constexpr int kTmemSlot = kTileRing + 32;
-  static constexpr int kTotal = kTmemSlot + 16;
+  static constexpr int kSeqChunks = 128;                     // packed mode: coarse prefix of q tiles
+  static constexpr int kSeqPre = kTmemSlot + 16;             // [kSeqChunks + 1] ints
+  static constexpr int kTotal = kSeqPre + (kSeqChunks + 1) * 4 + 12;
   static constexpr int kDynBytes = kTotal + 1024;
 };
 
@@ -776,9 +778,28 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
   volatile int* s_tile = reinterpret_cast<volatile int*>(smem + S::kTileRing);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
 
+  int* s_pre = reinterpret_cast<int*>(smem + S::kSeqPre);
+
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int QL = p.QL, KL = p.KL;
+  const bool packed = p.cu_q != nullptr;
+  // packed batches: q tiles per sequence, summed per chunk of sequences (exclusive prefix in s_pre)
+  const int seq_per = packed ? (p.nseq + S::kSeqChunks - 1) / S::kSeqChunks : 0;
+  auto tiles_of = [&](int z) { return (p.cu_q[z + 1] - p.cu_q[z] + 255) >> 8; };
+  if (packed) {
+    if (threadIdx.x < S::kSeqChunks) {
+      const int z0 = min(p.nseq, static_cast<int>(threadIdx.x) * seq_per), z1 = min(p.nseq, z0 + seq_per);
+      int cnt = 0;
+      for (int z = z0; z < z1; ++z) cnt += tiles_of(z);
+      s_pre[threadIdx.x + 1] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_pre[0] = 0;
+      for (int c = 0; c < S::kSeqChunks; ++c) s_pre[c + 1] += s_pre[c];
+    }
+    // (made visible to everyone by the __syncthreads after the barrier setup below)
+  }
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_q);
@@ -802,16 +823,27 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
 
   // work tile geometry, derived from a ring record by every role the same way
   struct Tile {
-    int bh_q, bh_kv, q0, act1, nb0, nb1, nblk;
+    int bh_q, bh_kv, q0, act1, nb0, nb1, nblk, QL, KL, q_off, k_off;
   };
-  auto make_tile = [&](int b, int h, int qt) -> Tile {
+  // zb = batch element (dense) or sequence (packed)
+  auto make_tile = [&](int zb, int h, int qt) -> Tile {
     Tile t;
     t.q0 = qt * 256;
-    t.bh_q = b * p.QH + h;
-    t.bh_kv = b * p.KH + h / (p.QH / p.KH);
-    t.act1 = t.q0 + 128 < QL;
-    t.nb0 = ((p.causal ? min(KL, t.q0 + 128) : KL) + 127) >> 7;
-    t.nb1 = t.act1 ? (((p.causal ? min(KL, t.q0 + 256) : KL) + 127) >> 7) : 0;
+    if (packed) {
+      t.q_off = p.cu_q[zb];
+      t.QL = p.cu_q[zb + 1] - t.q_off;
+      t.k_off = p.cu_k[zb];
+      t.KL = p.cu_k[zb + 1] - t.k_off;
+      t.bh_q = h;
+      t.bh_kv = h / (p.QH / p.KH);
+    } else {
+      t.q_off = 0; t.k_off = 0; t.QL = p.QL; t.KL = p.KL;
+      t.bh_q = zb * p.QH + h;
+      t.bh_kv = zb * p.KH + h / (p.QH / p.KH);
+    }
+    t.act1 = t.q0 + 128 < t.QL;
+    t.nb0 = ((p.causal ? min(t.KL, t.q0 + 128) : t.KL) + 127) >> 7;
+    t.nb1 = t.act1 ? (((p.causal ? min(t.KL, t.q0 + 256) : t.KL) + 127) >> 7) : 0;
     t.nblk = t.act1 ? t.nb1 : t.nb0;
     return t;
   };
@@ -831,22 +863,60 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
     setmaxnreg_dec<80>();
     if (warp == 3) {
       // ================================ tile scheduler ===============================
-      if (lane == 0) {
-        for (int n = 0;; ++n) {
-          const int slot = n & 1;
-          if (n > 0) mbar_wait(bars + S::kSchedGo, (n - 1) & 1);   // claim late (see the backward)
-          mbar_wait(bars + S::kTileEmpty + slot, ((n >> 1) & 1) ^ 1);
-          const int t = atomicAdd(tile_counter, 1);
-          const bool ok = t < n_tiles;
-          const int bh = ok ? t / nqt : 0;
-          const int r = ok ? t % nqt : 0;
-          s_tile[4 * slot] = bh / p.QH;                       // batch element
-          s_tile[4 * slot + 1] = bh % p.QH;                   // q head
-          s_tile[4 * slot + 2] = p.causal ? nqt - 1 - r : r;  // heaviest q tile of a head first
-          s_tile[4 * slot + 3] = ok ? 1 : -1;
-          mbar_arrive(bars + S::kTileFull + slot);
-          if (!ok) break;
+      // Dense: tile t = (batch * QH + head) * nqt + r.  Packed: sequences in order, within a sequence
+      // head-major with the q tiles of a head adjacent; the sequence is found in the coarse prefix, then
+      // by a walk over its chunk.  The whole warp runs this (uniformly); lane 0 claims and publishes.
+      const int total = packed ? s_pre[S::kSeqChunks] * p.QH : n_tiles;
+      for (int n = 0;; ++n) {
+        const int slot = n & 1;
+        if (n > 0) mbar_wait(bars + S::kSchedGo, (n - 1) & 1);   // claim late (see the backward)
+        mbar_wait(bars + S::kTileEmpty + slot, ((n >> 1) & 1) ^ 1);
+        int zb = 0, h = 0, qt = 0, flag = -1;
+        for (;;) {
+          int t = 0;
+          if (lane == 0) t = atomicAdd(tile_counter, 1);
+          t = __shfl_sync(0xffffffffu, t, 0);
+          if (t >= total) break;
+          int nq_z = nqt, r;
+          if (packed) {
+            // t = QH * (tiles before sequence z) + h * nq_z + r  ->  find z with QH * pre_z <= t
+            int c = 0;
+            while (c + 1 < S::kSeqChunks && s_pre[c + 1] * p.QH <= t) ++c;
+            int z = c * seq_per, run = s_pre[c];
+            nq_z = tiles_of(z);
+            while ((run + nq_z) * p.QH <= t) {
+              run += nq_z;
+              nq_z = tiles_of(++z);
+            }
+            const int tl = t - run * p.QH;
+            zb = z;
+            h = tl / nq_z;
+            r = tl - h * nq_z;
+          } else {
+            const int bh = t / nqt;
+            r = t - bh * nqt;
+            zb = bh / p.QH;
+            h = bh - zb * p.QH;
+          }
+          qt = p.causal ? nq_z - 1 - r : r;   // heaviest q tile of a head first
+          const Tile ti = make_tile(zb, h, qt);
+          if (ti.nb0 > 0) { flag = 1; break; }
+          // a packed sequence without keys: its output rows are 0 and lse = -inf (written here with plain
+          // stores; the tile is not published)
+          {
+            const int rows = min(256, ti.QL - ti.q0);
+            constexpr int kCPR = D / 8;
+            const int64_t row0 = static_cast<int64_t>(h) * p.total_q + ti.q_off + ti.q0;
+            for (int idx = lane; idx < rows * kCPR; idx += 32)
+              reinterpret_cast<uint4*>(static_cast<T*>(p.o_ptr) + row0 * D)[idx] = make_uint4(0u, 0u, 0u, 0u);
+            for (int idx = lane; idx < rows; idx += 32) p.lse[row0 + idx] = -INFINITY;
+          }
         }
+        if (lane == 0) {
+          s_tile[4 * slot] = zb; s_tile[4 * slot + 1] = h; s_tile[4 * slot + 2] = qt; s_tile[4 * slot + 3] = flag;
+          mbar_arrive(bars + S::kTileFull + slot);
+        }
+        if (flag < 0) break;
       }
     } else if (warp == 0) {
       // ================================ TMA producer =================================
@@ -867,7 +937,7 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
 #pragma unroll
             for (int bx = 0; bx < S::kNBox; ++bx)
               tma_load_3d(sQ + t * S::kTileBytes + bx * S::kBoxBytes, &tm_q, bars + S::kQFull + t, bx * 64,
-                          ti.q0 + t * 128, ti.bh_q);
+                          ti.q_off + ti.q0 + t * 128, ti.bh_q);
             ++cq[t];
           };
           auto load_kv = [&](const CUtensorMap* tm, int blk) {
@@ -878,7 +948,7 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
 #pragma unroll
             for (int bx = 0; bx < S::kNBox; ++bx)
               tma_load_3d(sKV + st * S::kTileBytes + bx * S::kBoxBytes, tm, bars + S::kKVFull + st, bx * 64,
-                          blk * 128, ti.bh_kv);
+                          ti.k_off + blk * 128, ti.bh_kv);
             ++n;
           };
           const int go_at = ti.nblk > 2 ? ti.nblk - 2 : 0;  // block whose loads trigger the next claim
@@ -1005,6 +1075,7 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
       const int nbt = t ? ti.nb1 : ti.nb0;
       if (nbt == 0) continue;   // this tile has no second half
       const int q0 = ti.q0;
+      const int QL = ti.QL, KL = ti.KL;
       const int q_row = q0 + t * 128 + row;
       float m_used = -1e30f;
       float l = 0.f;
@@ -1122,15 +1193,33 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
             const int cin = c * 4 + u;  // 16-byte chunk within the 128-byte box row
             *reinterpret_cast<uint4*>(stage + row * 128 + ((cin ^ (row & 7)) << 4)) = v;
           }
-        fence_proxy_async_smem();
-        named_bar_sync(1 + t, 128);
-        if (wq == 0 && lane == 0) {
-          tma_store_3d(&tm_o, stage, bx * 64, q0 + t * 128, ti.bh_q);
-          bulk_commit();
+        const int rows_left = QL - (q0 + t * 128);  // > 0 here
+        if (packed && rows_left < 128) {
+          // last, partial tile of a packed sequence: rows past its end belong to the next sequence, so
+          // copy the valid rows of this box with 16-byte stores (the barrier that opens the next use of
+          // the staging box also closes these reads)
+          named_bar_sync(1 + t, 128);
+          T* obase = static_cast<T*>(p.o_ptr) +
+                     (static_cast<int64_t>(ti.bh_q) * p.total_q + ti.q_off + q0 + t * 128) * D + bx * 64;
+          for (int idx = row; idx < rows_left * 8; idx += 128) {
+            const int r2 = idx >> 3, cin = idx & 7;
+            const uint4 v = *reinterpret_cast<const uint4*>(stage + r2 * 128 + ((cin ^ (r2 & 7)) << 4));
+            *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(r2) * D + cin * 8) = v;
+          }
+        } else {
+          fence_proxy_async_smem();
+          named_bar_sync(1 + t, 128);
+          if (wq == 0 && lane == 0) {
+            tma_store_3d(&tm_o, stage, bx * 64, ti.q_off + q0 + t * 128, ti.bh_q);
+            bulk_commit();
+          }
         }
       }
-      if (q_row < QL)
-        p.lse[static_cast<int64_t>(ti.bh_q) * QL + q_row] = l > 0.f ? (m_used + fast_log2(l)) * kLn2 : -INFINITY;
+      if (q_row < QL) {
+        const int64_t li = packed ? static_cast<int64_t>(ti.bh_q) * p.total_q + ti.q_off + q_row
+                                  : static_cast<int64_t>(ti.bh_q) * QL + q_row;
+        p.lse[li] = l > 0.f ? (m_used + fast_log2(l)) * kLn2 : -INFINITY;
+      }
     }
     if (wq == 0 && lane == 0) bulk_wait<0>();
   }
@@ -1264,24 +1353,30 @@ template <typename T, int D>
 int launch_fwd_persist(const AttnParams& a, int ctas) {
   using S = FwdPersistSmem<D>;
   alignas(64) CUtensorMap tq, tk, tv, to;
-  const uint64_t bhq = static_cast<uint64_t>(a.B) * a.QH, bhk = static_cast<uint64_t>(a.B) * a.KH;
-  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, D, a.QL, bhq, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, a.KL, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&to, a.o, a.dtype, D, a.QL, bhq, 64, 128)) return rc;
+  const bool packed = a.cu_q != nullptr;
+  const uint64_t bhq = packed ? a.QH : static_cast<uint64_t>(a.B) * a.QH;
+  const uint64_t bhk = packed ? a.KH : static_cast<uint64_t>(a.B) * a.KH;
+  const uint64_t rows_q = packed ? static_cast<uint64_t>(a.total_q) : a.QL;
+  const uint64_t rows_k = packed ? static_cast<uint64_t>(a.total_k) : a.KL;
+  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&to, a.o, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
   auto kern = attn_fwd_sm100_persist_kernel<T, D>;
   NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynBytes));
   FwdParams fp;
   fp.lse = a.lse;
   fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
   fp.scale_log2 = a.scale * kLog2e;
-  fp.cu_q = nullptr; fp.cu_k = nullptr; fp.o_ptr = a.o; fp.total_q = 0; fp.kpad = nullptr; fp.nseq = 0;
+  fp.cu_q = a.cu_q; fp.cu_k = a.cu_k; fp.o_ptr = a.o; fp.total_q = a.total_q; fp.kpad = nullptr;
+  fp.nseq = a.nseq;
   int* counters = nullptr;
   NNOP_CUDA_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&counters), g_fwd_tile_counters));
   int* counter = counters + (g_fwd_slot.fetch_add(1) & 255u);
   NNOP_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), a.stream));
   const int nqt = (a.QL + 255) / 256;
-  const int64_t n_tiles = static_cast<int64_t>(nqt) * a.QH * a.B;
+  // packed: the exact tile count is only known on the device; this is its upper bound (for the grid)
+  const int64_t n_tiles = packed ? (a.total_q / 256 + a.nseq) * a.QH : static_cast<int64_t>(nqt) * a.QH * a.B;
   const int grid = static_cast<int>(n_tiles < ctas ? n_tiles : ctas);
   timing_begin(0, a.stream);
   kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, fp, counter, static_cast<int>(n_tiles), nqt);
@@ -1338,8 +1433,10 @@ int attn_sm100_fwd(const AttnParams& a) {
   // forward variant (nnop_set_fwd_mode / NNOP_FWD_MODE): 0 automatic, 1 one CTA per q tile, 2 persistent,
   // 100+n persistent on n CTAs
   const int mode = fwd_mode();
-  const int64_t n_tiles = static_cast<int64_t>((a.QL + 255) / 256) * a.QH * a.B;
-  const bool persist_ok = a.cu_q == nullptr && a.kpad == nullptr && a.KL >= 1 && n_tiles < (1LL << 30);
+  const bool packed = a.cu_q != nullptr;
+  const int64_t n_tiles = packed ? (a.total_q / 256 + a.nseq) * a.QH
+                                 : static_cast<int64_t>((a.QL + 255) / 256) * a.QH * a.B;
+  const bool persist_ok = a.kpad == nullptr && (packed || a.KL >= 1) && n_tiles < (1LL << 30);
   // automatic choice, from measurement (profiles/r01d_perf_fwd_modes.txt): the persistent kernel wins
   // where the per-tile fixed cost matters -- E = 64 (+15 %) and short sequences (L = 2 048: +6 %) --
   // and is neutral (bench.py regime) to slower (back-to-back launches) on long E = 128 tiles

@@ -23,6 +23,13 @@ def timeit(fn, n=10):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
 o, lse = nn._flash_attention_varlen(q, k, v, cu, cu, mx, mx, causal=True)
+tfs = {}
+for mode in (1, 2, 1, 2):   # forward variants: one CTA per q tile / persistent, alternating
+    nn.set_fwd_mode(mode)
+    t_ = timeit(lambda: nn._flash_attention_varlen(q, k, v, cu, cu, mx, mx, causal=True))
+    tfs[mode] = min(tfs.get(mode, 1e9), t_)
+nn.set_fwd_mode(0)
+print("forward: " + "  ".join(f"mode {m}: {t:.3f} ms {f/t/1e9:.0f} TF/s" for m, t in tfs.items()), flush=True)
 tf = timeit(lambda: nn._flash_attention_varlen(q, k, v, cu, cu, mx, mx, causal=True))
 tbs = {}
 for mode in (2, 3, 2, 3):   # backward variants: one CTA per tile / persistent, alternating

@@ -202,3 +202,33 @@ def test_varlen_many_short_sequences(nnop):
             _check(nnop, lens, lens, 4, 2, 64, torch.bfloat16, True, seed=9)
     finally:
         nnop.set_bwd_pair_mode(0)
+
+
+@pytest.mark.parametrize("mode", [2, 101, 103])
+def test_varlen_persistent_forward(nnop, mode):
+    """The persistent forward on packed batches (sequence found in a per-CTA coarse tile prefix, partial
+    last tiles stored row by row, key-less sequences zero-filled by the scheduler warp): O and lse bit
+    for bit against the one-CTA-per-tile kernel, which the other tests of this file pin to the oracle."""
+    import random
+    rng = random.Random(3)
+    cases = [([255, 1, 128, 513, 256, 129, 64, 511], None, 4, 4, 128, True),
+             ([255, 1, 128, 513, 256, 129, 64, 511], None, 4, 4, 64, False),
+             ([300, 77, 1024, 5], None, 8, 2, 128, True),
+             ([100, 257, 31], [513, 64, 200], 2, 2, 128, False),
+             ([130, 0, 64, 0], None, 2, 1, 64, True),
+             ([40, 200], [0, 200], 2, 2, 128, False),
+             ([rng.choice([0, 1, 7, 40, 128, 129, 200, 300, 600]) for _ in range(300)], None, 2, 2, 64, True)]
+    try:
+        for lens_q, lens_k, QH, KH, E, causal in cases:
+            lens_k = lens_k or lens_q
+            q, k, v, dO, cu_q, cu_k = (t.cuda() for t in _packed(lens_q, lens_k, QH, KH, E, torch.bfloat16, 13))
+            mq, mk = max(lens_q), max(lens_k)
+            nnop.set_fwd_mode(1)
+            o_ref, lse_ref = nnop._flash_attention_varlen(q, k, v, cu_q, cu_k, mq, mk, causal=causal)
+            nnop.set_fwd_mode(mode)
+            for _ in range(2):
+                o, lse = nnop._flash_attention_varlen(q, k, v, cu_q, cu_k, mq, mk, causal=causal)
+                assert torch.equal(o, o_ref), (lens_q[:8], lens_k[:8], E, causal)
+                assert torch.equal(lse, lse_ref), (lens_q[:8], lens_k[:8], E, causal)
+    finally:
+        nnop.set_fwd_mode(0)
