@@ -84,6 +84,9 @@ struct BwdParams {
   // sequences before z (nseq + 1 entries, built by packed_tile_prefix_kernel)
   const int* tile_pre;
   int nseq;
+  // persistent kernel, dense causal mode: (batch, kv head) units are walked in groups of `lpt_group`
+  // whose Q / dO streams fit in L2 together, each group heaviest kv block first (0 = unit by unit)
+  int lpt_group;
   // additive bias (dense mode, BIAS kernels): head-major copies (B, QH, QL, KLp), see attn_pair.cu
   const void* pair_t;
   void* dpair_t;
@@ -768,6 +771,18 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
             const int nkv_z = (p.tile_pre[zb + 1] - p.tile_pre[zb]) / p.KH;
             hk = tl / nkv_z;
             j = tl - hk * nkv_z;
+          } else if (p.lpt_group > 1) {
+            // unit by unit, the last unit's heaviest tile is claimed when the queue is ~99 % drained and
+            // then runs alone; group-wise heaviest-first leaves only light tiles for the end
+            const int nbh = n_tiles / nkv;
+            const int per = p.lpt_group * nkv;
+            const int g0 = (t / per) * p.lpt_group;
+            const int gsz = min(p.lpt_group, nbh - g0);
+            const int idx = t - (t / per) * per;
+            j = idx / gsz;
+            const int u = g0 + idx - j * gsz;
+            hk = u % p.KH;
+            zb = u / p.KH;
           } else {
             j = t % nkv;
             const int u = t / nkv;
@@ -1883,6 +1898,18 @@ int launch_bwd(const AttnParams& a) {
   bp.kpad = packed ? nullptr : a.kpad;
   bp.pair_t = a.pair_t; bp.dpair_t = a.dpair_t; bp.KLp = a.KLp;
   bp.tile_pre = tile_pre; bp.nseq = a.nseq;
+  bp.lpt_group = 0;
+  if (!packed && a.causal) {
+    // a few (batch, kv head) units at a time: their Q + dO streams (all q heads of the group) must share
+    // L2 with the dQ accumulator traffic.  Measured on C2 / C3 (profiles/r01e_perf_lpt_order.txt): 4 units
+    // +1.5 % / +5.4 %, 12 units 0 / +3.7 %, 32 units -2.7 % / -1 % against unit-by-unit order.
+    const double qdo_bytes = 2.0 * a.QL * D * sizeof(T) * (static_cast<double>(a.QH) / a.KH);
+    const int env = getenv("NNOP_BWD_LPT_GROUP") ? atoi(getenv("NNOP_BWD_LPT_GROUP")) : -1;
+    int grp = static_cast<int>(16.0 * 1024 * 1024 / (qdo_bytes > 1 ? qdo_bytes : 1));
+    grp = grp < 4 ? 4 : (grp > 16 ? 16 : grp);
+    bp.lpt_group = env >= 0 ? env : grp;
+    if (bp.lpt_group > a.KH * a.B) bp.lpt_group = a.KH * a.B;
+  }
   const bool bias = a.pair != nullptr;
   if (bias && !a.pair_t_ready)
     if (int rc = attn_pair_to_head_major(a)) return rc;

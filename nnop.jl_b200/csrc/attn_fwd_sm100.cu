@@ -72,6 +72,9 @@ struct FwdParams {
   int64_t total_q;
   const uint8_t* kpad;  // (B, KL) key padding mask, 1 = attend, or nullptr (dense mode only)
   int nseq;             // packed mode: number of sequences
+  // dense causal mode, one CTA per q tile: heads are walked in groups of `lpt_group` (batch, head) pairs
+  // whose K / V fit in L2 together; inside a group all heaviest q tiles come first.  0 = head by head.
+  int lpt_group;
 };
 
 // NS = stages of the K/V ring; BIASB = bytes of additive-bias staging (pair: 4 x 16 KB, ring of 3)
@@ -141,8 +144,25 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   // ---- work assignment ----------------------------------------------------------------
   const bool packed = p.cu_q != nullptr;
   int qt = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heaviest first
-  const int h = blockIdx.y;
+  int h = blockIdx.y;
   int QL = p.QL, KL = p.KL, q_off = 0, k_off = 0, b = blockIdx.z;
+  if (!packed && p.lpt_group > 1) {
+    // Blocks are dispatched in linear order (x fastest).  Head by head, the last head's heaviest tile
+    // starts when the grid is ~99 % dispatched and runs alone for its whole length; walking the heads
+    // in groups and dispatching each group heaviest-tile-first leaves only light tiles for the end,
+    // while a group's K / V still share L2.
+    const int nqt = gridDim.x, nbh = gridDim.y * gridDim.z;
+    const int lin = blockIdx.x + nqt * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int per = p.lpt_group * nqt;
+    const int g0 = (lin / per) * p.lpt_group;          // first (batch, head) pair of this group
+    const int gsz = min(p.lpt_group, nbh - g0);        // the last group may be smaller
+    const int idx = lin - (lin / per) * per;
+    const int r = idx / gsz, u = idx - r * gsz;
+    const int bh = g0 + u;
+    qt = p.causal ? nqt - 1 - r : r;
+    h = bh % gridDim.y;
+    b = bh / gridDim.y;
+  }
   if (packed) {
     // The grid has one CTA per 256-row q tile of the packed batch (upper bound total_q / 256 + nseq,
     // no CTAs for tiles a shorter sequence does not have).  Tile e = blockIdx.x belongs to the
@@ -1289,6 +1309,7 @@ int launch_fwd_f32(const AttnParams& a) {
   fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
   fp.scale_log2 = a.scale * kLog2e;
   fp.cu_q = nullptr; fp.cu_k = nullptr; fp.o_ptr = a.o; fp.total_q = 0; fp.nseq = 0;
+  fp.lpt_group = 0;
   fp.kpad = a.kpad;
   dim3 grid((a.QL + 255) / 256, a.QH, a.B);
   timing_begin(0, a.stream);
@@ -1324,6 +1345,14 @@ int launch_fwd(const AttnParams& a) {
   fp.cu_q = a.cu_q; fp.cu_k = a.cu_k; fp.o_ptr = a.o; fp.total_q = a.total_q;
   fp.kpad = packed ? nullptr : a.kpad;
   fp.nseq = a.nseq;
+  fp.lpt_group = 0;
+  if (!packed && a.causal) {
+    // (batch, head) pairs whose K + V stay under ~48 MB of L2 together; GQA heads share theirs
+    const double kv_bytes = 2.0 * a.KL * D * sizeof(T) * (static_cast<double>(a.KH) / a.QH);
+    const int env = getenv("NNOP_FWD_LPT_GROUP") ? atoi(getenv("NNOP_FWD_LPT_GROUP")) : -1;
+    fp.lpt_group = env >= 0 ? env : static_cast<int>(48.0 * 1024 * 1024 / (kv_bytes > 1 ? kv_bytes : 1));
+    if (fp.lpt_group > a.QH * a.B) fp.lpt_group = a.QH * a.B;
+  }
   dim3 grid(packed ? static_cast<unsigned>(a.total_q / 256 + a.nseq) : (a.QL + 255) / 256, a.QH, packed ? 1 : a.B);
   timing_begin(0, a.stream);
   kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, tb, fp);
@@ -1370,6 +1399,7 @@ int launch_fwd_persist(const AttnParams& a, int ctas) {
   fp.scale_log2 = a.scale * kLog2e;
   fp.cu_q = a.cu_q; fp.cu_k = a.cu_k; fp.o_ptr = a.o; fp.total_q = a.total_q; fp.kpad = nullptr;
   fp.nseq = a.nseq;
+  fp.lpt_group = 0;
   int* counters = nullptr;
   NNOP_CUDA_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&counters), g_fwd_tile_counters));
   int* counter = counters + (g_fwd_slot.fetch_add(1) & 255u);
