@@ -345,4 +345,11 @@ function CRC.rrule(::typeof(llama_rope), q, k; cos, sin)                   # :94
     return (qr, kr), _pullback
 end
 
+# ------------------------------------------------------------------ diagnostics
+# kernel-variant switches of the tcgen05 attention path (process-wide; see include/nnop_b200.h)
+set_attention_path(mode::Integer) = check(ccall((:nnop_set_attention_path, libnnop_b200), Cint, (Cint,), mode))
+last_attention_path() = ccall((:nnop_last_attention_path, libnnop_b200), Cint, ())
+set_fwd_mode(mode::Integer) = check(ccall((:nnop_set_fwd_mode, libnnop_b200), Cint, (Cint,), mode))
+set_bwd_mode(mode::Integer) = check(ccall((:nnop_set_bwd_pair_mode, libnnop_b200), Cint, (Cint,), mode))
+
 end # module

@@ -76,3 +76,19 @@ def test_two_rank_gloo_shards_reproduce_full_result(tmp_path):
     assert torch.equal(torch.cat([p["dq"] for p in parts]), dq)
     assert torch.equal(torch.cat([p["dk"] for p in parts]), dk)
     assert torch.equal(torch.cat([p["dv"] for p in parts]), dv)
+
+
+def test_bench_pinned_buffer_affinity_helper_restores_affinity():
+    """bench.py allocates its pinned host buffers from the CPUs NVML reports as local to the GPU; whatever
+    NVML says (here: no driver at all), the helper must leave the process affinity as it found it."""
+    import importlib.util
+    import os
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    before = os.sched_getaffinity(0)
+    with bench.gpu_local_cpus(0) as note:
+        assert isinstance(note[0], str) and note[0]
+        assert os.sched_getaffinity(0) <= before
+    assert os.sched_getaffinity(0) == before
