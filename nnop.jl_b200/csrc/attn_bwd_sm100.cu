@@ -900,7 +900,8 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
       for (int tl = 0;; ++tl) {
         Tile ti;
         if (!next_tile(tl, ti)) break;
-        const int j = ti.j, n_it = ti.n_it;
+        [[maybe_unused]] const int j = ti.j;  // (trace builds log it)
+        const int n_it = ti.n_it;
         PT_STAMP(0);
         // dP^T(0) = V dO_0^T: its TMEM columns hold the previous tile's last dQ until drained
         mbar_wait(bars + PB::kVFull, tl & 1);
