@@ -183,9 +183,11 @@ int nnop_flash_attn_varlen_bwd(void* dq, void* dk, void* dv, const void* dO, con
  *   nnop_attn_merge: (o_acc, lse_acc) <- logsumexp-weighted combination with (o_part, lse_part);
  *     o_acc (E, rows) float in/out, lse_acc (rows) float in, lse_out (rows) float out (must not
  *     alias lse_acc unless init), o_part (E, rows) T, lse_part (rows) float; init != 0 copies.
- *   nnop_accumulate_f32: acc[n] (+)= float(part[n])  (dq over steps; travelling dk / dv); n % 8 == 0.
+ *   nnop_accumulate_f32: acc[n] (+)= float(part[n])  (dq over steps; travelling dk / dv); n a multiple
+ *     of the elements in a 128-bit vector of `part` (4 for Float32, 8 for 16-bit).
  *   nnop_store_rows_from_f32: out[:, offset : offset+rows, slab] = T(acc[:, :, slab]) for
  *     acc (E, rows, n_slabs) float and out (E, out_slab_rows, n_slabs) T.
+ * E % 8 == 0 and every array pointer 16-byte aligned (128-bit accesses), else NNOP_ERR_SHAPE / _ARG.
  */
 int nnop_attn_merge(float* o_acc, float* lse_acc, float* lse_out, const void* o_part,
                     const float* lse_part, int dtype, int E, int64_t rows, int init, void* stream);

@@ -6,6 +6,8 @@
 //   nnop_store_rows_from_f32 T(acc) into a row window of a (slabs, rows, E) output
 // 128-bit accesses, one thread per 8 (16-bit) or 4 (fp32) elements.
 #include "common.cuh"
+#include <initializer_list>
+
 #include "internal.h"
 
 namespace nnop {
@@ -129,6 +131,13 @@ store_rows_kernel(T* __restrict__ out, const float* __restrict__ acc, int vpr, i
 
 inline unsigned blocks(int64_t n) { return static_cast<unsigned>((n + 255) / 256); }
 
+// every kernel here moves float4 / uint4 vectors: all pointers must be 16-byte aligned
+inline bool aligned16(std::initializer_list<const void*> ps) {
+  uintptr_t x = 0;
+  for (const void* p : ps) x |= reinterpret_cast<uintptr_t>(p);
+  return (x & 15) == 0;
+}
+
 template <typename F>
 int by_dtype(int dtype, F&& f) {
   if (dtype == NNOP_F32) return f(float{});
@@ -149,6 +158,7 @@ extern "C" int nnop_attn_merge(float* o_acc, float* lse_acc, float* lse_out, con
   if (rows == 0) return NNOP_OK;
   if (!o_acc || !lse_acc || !lse_out || !o_part || !lse_part) return fail(NNOP_ERR_ARG, "NULL pointer");
   if (E <= 0 || rows < 0 || E % 8 != 0) return fail(NNOP_ERR_SHAPE, "E must be a positive multiple of 8");
+  if (!aligned16({o_acc, o_part})) return fail(NNOP_ERR_ARG, "o_acc and o_part must be 16-byte aligned");
   if (lse_out == lse_acc && !init)
     return fail(NNOP_ERR_ARG, "lse_out must not alias lse_acc (rows are updated by several threads)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -169,7 +179,10 @@ extern "C" int nnop_accumulate_f32(float* acc, const void* part, int dtype, int6
   clear_error();
   if (n == 0) return NNOP_OK;
   if (!acc || !part) return fail(NNOP_ERR_ARG, "NULL pointer");
-  if (n < 0 || n % 8 != 0) return fail(NNOP_ERR_SHAPE, "element count must be a multiple of 8");
+  const int vec = dtype == NNOP_F32 ? 4 : 8;  // elements per 128-bit vector of `part`
+  if (n < 0 || n % vec != 0)
+    return fail(NNOP_ERR_SHAPE, "element count must be a multiple of %d for this dtype", vec);
+  if (!aligned16({acc, part})) return fail(NNOP_ERR_ARG, "acc and part must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return by_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
@@ -190,6 +203,7 @@ extern "C" int nnop_store_rows_from_f32(void* out, const float* acc, int dtype, 
     return fail(NNOP_ERR_SHAPE, "bad row window: rows=%lld offset=%lld slab rows=%lld",
                 static_cast<long long>(rows), static_cast<long long>(out_row_offset),
                 static_cast<long long>(out_slab_rows));
+  if (!aligned16({out, acc})) return fail(NNOP_ERR_ARG, "out and acc must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return by_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);

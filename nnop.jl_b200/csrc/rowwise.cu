@@ -106,29 +106,61 @@ __device__ __forceinline__ void store_vec<__nv_bfloat16>(__nv_bfloat16* p, const
   *reinterpret_cast<uint4*>(p) = v;
 }
 
-// sum / max over the TPR threads that share a row (TPR == 32: a warp; TPR == 256: the CTA)
+// sum / max over the TPR threads that share a row (TPR == 32: a warp; TPR == 256: the CTA).
+// The block form hops through `red`, a [2][2][8] scratch indexed by a parity the caller flips
+// per reduction: consecutive reductions use different halves, so ONE barrier per reduction is
+// enough (a thread can only overwrite half p again after passing the barrier of the reduction
+// in between, which every thread reaches after it has read half p).  The rows of these kernels
+// are a dependent chain load -> reduce -> normalise -> store with few warps per SM, so each
+// barrier removed is latency off the chain (r01: two barriers per reduction, four per
+// layer-norm row).
+using RedBuf = float[2][2][kThreads / 32];
 template <int TPR>
-__device__ __forceinline__ float row_sum(float v, float* red) {
+__device__ __forceinline__ float row_sum(float v, RedBuf& red, int& parity) {
   v = warp_sum(v);
   if constexpr (TPR == 32) return v;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  float* r = red[parity][0];
+  parity ^= 1;
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
   __syncthreads();
   float t = 0.f;
 #pragma unroll
-  for (int i = 0; i < kThreads / 32; ++i) t += red[i];
+  for (int i = 0; i < kThreads / 32; ++i) t += r[i];
   return t;
 }
+// two sums in one hop (layer-norm backward: mean(w d xh) and mean(w d))
 template <int TPR>
-__device__ __forceinline__ float row_max(float v, float* red) {
+__device__ __forceinline__ void row_sum2(float& a, float& b, RedBuf& red, int& parity) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if constexpr (TPR == 32) return;
+  float(*r)[kThreads / 32] = red[parity];
+  parity ^= 1;
+  if ((threadIdx.x & 31) == 0) {
+    r[0][threadIdx.x >> 5] = a;
+    r[1][threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  float ta = 0.f, tb = 0.f;
+#pragma unroll
+  for (int i = 0; i < kThreads / 32; ++i) {
+    ta += r[0][i];
+    tb += r[1][i];
+  }
+  a = ta;
+  b = tb;
+}
+template <int TPR>
+__device__ __forceinline__ float row_max(float v, RedBuf& red, int& parity) {
   v = warp_max(v);
   if constexpr (TPR == 32) return v;
+  float* r = red[parity][0];
+  parity ^= 1;
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float t = red[0];
+  float t = r[0];
 #pragma unroll
-  for (int i = 1; i < kThreads / 32; ++i) t = fmaxf(t, red[i]);
+  for (int i = 1; i < kThreads / 32; ++i) t = fmaxf(t, r[i]);
   return t;
 }
 
@@ -143,7 +175,8 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
                 int64_t emb, int64_t n, float eps, float offset) {
   constexpr int VE = VecIO<T>::N;
   constexpr int RPB = kThreads / TPR;
-  __shared__ float red[kThreads / 32];
+  __shared__ RedBuf red;
+  int parity = 0;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * RPB + threadIdx.x / TPR;
   if (row >= n) return;  // TPR==256: whole CTA exits together; TPR==32: whole warp
   const int t = threadIdx.x % TPR;
@@ -170,7 +203,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
     for (int i = 0; i < MAXV; ++i)
 #pragma unroll
       for (int j = 0; j < VE; ++j) m = fmaxf(m, xv[i][j]);
-    m = row_max<TPR>(m, red);
+    m = row_max<TPR>(m, red, parity);
     const float ml2 = (m == -INFINITY) ? 0.f : m * 1.4426950408889634f;
     float s = 0.f;
 #pragma unroll
@@ -180,7 +213,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
         xv[i][j] = fast_exp2(fmaf(xv[i][j], 1.4426950408889634f, -ml2));
         s += xv[i][j];
       }
-    s = row_sum<TPR>(s, red);
+    s = row_sum<TPR>(s, red, parity);
     const float inv = 1.f / s;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
@@ -197,7 +230,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
     for (int i = 0; i < MAXV; ++i)
 #pragma unroll
       for (int j = 0; j < VE; ++j) ss = fmaf(xv[i][j], xv[i][j], ss);
-    ss = row_sum<TPR>(ss, red);
+    ss = row_sum<TPR>(ss, red, parity);
     const float rstd = rsqrtf(ss * inv_n + eps);
     if (t == 0) stat0[row] = rstd;
 #pragma unroll
@@ -217,7 +250,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
     for (int i = 0; i < MAXV; ++i)
 #pragma unroll
       for (int j = 0; j < VE; ++j) s += xv[i][j];
-    s = row_sum<TPR>(s, red);
+    s = row_sum<TPR>(s, red, parity);
     const float mu = s * inv_n;
     float ss = 0.f;
 #pragma unroll
@@ -231,7 +264,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
         }
       }
     }
-    ss = row_sum<TPR>(ss, red);
+    ss = row_sum<TPR>(ss, red, parity);
     const float rstd = rsqrtf(ss * inv_n + eps);
     if (t == 0) {
       stat0[row] = mu;
@@ -258,7 +291,8 @@ __global__ void __launch_bounds__(kThreads)
 rowwise_fwd_generic(T* __restrict__ y, float* __restrict__ stat0, float* __restrict__ stat1,
                     const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b,
                     int64_t emb, int64_t n, float eps, float offset) {
-  __shared__ float red[kThreads / 32];
+  __shared__ RedBuf red;
+  int parity = 0;
   const int64_t row = blockIdx.x;
   const T* xr = x + row * emb;
   T* yr = y + row * emb;
@@ -266,11 +300,11 @@ rowwise_fwd_generic(T* __restrict__ y, float* __restrict__ stat0, float* __restr
   if constexpr (OP == 0) {
     float m = -INFINITY;
     for (int64_t e = threadIdx.x; e < emb; e += kThreads) m = fmaxf(m, to_f32<T>(xr[e]));
-    m = row_max<256>(m, red);
+    m = row_max<256>(m, red, parity);
     if (m == -INFINITY) m = 0.f;
     float s = 0.f;
     for (int64_t e = threadIdx.x; e < emb; e += kThreads) s += __expf(to_f32<T>(xr[e]) - m);
-    s = row_sum<256>(s, red);
+    s = row_sum<256>(s, red, parity);
     const float inv = 1.f / s;
     for (int64_t e = threadIdx.x; e < emb; e += kThreads)
       yr[e] = from_f32<T>(__expf(to_f32<T>(xr[e]) - m) * inv);
@@ -280,7 +314,7 @@ rowwise_fwd_generic(T* __restrict__ y, float* __restrict__ stat0, float* __restr
       const float v = to_f32<T>(xr[e]);
       ss = fmaf(v, v, ss);
     }
-    ss = row_sum<256>(ss, red);
+    ss = row_sum<256>(ss, red, parity);
     const float rstd = rsqrtf(ss * inv_n + eps);
     if (threadIdx.x == 0) stat0[row] = rstd;
     for (int64_t e = threadIdx.x; e < emb; e += kThreads)
@@ -288,14 +322,14 @@ rowwise_fwd_generic(T* __restrict__ y, float* __restrict__ stat0, float* __restr
   } else {
     float s = 0.f;
     for (int64_t e = threadIdx.x; e < emb; e += kThreads) s += to_f32<T>(xr[e]);
-    s = row_sum<256>(s, red);
+    s = row_sum<256>(s, red, parity);
     const float mu = s * inv_n;
     float ss = 0.f;
     for (int64_t e = threadIdx.x; e < emb; e += kThreads) {
       const float d = to_f32<T>(xr[e]) - mu;
       ss = fmaf(d, d, ss);
     }
-    ss = row_sum<256>(ss, red);
+    ss = row_sum<256>(ss, red, parity);
     const float rstd = rsqrtf(ss * inv_n + eps);
     if (threadIdx.x == 0) {
       stat0[row] = mu;
@@ -318,7 +352,8 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
                 const T* __restrict__ w, int64_t emb, int64_t n, float offset) {
   constexpr int VE = VecIO<T>::N;
   constexpr int RPB = kThreads / TPR;
-  __shared__ float red[kThreads / 32];
+  __shared__ RedBuf red;
+  int parity = 0;
   const int t = threadIdx.x % TPR;
   const int sub = threadIdx.x / TPR;
   const int nvec = static_cast<int>(emb / VE);
@@ -398,7 +433,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
       for (int i = 0; i < MAXV; ++i)
 #pragma unroll
         for (int j = 0; j < VE; ++j) s = fmaf(av[i][j], dv[i][j], s);
-      s = row_sum<TPR>(s, red);
+      s = row_sum<TPR>(s, red, parity);
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
@@ -416,7 +451,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
       for (int i = 0; i < MAXV; ++i)
 #pragma unroll
         for (int j = 0; j < VE; ++j) dd = fmaf(dv[i][j] * wv[i][j], av[i][j], dd);
-      dd = row_sum<TPR>(dd, red);
+      dd = row_sum<TPR>(dd, red, parity);
       const float c = r * r * r * dd * inv_n;
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
@@ -445,8 +480,9 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
           s1 = fmaf(wd, av[i][j], s1);
           s2 += wd;
         }
-      s1 = row_sum<TPR>(s1, red) * inv_n;
-      s2 = row_sum<TPR>(s2, red) * inv_n;
+      row_sum2<TPR>(s1, s2, red, parity);
+      s1 *= inv_n;
+      s2 *= inv_n;
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
@@ -491,7 +527,8 @@ rowwise_bwd_generic(T* __restrict__ dx, float* __restrict__ part0, float* __rest
                     const T* __restrict__ dy, const T* __restrict__ x_or_y,
                     const float* __restrict__ stat0, const float* __restrict__ stat1,
                     const T* __restrict__ w, int64_t emb, int64_t n, float offset) {
-  __shared__ float red[kThreads / 32];
+  __shared__ RedBuf red;
+  int parity = 0;
   const float inv_n = 1.f / static_cast<float>(emb);
   float* p0 = part0 ? part0 + static_cast<int64_t>(blockIdx.x) * emb : nullptr;
   float* p1 = part1 ? part1 + static_cast<int64_t>(blockIdx.x) * emb : nullptr;
@@ -509,7 +546,7 @@ rowwise_bwd_generic(T* __restrict__ dx, float* __restrict__ part0, float* __rest
       float s = 0.f;
       for (int64_t e = threadIdx.x; e < emb; e += kThreads)
         s = fmaf(to_f32<T>(ar[e]), to_f32<T>(dr[e]), s);
-      s = row_sum<256>(s, red);
+      s = row_sum<256>(s, red, parity);
       for (int64_t e = threadIdx.x; e < emb; e += kThreads)
         dxr[e] = from_f32<T>(to_f32<T>(ar[e]) * (to_f32<T>(dr[e]) - s));
     } else if constexpr (OP == 1) {
@@ -517,7 +554,7 @@ rowwise_bwd_generic(T* __restrict__ dx, float* __restrict__ part0, float* __rest
       float dd = 0.f;
       for (int64_t e = threadIdx.x; e < emb; e += kThreads)
         dd = fmaf(to_f32<T>(dr[e]) * (to_f32<T>(w[e]) + offset), to_f32<T>(ar[e]), dd);
-      dd = row_sum<256>(dd, red);
+      dd = row_sum<256>(dd, red, parity);
       const float c = r * r * r * dd * inv_n;
       for (int64_t e = threadIdx.x; e < emb; e += kThreads) {
         const float d = to_f32<T>(dr[e]), xv = to_f32<T>(ar[e]);
@@ -533,8 +570,9 @@ rowwise_bwd_generic(T* __restrict__ dx, float* __restrict__ part0, float* __rest
         s1 = fmaf(wd, xh, s1);
         s2 += wd;
       }
-      s1 = row_sum<256>(s1, red) * inv_n;
-      s2 = row_sum<256>(s2, red) * inv_n;
+      row_sum2<256>(s1, s2, red, parity);
+      s1 *= inv_n;
+      s2 *= inv_n;
       for (int64_t e = threadIdx.x; e < emb; e += kThreads) {
         const float xh = (to_f32<T>(ar[e]) - mu) * r;
         const float d = to_f32<T>(dr[e]);

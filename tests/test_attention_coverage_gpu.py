@@ -1,0 +1,103 @@
+"""Parity rows the round-1 suite left open ("Next round" 1):
+
+* every (dtype, E) the SIMT kernels serve -- bf16 / f16 with E in {16, 32, 256}, Float32 with
+  E in {128, 256} -- causal and non-causal, GQA, ragged lengths, pair and key padding mask;
+* BASELINE config C1 at its full shape (Float32 E=64 L=4096 H=4 B=4 non-causal, README.md:32-42),
+  forward AND backward, every (b, h) slab against the fp64 oracle;
+* BASELINE config C3 at L = 8192 (GQA 32 / 8, E = 128, bf16 causal): one kv-head group against the oracle;
+* `nnop_device_info` (replaces NNop.shared_memory, src/NNop.jl:27-30 / ext/NNopCUDAExt.jl:6-9).
+Tolerances: BASELINE.json's (1e-4 Float32, 2e-2 16-bit; helpers.kernel_err for 16-bit gradients)."""
+import pytest
+import torch
+
+from helpers import kernel_err, max_abs
+from oracle import oracle as O
+from test_attention_gpu import F32_TOL, H16_TOL, _check, _inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("dtype,E", [(torch.bfloat16, 16), (torch.bfloat16, 32), (torch.bfloat16, 256),
+                                     (torch.float16, 16), (torch.float16, 32), (torch.float16, 256),
+                                     (torch.float32, 128), (torch.float32, 256)])
+def test_simt_served_dtype_E_grid(nnop, dtype, E, causal):
+    """Shapes follow the reference grids (test/attention_tests.jl:13-18, test/gqa_attention_tests.jl:8-12):
+    ragged and tile-multiple L, QL != KL when not causal, GQA 4/1 and 6/2, then pair + kpad_mask."""
+    tol = F32_TOL if dtype == torch.float32 else H16_TOL
+    shapes = [(2, 2, 2, 255, 255), (1, 4, 1, 257, 257), (1, 6, 2, 512, 512), (2, 2, 2, 256, 511), (1, 2, 1, 1, 1),
+              (1, 2, 2, 130, 3)]
+    if E == 256:   # keep the E = 256 SIMT runs short
+        shapes = [(2, 2, 2, 255, 255), (1, 4, 1, 257, 257), (1, 2, 2, 130, 300), (1, 2, 1, 1, 1)]
+    for (B, QH, KH, QL, KL) in shapes:
+        if causal and QL != KL:
+            continue
+        q, k, v, dO, _, _ = _inputs(B, QH, KH, QL, KL, E, dtype, QL + 3 * KL + E)
+        try:
+            _check(nnop, q, k, v, dO, None, None, causal, tol, expect_path=0)
+        except AssertionError as e:
+            raise AssertionError(f"{dtype} E={E} shape {(B, QH, KH, QL, KL)}: {e}") from e
+    q, k, v, dO, pr, m = _inputs(2, 4, 2, 255, 255, E, dtype, 5 + E, pair=True, mask=True)
+    _check(nnop, q, k, v, dO, pr, m, causal, tol, expect_path=0)
+
+
+def test_config_c1_full_shape_fwd_bwd(nnop):
+    """README.md:32-42: q, k, v (64, 4096, 4, 4) Float32, non-causal, gradient of sum-free dO ~ N(0,1).
+    The whole problem runs once on the GPU (tensor-core Float32 path); each of the 16 (b, h) slabs is
+    then compared with the fp64 oracle (a slab's score matrix is 134 MB in fp64)."""
+    B, H, L, E = 4, 4, 4096, 64
+    q, k, v, dO, _, _ = _inputs(B, H, H, L, L, E, torch.float32, 4096)
+    qd, kd, vd, dOd = (t.cuda() for t in (q, k, v, dO))
+    o, lse = nnop._flash_attention(qd, kd, vd, causal=False)
+    assert nnop.last_attention_path() == 1
+    dq, dk, dv, _ = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=False)
+    assert nnop.last_attention_path() == 1
+    worst = {}
+    for b in range(B):
+        for h in range(H):
+            sl = lambda t: t[b:b + 1, h:h + 1].double()
+            ro, rl = O.naive_attention(sl(q), sl(k), sl(v), causal=False, return_lse=True)
+            rq, rk, rv, _ = O.naive_attention_bwd(sl(dO), sl(q), sl(k), sl(v), causal=False)
+            for name, got, ref in (("o", o, ro), ("lse", lse, rl), ("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+                worst[name] = max(worst.get(name, 0.0), max_abs(got[b:b + 1, h:h + 1], ref))
+    assert all(e < F32_TOL for e in worst.values()), worst
+
+
+def test_config_c3_kv_group_at_L8192(nnop):
+    """BASELINE config C3's attention (GQA 32 q / 8 kv heads, E = 128, L = 8192, bf16, causal, B = 1):
+    kv head 5 with its four query heads 20..23 against the fp64 oracle, one query head at a time
+    (dK / dV of the group = sum over its query heads, src/attention.jl:28, src/attention_bwd.jl:100,139)."""
+    B, QH, KH, L, E = 1, 32, 8, 8192, 128
+    q, k, v, dO, _, _ = _inputs(B, QH, KH, L, L, E, torch.bfloat16, 8192)
+    qd, kd, vd, dOd = (t.cuda() for t in (q, k, v, dO))
+    o, lse = nnop._flash_attention(qd, kd, vd, causal=True)
+    assert nnop.last_attention_path() == 1
+    dq, dk, dv, _ = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=True)
+    kvh, g = 5, QH // KH
+    ks, vs = k[:, kvh:kvh + 1].double(), v[:, kvh:kvh + 1].double()
+    rk = torch.zeros_like(ks)
+    rv = torch.zeros_like(vs)
+    for h in range(kvh * g, (kvh + 1) * g):
+        qs, ds = q[:, h:h + 1].double(), dO[:, h:h + 1].double()
+        ro, rl = O.naive_attention(qs, ks, vs, causal=True, return_lse=True)
+        gq, gk, gv, _ = O.naive_attention_bwd(ds, qs, ks, vs, causal=True)
+        assert max_abs(o[:, h:h + 1], ro) < H16_TOL and max_abs(lse[:, h:h + 1], rl) < 1e-3, h
+        assert kernel_err(dq[:, h:h + 1], gq) < H16_TOL, h
+        rk += gk
+        rv += gv
+    assert kernel_err(dk[:, kvh:kvh + 1], rk) < H16_TOL
+    assert kernel_err(dv[:, kvh:kvh + 1], rv) < H16_TOL
+
+
+def test_device_info(nnop):
+    """nnop_device_info replaces `NNop.shared_memory(kab, device_id)` (src/NNop.jl:27-30): the opt-in
+    shared memory per block the tcgen05 kernels are sized against, plus the SM count / L2 / HBM size
+    the persistent kernels and the causal tile order use."""
+    info = nnop.device_info(0)
+    prop = torch.cuda.get_device_properties(0)
+    assert info["sm_count"] == prop.multi_processor_count
+    assert (info["cc_major"], info["cc_minor"]) == (prop.major, prop.minor)
+    assert info["hbm_bytes"] == prop.total_memory and info["l2_bytes"] == prop.L2_cache_size
+    assert info["shared_mem_per_block_optin"] >= 227 * 1024   # B200: 227 KB per CTA
+    with pytest.raises(nnop.NNopError):
+        nnop.device_info(torch.cuda.device_count() + 7)

@@ -11,7 +11,7 @@ import math
 import pytest
 import torch
 
-from helpers import load_golden, max_abs, reference_isapprox
+from helpers import kernel_err, load_golden, max_abs, reference_isapprox
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -49,16 +49,15 @@ def _check(nnop, q, k, v, dO, pr, m, causal, tol, expect_path=None):
     dq, dk, dv, dpair = nnop.grad_flash_attention(dev(dO), o, lse, dev(q), dev(k), dev(v), dev(pr),
                                                   causal=causal, kpad_mask=dev(m))
     rq, rk, rv, rp = O.naive_attention_bwd(D(dO), D(q), D(k), D(v), D(pr), causal=causal, kpad_mask=m)
-    # 16-bit outputs: the bound is absolute for O(1) values and follows the output rounding
-    # (2^-8 relative for bf16) once a gradient's magnitude exceeds 2.  Float32 keeps the strict
-    # 1e-4, also on the tensor-core path (E = 64): its dK / dV accumulators are flushed with exact
-    # fp32 adds every few q blocks precisely so that this bound holds for gradients of magnitude ~10.
-    mag = (lambda r: max(1.0, r.abs().max().item() / 2)) if tol > 1e-3 else (lambda r: 1.0)
-    assert max_abs(dq, rq) < tol * mag(rq), "dq"
-    assert max_abs(dk, rk) < tol * mag(rk), "dk"
-    assert max_abs(dv, rv) < tol * mag(rv), "dv"
+    # BASELINE.json's bound (1e-4 Float32, 2e-2 16-bit) on the kernel's error: for 16-bit outputs that is the
+    # error beyond the final rounding of the result to T (helpers.kernel_err).  Float32
+    # keeps the plain max-abs 1e-4, also on the tensor-core path (E = 64): its dK / dV accumulators are
+    # flushed with exact fp32 adds every few q blocks so that the bound holds for gradients of magnitude ~10.
+    assert kernel_err(dq, rq) < tol, "dq"
+    assert kernel_err(dk, rk) < tol, "dk"
+    assert kernel_err(dv, rv) < tol, "dv"
     if pr is not None:
-        assert max_abs(dpair, rp) < tol * mag(rp), "dpair"
+        assert kernel_err(dpair, rp) < tol, "dpair"
     return o, lse
 
 
@@ -184,8 +183,8 @@ def test_tcgen05_matches_generic_path(nnop, causal):
         nnop.set_attention_path(0)
     assert max_abs(o_f, o_g) < H16_TOL and max_abs(lse_f, lse_g) < 1e-3
     g_f = nnop.grad_flash_attention(dOd, o_f, lse_f, qd, kd, vd, causal=causal)
-    for a, b in zip(g_f[:3], g_g[:3]):  # two bf16 results: allow one output ulp at the gradient's magnitude
-        assert max_abs(a, b) < H16_TOL * max(1.0, b.abs().max().item() / 2)
+    for a, b in zip(g_f[:3], g_g[:3]):  # two bf16 results: the bound applies beyond one output ulp
+        assert kernel_err(a, b) < H16_TOL
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
@@ -200,7 +199,7 @@ def test_16bit_pair_on_tensor_cores(nnop, dtype, E, causal):
         if causal and QL != KL:
             continue
         q, k, v, dO, pr, m = _inputs(B, QH, KH, QL, KL, E, dtype, QL + E, pair=True, mask=True)
-        _check(nnop, q, k, v, dO, pr, m, causal, 4e-2, expect_path=1)
+        _check(nnop, q, k, v, dO, pr, m, causal, H16_TOL, expect_path=1)
 
 
 def test_pair_without_workspace_falls_to_generic(nnop):
@@ -255,8 +254,7 @@ def _zero_masked_check(nnop, q, k, v, dO, m, causal):
     assert torch.equal(torch.isfinite(lse.cpu()), fin) and max_abs(lse.cpu()[fin], rl[fin]) < 1e-3
     dq, dk, dv, _ = nnop.grad_flash_attention(dev(dO), o, lse, dev(q), dev(k), dev(v), causal=causal, kpad_mask=dev(m))
     rq, rk, rv, _ = O.naive_attention_bwd(D(dO), D(q), D(k), D(v), causal=causal, kpad_mask=m, zero_masked_rows=True)
-    mag = lambda r: max(1.0, r.abs().max().item() / 2)
-    assert max_abs(dq, rq) < H16_TOL * mag(rq) and max_abs(dk, rk) < H16_TOL * mag(rk) and max_abs(dv, rv) < H16_TOL * mag(rv)
+    assert kernel_err(dq, rq) < H16_TOL and kernel_err(dk, rk) < H16_TOL and kernel_err(dv, rv) < H16_TOL
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
@@ -327,9 +325,9 @@ def test_full_size_properties_config_c2(nnop):
     o_ref, lse_ref = O.naive_attention(sl(q), sl(k), sl(v), causal=True, return_lse=True)
     assert max_abs(o[b:b + 1, h:h + 1], o_ref) < H16_TOL and max_abs(lse[b:b + 1, h:h + 1], lse_ref) < 1e-3
     rq, rk, rv, _ = O.naive_attention_bwd(sl(dO), sl(q), sl(k), sl(v), causal=True)
-    assert max_abs(dq[b:b + 1, h:h + 1], rq) < H16_TOL
-    assert max_abs(dk[b:b + 1, h:h + 1], rk) < H16_TOL * 2
-    assert max_abs(dv[b:b + 1, h:h + 1], rv) < H16_TOL * 2
+    assert kernel_err(dq[b:b + 1, h:h + 1], rq) < H16_TOL
+    assert kernel_err(dk[b:b + 1, h:h + 1], rk) < H16_TOL
+    assert kernel_err(dv[b:b + 1, h:h + 1], rv) < H16_TOL
 
 
 @pytest.mark.parametrize("causal", [False, True])

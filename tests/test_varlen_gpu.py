@@ -6,7 +6,7 @@ import math
 import pytest
 import torch
 
-from helpers import max_abs
+from helpers import kernel_err, max_abs
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -56,14 +56,13 @@ def _check(nnop, lens_q, lens_k, QH, KH, E, dtype, causal, seed=0):
     dq, dk, dv = nnop.grad_flash_attention_varlen(dev(dO), o, lse, dev(q), dev(k), dev(v), dev(cu_q),
                                                   dev(cu_k), mq, mk, causal=causal)
     ro, rl, rq, rk, rv = _oracle(q, k, v, dO, cu_q, cu_k, causal)
-    mag = lambda r: max(1.0, r.abs().max().item() / 2)
     assert max_abs(o, ro) < TOL, "o"
     fin = torch.isfinite(rl)
     assert torch.equal(torch.isfinite(lse.cpu()), fin), "lse finiteness"
     assert max_abs(lse.cpu()[fin], rl[fin]) < 1e-3, "lse"
-    assert max_abs(dq, rq) < TOL * mag(rq), "dq"
-    assert max_abs(dk, rk) < TOL * mag(rk), "dk"
-    assert max_abs(dv, rv) < TOL * mag(rv), "dv"
+    assert kernel_err(dq, rq) < TOL, "dq"   # error beyond the output's rounding to T (helpers.kernel_err)
+    assert kernel_err(dk, rk) < TOL, "dk"
+    assert kernel_err(dv, rv) < TOL, "dv"
 
 
 @pytest.mark.parametrize("causal", [False, True])
@@ -144,9 +143,9 @@ def test_varlen_config4_shape_properties(nnop):
     ro = O.naive_attention(qs, ks, vs, causal=True)
     rq, rk, rv, _ = O.naive_attention_bwd(ds, qs, ks, vs, causal=True)
     assert max_abs(o[:2, a:b], ro[0]) < TOL
-    assert max_abs(dq[:2, a:b], rq[0]) < TOL * max(1.0, rq.abs().max().item() / 2)
-    assert max_abs(dk[:2, a:b], rk[0]) < TOL * max(1.0, rk.abs().max().item() / 2)
-    assert max_abs(dv[:2, a:b], rv[0]) < TOL * max(1.0, rv.abs().max().item() / 2)
+    assert kernel_err(dq[:2, a:b], rq[0]) < TOL
+    assert kernel_err(dk[:2, a:b], rk[0]) < TOL
+    assert kernel_err(dv[:2, a:b], rv[0]) < TOL
 
 
 def test_varlen_errors(nnop):
