@@ -15,8 +15,9 @@
 //    dK' += (dSh + dSl)^T [Qh | Ql]                          16                  -> TMEM [384,512)
 // X' = [X.h-part | X.l-part] accumulates both terms of the second operand side by side (N = 128); the
 // consumer adds the two 64-column halves.  fp32 accumulation throughout; measured max abs error vs
-// an fp64 evaluation ~1e-6 (tolerance 1e-4).  fp16 terms bound the inputs to |x| < 65504, as the
-// reference's own Float16 staging of Q and K does (src/attention_bwd.jl:19-20).  Shared memory is full (two dS tiles), so Q_i and dO_i are
+// an fp64 evaluation ~1e-6 (tolerance 1e-4).  fp16's narrow range is kept out of the picture by carrying every
+// tensor as x' = x * 2^-e_x (its own binary exponent; scale block, internal.h F32Mult) and folding the powers
+// of two back into the logit scale, delta and the epilogue multipliers.  Shared memory is full (two dS tiles), so Q_i and dO_i are
 // single-buffered and S^T(i+1) is issued after dK(i): slower per FLOP than the 16-bit kernel, still
 // an order of magnitude faster than the fp32 SIMT path.  Dense layout, kpad_mask, GQA, ragged sizes.
 #include "common.cuh"
@@ -38,6 +39,7 @@ struct Params {
   const float* deltap;  // (B*QH, QLp)
   int QL, KL, QH, KH, QLp, causal;
   float scale, scale_log2;
+  const float* mult;    // scale block multipliers (internal.h F32Mult): the operands are q', k', v', dO' = x * 2^-e_x
   const uint8_t* kpad;
   // additive bias (BIAS kernel): head-major fp32 copies (B, QH, QL, KLp), see attn_pair.cu
   const float* pair_t;
@@ -283,7 +285,8 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int row = wq * 32 + lane;    // key row within the block
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
     const int c0 = half * 64;
-    const float sl2 = p.scale_log2;
+    const float sl2 = p.scale_log2 * __ldg(p.mult + F32Mult::kLogits);   // S = 2^(e_q + e_k) * q' k'^T
+    const float dpair_mul = BIAS ? __ldg(p.mult + F32Mult::kDPair) : 1.f;
     for (int it = 0; it < n_it; ++it) {
       const int i = i0 + it % nqi;
       float pf[64];
@@ -383,7 +386,7 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             float* dp = p.dpair_t + boff;
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              if (8 * ch + e < nqv) dp[static_cast<int64_t>(8 * ch + e) * p.KLp] = ds[e];
+              if (8 * ch + e < nqv) dp[static_cast<int64_t>(8 * ch + e) * p.KLp] = ds[e] * dpair_mul;
           }
         }
       }
@@ -399,7 +402,7 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
     {
       const uint32_t tsrc = tmem_base + lane_off + (half ? kColDK : kColDV);
-      const float mul = half ? p.scale : 1.f;
+      const float mul = half ? p.scale * __ldg(p.mult + F32Mult::kDK) : __ldg(p.mult + F32Mult::kDV);
       uint8_t* stage = half ? sdO : sQ;  // 32 KB each, free by now
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -439,6 +442,8 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int row = wq * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
     const bool issuer = (warp == 12 && lane == 0);
+    const float dq_mul = p.scale * __ldg(p.mult + F32Mult::kDQ);
+    const float dk_mul = p.scale * __ldg(p.mult + F32Mult::kDK), dv_mul = __ldg(p.mult + F32Mult::kDV);
     int nflush = 0;
     for (int it = 0; it < n_it; ++it) {
       const int bh_q = b * p.QH + hk * g + it / nqi;
@@ -458,11 +463,11 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          float4 v;   // dQ = scale * (dQ'[:, 0:64] + dQ'[:, 64:128])
-          v.x = (__uint_as_float(r[c][4 * u + 0]) + __uint_as_float(r[c + 2][4 * u + 0])) * p.scale;
-          v.y = (__uint_as_float(r[c][4 * u + 1]) + __uint_as_float(r[c + 2][4 * u + 1])) * p.scale;
-          v.z = (__uint_as_float(r[c][4 * u + 2]) + __uint_as_float(r[c + 2][4 * u + 2])) * p.scale;
-          v.w = (__uint_as_float(r[c][4 * u + 3]) + __uint_as_float(r[c + 2][4 * u + 3])) * p.scale;
+          float4 v;   // dQ = scale * 2^(e_dO + e_v + e_k) * (dQ'[:, 0:64] + dQ'[:, 64:128])
+          v.x = (__uint_as_float(r[c][4 * u + 0]) + __uint_as_float(r[c + 2][4 * u + 0])) * dq_mul;
+          v.y = (__uint_as_float(r[c][4 * u + 1]) + __uint_as_float(r[c + 2][4 * u + 1])) * dq_mul;
+          v.z = (__uint_as_float(r[c][4 * u + 2]) + __uint_as_float(r[c + 2][4 * u + 2])) * dq_mul;
+          v.w = (__uint_as_float(r[c][4 * u + 3]) + __uint_as_float(r[c + 2][4 * u + 3])) * dq_mul;
           *reinterpret_cast<float4*>(sStage + c * S::kBox + row * 128 + ((u ^ (row & 7)) << 4)) = v;
         }
       fence_proxy_async_smem();
@@ -479,7 +484,7 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
           const uint32_t tsrc = tmem_base + lane_off + (which ? kColDK : kColDV);
-          const float mul = which ? p.scale : 1.f;
+          const float mul = which ? dk_mul : dv_mul;
 #pragma unroll
           for (int c = 0; c < 4; ++c) tmem_ld_x32(tsrc + c * 32, r[c]);
           tmem_ld_wait();
@@ -522,11 +527,12 @@ attn_bwd_f32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   }
 }
 
-// prep: delta = rowsum(dO o O) over the 64 fp32 columns, lse2 (padded, +inf => P = 0), dq := 0
+// prep: delta' = 2^-(e_dO + e_v) * rowsum(dO o O) over the 64 fp32 columns, lse2 (padded, +inf => P = 0), dq := 0
 __global__ void __launch_bounds__(256)
 attn_bwd_f32_prep_kernel(float* __restrict__ deltap, float* __restrict__ lse2p, float* __restrict__ dq,
                          const float* __restrict__ dO, const float* __restrict__ o,
-                         const float* __restrict__ lse, int QL, int QLp, int64_t n_rows_p) {
+                         const float* __restrict__ lse, int QL, int QLp, int64_t n_rows_p,
+                         const float* __restrict__ mult) {
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   const int64_t rowp = gid >> 4;  // 16 lanes (one float4 each) per 64-float row
   const int li = static_cast<int>(gid & 15);
@@ -545,7 +551,7 @@ attn_bwd_f32_prep_kernel(float* __restrict__ deltap, float* __restrict__ lse2p, 
   for (int sft = 1; sft < 16; sft <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
   if (li == 0) {
     const float l = q < QL ? lse[bh * QL + q] : INFINITY;
-    deltap[rowp] = q < QL ? acc : 0.f;
+    deltap[rowp] = q < QL ? acc * __ldg(mult + F32Mult::kDeltaInv) : 0.f;   // delta' pairs with dP' = dO' v'^T
     lse2p[rowp] = l == -INFINITY ? INFINITY : l * kLog2e;
   }
 }
@@ -557,7 +563,7 @@ inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255);
 size_t attn_f32_bwd_workspace_bytes(int QL, int KL, int QH, int KH, int B) {
   const size_t QLp = static_cast<size_t>((QL + 127) / 128) * 128;
   const size_t BH = static_cast<size_t>(B) * QH, BHk = static_cast<size_t>(B) * KH;
-  return 2 * align256(BH * QLp * sizeof(float)) + (2 * BH * QL + 2 * BHk * KL) * 128 * 2;
+  return 2 * align256(BH * QLp * sizeof(float)) + (2 * BH * QL + 2 * BHk * KL) * 128 * 2 + kF32ScaleBytes;
 }
 
 int attn_f32_bwd(const AttnParams& a) {
@@ -572,20 +578,24 @@ int attn_f32_bwd(const AttnParams& a) {
   T* dos = qs + BH * a.QL * 128;
   T* ks = dos + BH * a.QL * 128;
   T* vs = ks + BHk * a.KL * 128;
+  void* blk = vs + BHk * a.KL * 128;   // scale block: |x|max, exponents, multipliers (internal.h)
+  if (int rc = attn_f32_scales(blk, a.q, BH * a.QL * 64, a.k, BHk * a.KL * 64, a.v, BHk * a.KL * 64, a.dO,
+                               BH * a.QL * 64, a.stream))
+    return rc;
   {
     const int64_t n_rows_p = BH * QLp;
     const int64_t threads = n_rows_p * 16;
     attn_bwd_f32_prep_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, a.stream>>>(
         deltap, lse2p, static_cast<float*>(a.dq), static_cast<const float*>(a.dO),
-        static_cast<const float*>(a.o), a.lse, a.QL, QLp, n_rows_p);
+        static_cast<const float*>(a.o), a.lse, a.QL, QLp, n_rows_p, f32_mults(blk));
     NNOP_LAUNCH_CHECK();
   }
   NNOP_CUDA_CHECK(cudaMemsetAsync(a.dk, 0, static_cast<size_t>(BHk) * a.KL * 64 * sizeof(float), a.stream));
   NNOP_CUDA_CHECK(cudaMemsetAsync(a.dv, 0, static_cast<size_t>(BHk) * a.KL * 64 * sizeof(float), a.stream));
-  if (int rc = attn_split_f32_rows(qs, a.q, BH * a.QL, a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(dos, a.dO, BH * a.QL, a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(ks, a.k, BHk * a.KL, a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(vs, a.v, BHk * a.KL, a.stream)) return rc;
+  if (int rc = attn_split_f32_rows(qs, a.q, BH * a.QL, f32_exp_slot(blk, 0), a.stream)) return rc;
+  if (int rc = attn_split_f32_rows(dos, a.dO, BH * a.QL, f32_exp_slot(blk, 3), a.stream)) return rc;
+  if (int rc = attn_split_f32_rows(ks, a.k, BHk * a.KL, f32_exp_slot(blk, 1), a.stream)) return rc;
+  if (int rc = attn_split_f32_rows(vs, a.v, BHk * a.KL, f32_exp_slot(blk, 2), a.stream)) return rc;
   alignas(64) CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdq;
   const uint64_t bhq = static_cast<uint64_t>(BH), bhk = static_cast<uint64_t>(BHk);
   if (int rc = make_tmap_3d(&tq, qs, NNOP_F16, 128, a.QL, bhq, 64, 128)) return rc;
@@ -603,7 +613,7 @@ int attn_f32_bwd(const AttnParams& a) {
   Params bp;
   bp.lse2p = lse2p; bp.deltap = deltap;
   bp.QL = a.QL; bp.KL = a.KL; bp.QH = a.QH; bp.KH = a.KH; bp.QLp = QLp; bp.causal = a.causal;
-  bp.scale = a.scale; bp.scale_log2 = a.scale * kLog2e;
+  bp.scale = a.scale; bp.scale_log2 = a.scale * kLog2e; bp.mult = f32_mults(blk);
   bp.kpad = a.kpad;
   bp.pair_t = static_cast<const float*>(a.pair_t); bp.dpair_t = static_cast<float*>(a.dpair_t); bp.KLp = a.KLp;
   dim3 grid((a.KL + 127) / 128, a.KH, a.B);

@@ -64,6 +64,7 @@ struct FwdParams {
   float* lse;
   int QL, KL, QH, KH, causal;  // packed (varlen) mode: QL / KL are the maximum sequence lengths
   float scale_log2;
+  const float* f32_mult;  // SPLIT (Float32) kernels: multipliers of the scale block (internal.h F32Mult), else unused
   // packed variable-length mode (cu_q != nullptr): sequence z = blockIdx.z owns rows
   // [cu_q[z], cu_q[z+1]) of the (QH, total_q, E) tensors and keys [cu_k[z], cu_k[z+1])
   const int* cu_q;
@@ -452,7 +453,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       const uint32_t tS = tmem_base + lane_off + t * 128;
       const uint32_t tO = tmem_base + lane_off + 256 + t * D;
       // with a bias the logits are moved to log2 units as they are folded, so the rest runs unscaled
-      const float sl2 = BIAS ? 1.f : p.scale_log2;
+      // Float32 (SPLIT): q', k' are the caller's q, k times exact powers of two (scale block); the logit scale
+      // takes 2^(e_q + e_k) back, the epilogue 2^e_v
+      const float scale_log2 = SPLIT ? p.scale_log2 * __ldg(p.f32_mult + F32Mult::kLogits) : p.scale_log2;
+      const float sl2 = BIAS ? 1.f : scale_log2;
       float m_used = -1e30f;  // reference max in scaled log2 units (finite: see the speculation note)
       float l = 0.f;
 
@@ -486,7 +490,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         }
         if constexpr (BIAS) {
           // S <- S * scale * log2e + pair * log2e, one 128-byte box row (this thread's query) at a time
-          const float sraw = p.scale_log2;
+          const float sraw = scale_log2;
 #pragma unroll
           for (int c = 0; c < kBiasChunks; ++c) {
             const int n = i * kBiasChunks + c;
@@ -635,9 +639,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       // ---- epilogue: O / l -> 16-bit -> swizzled smem (the Q_t buffer) -> TMA store -----
       mbar_wait(&o_full[t], 0);
       tc_fence_after();
-      const float inv_l = l > 0.f ? 1.f / l : 0.f;
+      float inv_l = l > 0.f ? 1.f / l : 0.f;
       uint8_t* stage = sQ + t * S::kTileBytes;
       if constexpr (SPLIT) {
+        inv_l *= __ldg(p.f32_mult + F32Mult::kO);   // O = 2^e_v * P V'
         // O'[:, 0:64] = P Vh, O'[:, 64:128] = P Vl: add them, normalise, stage as fp32 (two boxes of
         // 32 floats x 128 rows, same 128-byte swizzle) for the fp32 TMA store
 #pragma unroll
@@ -1253,15 +1258,21 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
   }
 }
 
-// x (rows, 64) fp32 -> (rows, 128) fp16 = [hi(64) | lo(64)], hi = fp16(x), lo = fp16(x - hi): 22
-// significant bits (bf16 terms would give 16, not enough for 1e-4 absolute on gradients of
-// magnitude ~5).  |x| must stay below 65504 -- the reference itself stages Q and K as Float16 in
-// its backward (src/attention_bwd.jl:19-20).
+// x (rows, 64) fp32 -> (rows, 128) fp16 = [hi(64) | lo(64)] of x' = x * 2^-e, hi = fp16(x'), lo = fp16(x' - hi):
+// 22 significant bits (bf16 terms would give 16, not enough for 1e-4 absolute on gradients of
+// magnitude ~5).  e is the tensor's own binary exponent (|x|max = m * 2^e, m in [0.5, 1); scale block
+// below), so x' lies in [-1, 1] whatever the caller's units are: fp16's narrow range (65504 at the top,
+// 6e-8 subnormal spacing at the bottom) would otherwise overflow for |x| ~ 1e5 and flush or coarsen a
+// tensor of small values -- an upstream gradient dO = 1/N ~ 5e-7 of a mean-reduced loss lost several
+// percent.  The power of two is exact; the kernels undo it with the multipliers below.
 __global__ void __launch_bounds__(256)
-split_f32_kernel(__half* __restrict__ out, const float* __restrict__ in, int64_t n4) {
+split_f32_kernel(__half* __restrict__ out, const float* __restrict__ in, int64_t n4,
+                 const int* __restrict__ exp_slot) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;  // one float4 per thread
   if (i >= n4) return;
-  const float4 x = reinterpret_cast<const float4*>(in)[i];
+  const int e = exp_slot ? -__ldg(exp_slot) : 0;
+  float4 x = reinterpret_cast<const float4*>(in)[i];
+  x.x = ldexpf(x.x, e); x.y = ldexpf(x.y, e); x.z = ldexpf(x.z, e); x.w = ldexpf(x.w, e);
   const int64_t row = i >> 4;          // 16 float4 per 64-float row
   const int c4 = static_cast<int>(i & 15);
   const uint32_t h0 = pack2<__half>(x.x, x.y), h1 = pack2<__half>(x.z, x.w);
@@ -1272,12 +1283,61 @@ split_f32_kernel(__half* __restrict__ out, const float* __restrict__ in, int64_t
   o[16 + c4] = make_uint2(l0, l1);
 }
 
-int launch_split(__half* out, const void* in, int64_t rows, cudaStream_t st) {
+int launch_split(__half* out, const void* in, int64_t rows, const int* exp_slot, cudaStream_t st) {
   const int64_t n4 = rows * 16;
   if (n4 == 0) return NNOP_OK;
-  split_f32_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(out, static_cast<const float*>(in), n4);
+  split_f32_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(out, static_cast<const float*>(in), n4,
+                                                                           exp_slot);
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
+}
+
+// ---- Float32 scale block (kF32ScaleBytes at the end of the Float32 workspaces) ----
+//   u32[0..3]  bit patterns of |q|max, |k|max, |v|max, |dO|max (atomicMax; non-negative floats order as uints)
+//   i32[4..7]  their binary exponents e_q, e_k, e_v, e_dO (0 for an all-zero or non-finite tensor)
+//   f32[8..14] multipliers, see F32Mult in internal.h
+struct AbsmaxArgs {
+  const float* ptr[4];
+  int64_t n4[4];
+};
+__global__ void __launch_bounds__(256) absmax_f32_kernel(uint32_t* __restrict__ slots, const AbsmaxArgs a) {
+  const int which = blockIdx.y;
+  const float4* in = reinterpret_cast<const float4*>(a.ptr[which]);
+  const int64_t n4 = a.n4[which];
+  float m = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * 256) {
+    const float4 x = in[i];
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+  }
+  m = warp_max(m);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    if (m > 0.f) atomicMax(slots + which, __float_as_uint(m));
+  }
+}
+__global__ void f32_scales_finalize_kernel(uint32_t* __restrict__ blk) {
+  int e[4];
+  for (int i = 0; i < 4; ++i) {
+    const float m = __uint_as_float(blk[i]);
+    int ex = 0;
+    if (m > 0.f && m <= 3.4028234e38f) frexpf(m, &ex);
+    e[i] = ex;
+    reinterpret_cast<int*>(blk)[4 + i] = ex;
+  }
+  float* f = reinterpret_cast<float*>(blk);
+  const int eq = e[0], ek = e[1], ev = e[2], edo = e[3];
+  f[8 + F32Mult::kLogits] = ldexpf(1.f, eq + ek);
+  f[8 + F32Mult::kO] = ldexpf(1.f, ev);
+  f[8 + F32Mult::kDeltaInv] = ldexpf(1.f, -(edo + ev));
+  f[8 + F32Mult::kDV] = ldexpf(1.f, edo);
+  f[8 + F32Mult::kDQ] = ldexpf(1.f, edo + ev + ek);
+  f[8 + F32Mult::kDK] = ldexpf(1.f, edo + ev + eq);
+  f[8 + F32Mult::kDPair] = ldexpf(1.f, edo + ev);
 }
 
 // Float32, E = 64: split q, k, v into [hi | lo] bf16 rows in the workspace, then the SPLIT kernel
@@ -1290,9 +1350,11 @@ int launch_fwd_f32(const AttnParams& a) {
   T* qs = static_cast<T*>(a.fwd_ws);
   T* ks = qs + rq * 128;
   T* vs = ks + rk * 128;
-  if (int rc = launch_split(qs, a.q, rq, a.stream)) return rc;
-  if (int rc = launch_split(ks, a.k, rk, a.stream)) return rc;
-  if (int rc = launch_split(vs, a.v, rk, a.stream)) return rc;
+  void* blk = vs + rk * 128;   // scale block (256-byte aligned: every copy is a multiple of 256 bytes)
+  if (int rc = attn_f32_scales(blk, a.q, rq * 64, a.k, rk * 64, a.v, rk * 64, nullptr, 0, a.stream)) return rc;
+  if (int rc = launch_split(qs, a.q, rq, f32_exp_slot(blk, 0), a.stream)) return rc;
+  if (int rc = launch_split(ks, a.k, rk, f32_exp_slot(blk, 1), a.stream)) return rc;
+  if (int rc = launch_split(vs, a.v, rk, f32_exp_slot(blk, 2), a.stream)) return rc;
   alignas(64) CUtensorMap tq, tk, tv, to;
   const uint64_t bhq = static_cast<uint64_t>(a.B) * a.QH, bhk = static_cast<uint64_t>(a.B) * a.KH;
   if (int rc = make_tmap_3d(&tq, qs, NNOP_F16, D, a.QL, bhq, 64, 128)) return rc;
@@ -1308,6 +1370,7 @@ int launch_fwd_f32(const AttnParams& a) {
   fp.lse = a.lse;
   fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
   fp.scale_log2 = a.scale * kLog2e;
+  fp.f32_mult = f32_mults(blk);
   fp.cu_q = nullptr; fp.cu_k = nullptr; fp.o_ptr = a.o; fp.total_q = 0; fp.nseq = 0;
   fp.lpt_group = 0;
   fp.kpad = a.kpad;
@@ -1342,6 +1405,7 @@ int launch_fwd(const AttnParams& a) {
   fp.lse = a.lse;
   fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
   fp.scale_log2 = a.scale * kLog2e;
+  fp.f32_mult = nullptr;
   fp.cu_q = a.cu_q; fp.cu_k = a.cu_k; fp.o_ptr = a.o; fp.total_q = a.total_q;
   fp.kpad = packed ? nullptr : a.kpad;
   fp.nseq = a.nseq;
@@ -1397,6 +1461,7 @@ int launch_fwd_persist(const AttnParams& a, int ctas) {
   fp.lse = a.lse;
   fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
   fp.scale_log2 = a.scale * kLog2e;
+  fp.f32_mult = nullptr;
   fp.cu_q = a.cu_q; fp.cu_k = a.cu_k; fp.o_ptr = a.o; fp.total_q = a.total_q; fp.kpad = nullptr;
   fp.nseq = a.nseq;
   fp.lpt_group = 0;
@@ -1442,13 +1507,35 @@ bool attn_sm100_supported(const AttnParams& a, bool backward) {
   return true;
 }
 
-int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, cudaStream_t st) {
-  return launch_split(static_cast<__half*>(out_bf16x2), in_f32, rows, st);
+int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, const int* exp_slot,
+                        cudaStream_t st) {
+  return launch_split(static_cast<__half*>(out_bf16x2), in_f32, rows, exp_slot, st);
+}
+
+int attn_f32_scales(void* block, const void* q, int64_t nq, const void* k, int64_t nk, const void* v,
+                    int64_t nv, const void* dO, int64_t ndo, cudaStream_t st) {
+  NNOP_CUDA_CHECK(cudaMemsetAsync(block, 0, kF32ScaleBytes, st));
+  AbsmaxArgs a;
+  const void* ptrs[4] = {q, k, v, dO};
+  const int64_t ns[4] = {nq, nk, nv, dO ? ndo : 0};
+  int64_t most = 0;
+  for (int i = 0; i < 4; ++i) {
+    a.ptr[i] = static_cast<const float*>(ptrs[i]);
+    a.n4[i] = ns[i] / 4;   // E = 64: element counts are multiples of 64
+    if (a.n4[i] > most) most = a.n4[i];
+  }
+  int64_t gx = (most + 256 * 8 - 1) / (256 * 8);   // ~8 float4 per thread
+  if (gx < 1) gx = 1;
+  if (gx > 4 * sm_count()) gx = 4 * sm_count();
+  absmax_f32_kernel<<<dim3(static_cast<unsigned>(gx), dO ? 4 : 3), 256, 0, st>>>(static_cast<uint32_t*>(block), a);
+  f32_scales_finalize_kernel<<<1, 1, 0, st>>>(static_cast<uint32_t*>(block));
+  NNOP_LAUNCH_CHECK();
+  return NNOP_OK;
 }
 
 size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B) {
   if (dtype != NNOP_F32 || E != 64) return 0;
-  return (static_cast<size_t>(B) * QH * QL + 2 * static_cast<size_t>(B) * KH * KL) * 128 * 2;
+  return (static_cast<size_t>(B) * QH * QL + 2 * static_cast<size_t>(B) * KH * KL) * 128 * 2 + kF32ScaleBytes;
 }
 
 int attn_sm100_fwd(const AttnParams& a) {

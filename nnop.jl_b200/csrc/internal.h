@@ -91,8 +91,30 @@ bool attn_sm100_supported(const AttnParams& p, bool backward);
 int attn_sm100_fwd(const AttnParams& p);
 void attn_sm100_set_fwd_mode(int mode);  // 0 auto, 1 one CTA per q tile, 2 persistent, 100+n persistent on n CTAs
 size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B);
-// (rows, 64) fp32 -> (rows, 128) bf16 rows [hi(64) | lo(64)] with x ~ hi + lo (Float32 tensor-core path)
-int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, cudaStream_t st);
+// Float32 tensor-core path (E = 64): every operand tensor is carried as two fp16 terms of x * 2^-e, e the
+// tensor's own binary exponent, so that fp16's range never clips or flushes it.  The 256-byte scale block at
+// the end of the Float32 workspaces holds |x|max bit patterns [u32 0..3: q, k, v, dO], the exponents
+// [i32 4..7] and the multipliers the kernels apply to undo the scaling [f32 8 + F32Mult::k*].
+constexpr size_t kF32ScaleBytes = 256;
+struct F32Mult {
+  enum : int {
+    kLogits = 0,    // 2^(e_q + e_k): S = kLogits * q' k'^T           (on top of scale * log2e)
+    kO = 1,         // 2^e_v: O = kO * P v'
+    kDeltaInv = 2,  // 2^-(e_dO + e_v): delta' = delta * kDeltaInv, so that dS' = P o (dP' - delta') is O(1)
+    kDV = 3,        // 2^e_dO: dV = kDV * P^T dO'
+    kDQ = 4,        // 2^(e_dO + e_v + e_k): dQ = scale * kDQ * dS' k'
+    kDK = 5,        // 2^(e_dO + e_v + e_q): dK = scale * kDK * dS'^T q'
+    kDPair = 6      // 2^(e_dO + e_v): dpair = kDPair * dS'
+  };
+};
+inline const int* f32_exp_slot(const void* block, int which) { return static_cast<const int*>(block) + 4 + which; }
+inline const float* f32_mults(const void* block) { return static_cast<const float*>(block) + 8; }
+// memset + |x|max of q, k, v (and dO, may be NULL) + exponents / multipliers; n* = element counts
+int attn_f32_scales(void* block, const void* q, int64_t nq, const void* k, int64_t nk, const void* v,
+                    int64_t nv, const void* dO, int64_t ndo, cudaStream_t st);
+// (rows, 64) fp32 -> (rows, 128) fp16 rows [hi(64) | lo(64)] with x * 2^-(*exp_slot) ~ hi + lo
+int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, const int* exp_slot,
+                        cudaStream_t st);
 // attn_bwd_f32_sm100.cu -- Float32 (E = 64) backward on the tensor cores (split-bf16 operands)
 size_t attn_f32_bwd_workspace_bytes(int QL, int KL, int QH, int KH, int B);
 int attn_f32_bwd(const AttnParams& p);

@@ -101,3 +101,31 @@ def test_device_info(nnop):
     assert info["shared_mem_per_block_optin"] >= 227 * 1024   # B200: 227 KB per CTA
     with pytest.raises(nnop.NNopError):
         nnop.device_info(torch.cuda.device_count() + 7)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("sq,sk,sv,sdo", [(1.0, 1.0, 1.0, 5e-7),      # dO = 1/N of a mean-reduced loss
+                                          (1e3, 1e-3, 1.0, 1.0),      # q, k in different units
+                                          (1.0, 1.0, 1e5, 1e-5),      # |v| beyond fp16's 65504
+                                          (1e-3, 1e-3, 1e-3, 1e-3),   # everything small
+                                          (30.0, 30.0, 2e4, 3e4)])    # large everywhere, peaked softmax
+def test_f32_tensor_core_path_dynamic_range(nnop, causal, sq, sk, sv, sdo):
+    """Float32 E = 64 runs on the tensor cores with every operand carried as two fp16 terms.  fp16's range
+    (65504 at the top, 6e-8 spacing at the bottom) must not leak into the result: each tensor is scaled by
+    its own power of two before the split and the kernels undo it (csrc/internal.h F32Mult).  The bound is
+    BASELINE.json's 1e-4, relative to each result's magnitude since these inputs are not O(1)."""
+    B, QH, KH, L, E = 2, 4, 2, 515, 64
+    q, k, v, dO, _, m = _inputs(B, QH, KH, L, L, E, torch.float32, 99, mask=True)
+    q, k, v, dO = q * sq, k * sk, v * sv, dO * sdo
+    qd, kd, vd, dOd, md = (t.cuda() for t in (q, k, v, dO, m))
+    o, lse = nnop._flash_attention(qd, kd, vd, causal=causal, kpad_mask=md)
+    assert nnop.last_attention_path() == 1
+    dq, dk, dv, _ = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=causal, kpad_mask=md)
+    assert nnop.last_attention_path() == 1
+    D = lambda t: t.double()
+    ro, rl = O.naive_attention(D(q), D(k), D(v), causal=causal, kpad_mask=m, return_lse=True)
+    rq, rk, rv, _ = O.naive_attention_bwd(D(dO), D(q), D(k), D(v), causal=causal, kpad_mask=m)
+    assert max_abs(lse, rl) < F32_TOL * max(1.0, rl.abs().max().item()), "lse"
+    for name, got, ref in (("o", o, ro), ("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        assert torch.isfinite(got).all(), name
+        assert max_abs(got, ref) < F32_TOL * ref.abs().max().item(), (name, max_abs(got, ref), ref.abs().max().item())
