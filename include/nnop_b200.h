@@ -197,6 +197,39 @@ int nnop_store_rows_from_f32(void* out, const float* acc, int dtype, int E, int6
                              void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Sequence-sharded ("ring") flash attention over the GPUs of ONE process (additive: the reference has
+ * no multi-GPU path; BASELINE config C5).  ndev ranks; rank r runs on CUDA device devices[r] (a device
+ * may appear more than once: ranks then share it, which is how a single-GPU box tests the schedule).
+ * Every array argument is a HOST array of ndev DEVICE pointers, one per rank:
+ *   q[r], o[r], dq[r], dO[r] (E, Ll, QH, B) T ;  k[r], v[r], dk[r], dv[r] (E, Ll, KH, B) T ;
+ *   lse[r] (Ll, QH, B) float -- the log-sum-exp over the WHOLE sequence (forward: out; backward: in,
+ *   together with the final o).  Rank r holds rows [r*Ll, (r+1)*Ll) of the sequence; with causal != 0
+ *   the zig-zag layout instead: the sequence is cut into 2*ndev chunks of Ll/2 rows and rank r holds
+ *   chunks r and 2*ndev-1-r, concatenated (equal work per rank and step, no mask beyond step 0).
+ *   workspace[r]: device memory on devices[r], 256-byte aligned, at least *_workspace_bytes(...) each.
+ *   streams[r]: cudaStream_t of devices[r] (NULL array or NULL entries = default streams).  Inputs are
+ *   read, and outputs complete, in the order of streams[r]; the call only enqueues.
+ * K / V blocks are pulled from their owner's tensors over NVLink (cudaMemcpyPeerAsync on copy streams
+ * made and released inside the call; peer access is enabled where available) one step ahead of the
+ * math; each step is one dense nnop_flash_attn_fwd / _bwd launch sequence; dk / dv partials are pushed
+ * to the block's owner and accumulated there in fp32.  Same math as `_flash_attention` /
+ * `∇flash_attention` on the gathered sequence (src/attention.jl:133-177, src/attention_bwd.jl:199-275).
+ */
+size_t nnop_ring_attn_fwd_workspace_bytes(int dtype, int E, int Ll, int QH, int KH, int B, int ndev,
+                                          int causal);
+int nnop_ring_attn_fwd(void* const* o, float* const* lse, const void* const* q, const void* const* k,
+                       const void* const* v, const int* devices, int ndev, int dtype, int E, int Ll,
+                       int QH, int KH, int B, int causal, float scale, void* const* workspace,
+                       size_t workspace_bytes, void* const* streams);
+size_t nnop_ring_attn_bwd_workspace_bytes(int dtype, int E, int Ll, int QH, int KH, int B, int ndev,
+                                          int causal);
+int nnop_ring_attn_bwd(void* const* dq, void* const* dk, void* const* dv, const void* const* dO,
+                       const void* const* o, const float* const* lse, const void* const* q,
+                       const void* const* k, const void* const* v, const int* devices, int ndev,
+                       int dtype, int E, int Ll, int QH, int KH, int B, int causal, float scale,
+                       void* const* workspace, size_t workspace_bytes, void* const* streams);
+
+/* ---------------------------------------------------------------------------------------
  * online softmax over dim 1 of x (N, cols).  Replaces `online_softmax` / `online_softmax!`
  * (src/softmax.jl:60-68, :19-58) and `∇online_softmax` (src/softmax.jl:70-80).
  */

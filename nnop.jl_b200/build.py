@@ -18,7 +18,7 @@ CSRC = HERE / "csrc"
 OBJ = HERE / "build"
 LIB = HERE / "lib" / "libnnop_b200.so"
 SOURCES = ["api.cu", "rowwise.cu", "rope.cu", "attn_generic.cu", "attn_fwd_sm100.cu",
-           "attn_bwd_sm100.cu", "attn_bwd_f32_sm100.cu", "attn_pair.cu", "ring_ops.cu", "selftest.cu"]
+           "attn_bwd_sm100.cu", "attn_bwd_f32_sm100.cu", "attn_pair.cu", "ring_ops.cu", "ring_attn.cu", "selftest.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v",

@@ -16,9 +16,11 @@ void clear_error();
 #define NNOP_CUDA_CHECK(expr)                                                              \
   do {                                                                                     \
     cudaError_t _e = (expr);                                                               \
-    if (_e != cudaSuccess)                                                                 \
+    if (_e != cudaSuccess) {                                                               \
+      (void)cudaGetLastError(); /* reported here: do not leave it for the next launch check */ \
       return ::nnop::fail(NNOP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                   \
                           cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+    }                                                                                      \
   } while (0)
 
 #define NNOP_LAUNCH_CHECK()                                                                \

@@ -4,7 +4,10 @@
 # pxl-th/NNop.jl v0.2.0; every body is: validate -> allocate outputs with `similar` -> one
 # `ccall` into libnnop_b200.so (C ABI: include/nnop_b200.h) on the task-local CUDA stream.
 # It replaces ext/NNopCUDAExt.jl and the KernelAbstractions kernels of src/*.jl; there is no
-# AMDGPU dispatch and no CPU fallback.  (Written without a Julia toolchain at hand -- the image
+# AMDGPU dispatch and no CPU fallback.  Two ways in: with the reference installed,
+# `using NNop, NNopB200` loads ext/NNopB200NNopExt.jl, which adds these bodies as CuArray methods of
+# NNop's own functions (the reference's extension seam, Project.toml:14-20); without it,
+# `const NNop = NNopB200` gives user code the same names.  (Written without a Julia toolchain at hand -- the image
 # this repo is built in has none -- so it is kept deliberately thin; the same ABI is exercised
 # end to end by the Python twin in nnop.jl_b200/nnop_b200/.)
 module NNopB200
@@ -29,6 +32,30 @@ end
 ptr(x::CuArray) = Base.unsafe_convert(CuPtr{Cvoid}, x)
 ptr(::Nothing) = CuPtr{Cvoid}(0)
 stream() = CUDA.stream().handle
+
+# Workspaces are released right after the (enqueue-only) library call.  That is safe because CUDA.jl's
+# memory pool is stream-ordered: `unsafe_free!` hands the block back with `cuMemFreeAsync` semantics on
+# the task-local stream -- the stream the kernels were just enqueued on -- so the memory cannot be
+# reused before they have run.  With a non-stream-ordered pool (`JULIA_CUDA_MEMORY_POOL=none`) set
+# `NNOP_B200_EAGER_FREE=0` and the garbage collector releases them instead.
+const EAGER_FREE = get(ENV, "NNOP_B200_EAGER_FREE", "1") != "0"
+release!(ws::CuArray) = (EAGER_FREE && CUDA.unsafe_free!(ws); nothing)
+release!(::Nothing) = nothing
+
+# nnop_device_info: replaces NNop.shared_memory / _shared_memory (src/NNop.jl:27-30, ext/NNopCUDAExt.jl:6-9)
+struct DeviceInfo
+    sm_count::Cint
+    cc_major::Cint
+    cc_minor::Cint
+    shared_mem_per_block_optin::Csize_t
+    l2_bytes::Csize_t
+    hbm_bytes::Csize_t
+end
+function device_info(device::Integer = CUDA.deviceid(CUDA.device()))
+    info = Ref{DeviceInfo}()
+    check(ccall((:nnop_device_info, libnnop_b200), Cint, (Cint, Ptr{DeviceInfo}), device, info))
+    return info[]
+end
 
 within_gradient(x) = false                                                     # src/attention_crc.jl:1-2
 CRC.rrule(::typeof(within_gradient), x) = true, _ -> (CRC.NoTangent(), CRC.NoTangent())
@@ -71,8 +98,10 @@ function _flash_attention(
         dtype_code(T), QE, QL, KL, QH, KH, B, causal, Float32(inv(sqrt(QE))), ptr(ws), nbytes, stream()))
     # third residual (the reference's `ls` slot): with a pair bias, the workspace that now holds the
     # head-major copy of `pair`, and its offset -- the backward takes it instead of making its own
-    if isnothing(pair)
-        isnothing(ws) || CUDA.unsafe_free!(ws)
+    # ... but only when the tensor-core path actually ran and wrote that copy (the SIMT kernels read
+    # `pair` in place and leave the workspace untouched)
+    if isnothing(pair) || ccall((:nnop_last_attention_path, libnnop_b200), Cint, ()) != 1
+        release!(ws)
         return o, lse, nothing
     end
     return o, lse, (ws, Int((base + 255) & ~Csize_t(255)))
@@ -105,7 +134,7 @@ function ∇flash_attention(
         ptr(dq), ptr(dk), ptr(dv), ptr(dpair), ptr(Δ), ptr(o), ptr(ms), ptr(q), ptr(k), ptr(v),
         ptr(pair), ptr(kpad_mask), dtype_code(T), QE, QL, KL, QH, KH, B, causal,
         Float32(inv(sqrt(QE))), ptr(ws), nbytes, stream(), pair_hm))
-    CUDA.unsafe_free!(ws)
+    release!(ws)
     return dq, dk, dv, dpair
 end
 
@@ -171,7 +200,7 @@ function ∇flash_attention_varlen(
         ptr(dq), ptr(dk), ptr(dv), ptr(Δ), ptr(o), ptr(lse), ptr(q), ptr(k), ptr(v),
         ptr(cu_seqlens_q), ptr(cu_seqlens_k), nseq, max_seqlen_q, max_seqlen_k, TQ, TK,
         dtype_code(T), E, QH, KH, causal, Float32(inv(sqrt(E))), ptr(ws), nbytes, stream()))
-    CUDA.unsafe_free!(ws)
+    release!(ws)
     return dq, dk, dv
 end
 
@@ -187,6 +216,101 @@ function CRC.rrule(::typeof(flash_attention_varlen), q, k, v, cu_q, cu_k, max_q,
         return nt, dq, dk, dv, nt, nt, nt, nt
     end
     return o, _pullback
+end
+
+# ------------------------------------------------------------------ sequence-sharded ("ring") attention
+# Additive (the reference has no multi-GPU path): one process, rank r = the r-th array of each vector, each
+# on its own device.  qs[r] (E, Ll, QH, B), ks[r] / vs[r] (E, Ll, KH, B); causal inputs in zig-zag order
+# (rank r holds chunks r and 2W-1-r of 2W).  K / V blocks move device to device over NVLink inside
+# nnop_ring_attn_fwd / _bwd (include/nnop_b200.h); every rank's work is enqueued on that device's
+# task-local stream.
+on_device(f, x::CuArray) = CUDA.device!(f, CUDA.device(x))
+dev_ptrs(xs) = CuPtr{Cvoid}[ptr(x) for x in xs]
+dev_ids(xs) = Cint[CUDA.deviceid(CUDA.device(x)) for x in xs]
+dev_streams(xs) = Ptr{Cvoid}[on_device(() -> reinterpret(Ptr{Cvoid}, CUDA.stream().handle), x) for x in xs]
+
+function _ring_flash_attention(qs::Vector{<:CuArray{T,4}}, ks::Vector{<:CuArray{T,4}},
+                               vs::Vector{<:CuArray{T,4}}; causal::Bool) where T <: FloatT
+    W = length(qs)
+    E, Ll, QH, B = size(qs[1])
+    KH = size(ks[1], 3)
+    os = [on_device(() -> similar(q), q) for q in qs]
+    lses = [on_device(() -> CUDA.zeros(Float32, Ll, QH, B), q) for q in qs]
+    nbytes = ccall((:nnop_ring_attn_fwd_workspace_bytes, libnnop_b200), Csize_t,
+        (Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint), dtype_code(T), E, Ll, QH, KH, B, W, causal)
+    wss = [on_device(() -> CuArray{UInt8}(undef, max(nbytes, 1)), q) for q in qs]
+    check(ccall((:nnop_ring_attn_fwd, libnnop_b200), Cint,
+        (Ptr{CuPtr{Cvoid}}, Ptr{CuPtr{Cvoid}}, Ptr{CuPtr{Cvoid}}, Ptr{CuPtr{Cvoid}}, Ptr{CuPtr{Cvoid}},
+         Ptr{Cint}, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cfloat,
+         Ptr{CuPtr{Cvoid}}, Csize_t, Ptr{Ptr{Cvoid}}),
+        dev_ptrs(os), dev_ptrs(lses), dev_ptrs(qs), dev_ptrs(ks), dev_ptrs(vs),
+        dev_ids(qs), W, dtype_code(T), E, Ll, QH, KH, B, causal, Float32(inv(sqrt(E))),
+        dev_ptrs(wss), nbytes, dev_streams(qs)))
+    foreach(ws -> on_device(() -> release!(ws), ws), wss)
+    return os, lses
+end
+
+function ∇ring_flash_attention(Δs::Vector{<:CuArray{T,4}}, os, lses, qs::Vector{<:CuArray{T,4}},
+                               ks::Vector{<:CuArray{T,4}}, vs::Vector{<:CuArray{T,4}}; causal::Bool) where T <: FloatT
+    W = length(qs)
+    E, Ll, QH, B = size(qs[1])
+    KH = size(ks[1], 3)
+    dqs = [on_device(() -> similar(q), q) for q in qs]
+    dks = [on_device(() -> similar(k), k) for k in ks]
+    dvs = [on_device(() -> similar(v), v) for v in vs]
+    nbytes = ccall((:nnop_ring_attn_bwd_workspace_bytes, libnnop_b200), Csize_t,
+        (Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint), dtype_code(T), E, Ll, QH, KH, B, W, causal)
+    wss = [on_device(() -> CuArray{UInt8}(undef, max(nbytes, 1)), q) for q in qs]
+    check(ccall((:nnop_ring_attn_bwd, libnnop_b200), Cint,
+        (Ptr{CuPtr{Cvoid}}, Ptr{CuPtr{Cvoid}}, Ptr{CuPtr{Cvoid}}, Ptr{CuPtr{Cvoid}}, Ptr{CuPtr{Cvoid}},
+         Ptr{CuPtr{Cvoid}}, Ptr{CuPtr{Cvoid}}, Ptr{CuPtr{Cvoid}}, Ptr{CuPtr{Cvoid}},
+         Ptr{Cint}, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cfloat,
+         Ptr{CuPtr{Cvoid}}, Csize_t, Ptr{Ptr{Cvoid}}),
+        dev_ptrs(dqs), dev_ptrs(dks), dev_ptrs(dvs), dev_ptrs(Δs), dev_ptrs(os), dev_ptrs(lses),
+        dev_ptrs(qs), dev_ptrs(ks), dev_ptrs(vs),
+        dev_ids(qs), W, dtype_code(T), E, Ll, QH, KH, B, causal, Float32(inv(sqrt(E))),
+        dev_ptrs(wss), nbytes, dev_streams(qs)))
+    foreach(ws -> on_device(() -> release!(ws), ws), wss)
+    return dqs, dks, dvs
+end
+
+ring_flash_attention(qs, ks, vs; causal::Bool) = _ring_flash_attention(qs, ks, vs; causal)[1]
+
+function CRC.rrule(::typeof(ring_flash_attention), qs, ks, vs; causal::Bool)
+    os, lses = _ring_flash_attention(qs, ks, vs; causal)
+    function _pullback(Δs)
+        Δd = [convert(typeof(o), CRC.unthunk(Δ)) for (o, Δ) in zip(os, CRC.unthunk(Δs))]
+        dqs, dks, dvs = ∇ring_flash_attention(Δd, os, lses, qs, ks, vs; causal)
+        return CRC.NoTangent(), dqs, dks, dvs
+    end
+    return os, _pullback
+end
+
+# building blocks for hosts that drive the ring themselves (one process per GPU, NCCL.jl / MPI transport;
+# the Python twin nnop_b200/ring.py does exactly that): fold a partial result, accumulate a partial gradient
+function attn_merge!(o_acc::CuArray{Float32}, lse_acc::CuArray{Float32}, lse_out::CuArray{Float32},
+                     o_part::CuArray{T}, lse_part::CuArray{Float32}; init::Bool) where T <: FloatT
+    check(ccall((:nnop_attn_merge, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Cint, Int64, Cint, Ptr{Cvoid}),
+        ptr(o_acc), ptr(lse_acc), ptr(lse_out), ptr(o_part), ptr(lse_part), dtype_code(T), size(o_part, 1),
+        length(lse_part), init, stream()))
+    return lse_out
+end
+
+function accumulate_f32!(acc::CuArray{Float32}, part::CuArray{T}; init::Bool) where T <: FloatT
+    check(ccall((:nnop_accumulate_f32, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Int64, Cint, Ptr{Cvoid}),
+        ptr(acc), ptr(part), dtype_code(T), length(part), init, stream()))
+    return acc
+end
+
+# out[:, row_offset+1 : row_offset+rows, slab] = T(acc[:, :, slab]) for acc (E, rows, slabs...), out (E, out_rows, slabs...)
+function store_rows_from_f32!(out::CuArray{T}, acc::CuArray{Float32}; row_offset::Integer = 0) where T <: FloatT
+    E, rows = size(acc, 1), size(acc, 2)
+    check(ccall((:nnop_store_rows_from_f32, libnnop_b200), Cint,
+        (CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Int64, Ptr{Cvoid}),
+        ptr(out), ptr(acc), dtype_code(T), E, length(acc) ÷ (E * rows), rows, size(out, 2), row_offset, stream()))
+    return out
 end
 
 # ------------------------------------------------------------------ online softmax (src/softmax.jl:60-86)
@@ -239,7 +363,7 @@ function ∇rms_norm(Δ::CuMatrix{T}, rms, x::CuMatrix{T}, w::CuVector{T}; offse
          Cint, Int64, Int64, Cfloat, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
         ptr(dx), ptr(dw), ptr(Δ), ptr(rms), ptr(x), ptr(w), dtype_code(T), emb, n, offset,
         ptr(ws), nbytes, stream()))
-    CUDA.unsafe_free!(ws)
+    release!(ws)
     return dx, dw
 end
 
@@ -281,7 +405,7 @@ function ∇layer_norm(Δ::CuMatrix{T}, μ, Σ, x::CuMatrix{T}, w::CuVector{T}, 
          CuPtr{Cvoid}, Cint, Int64, Int64, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
         ptr(dx), ptr(dw), ptr(db), ptr(Δ), ptr(μ), ptr(Σ), ptr(x), ptr(w), dtype_code(T), emb, n,
         ptr(ws), nbytes, stream()))
-    CUDA.unsafe_free!(ws)
+    release!(ws)
     return dx, dw, db
 end
 

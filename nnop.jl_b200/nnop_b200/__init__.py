@@ -20,7 +20,7 @@ from .ops import (  # noqa: F401
 from .sharding import shard_slices, shard_attention_inputs  # noqa: F401
 from .ring import (  # noqa: F401
     ring_flash_attention, ring_attention_forward, ring_attention_backward, ring_schedule,
-    zigzag_shard, zigzag_unshard, contiguous_shard,
+    zigzag_shard, zigzag_unshard, contiguous_shard, p2p_ring_attention_forward, p2p_ring_attention_backward,
 )
 
 __all__ = [
@@ -32,6 +32,7 @@ __all__ = [
     "HostAttentionPipeline", "flash_attention_varlen", "_flash_attention_varlen",
     "grad_flash_attention_varlen", "set_bwd_pair_mode", "set_fwd_mode", "ring_flash_attention", "ring_attention_forward",
     "ring_attention_backward", "ring_schedule", "zigzag_shard", "zigzag_unshard", "contiguous_shard",
+    "p2p_ring_attention_forward", "p2p_ring_attention_backward",
 ]
 # the reference spells its pullbacks with a nabla; reachable via getattr(nnop_b200, "∇flash_attention")
 globals().update({

@@ -38,6 +38,7 @@ if not LIB_PATH.exists():
 lib = C.CDLL(str(LIB_PATH))
 
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+_pp, _ip = C.POINTER(C.c_void_p), C.POINTER(C.c_int)   # host arrays: per-rank device pointers / device ids
 # name -> (restype, argtypes); must list every symbol include/nnop_b200.h declares
 SIGNATURES = {
     "nnop_version": (_i, []),
@@ -60,6 +61,10 @@ SIGNATURES = {
     "nnop_attn_merge": (_i, [_vp] * 5 + [_i, _i, _i64, _i, _vp]),
     "nnop_accumulate_f32": (_i, [_vp, _vp, _i, _i64, _i, _vp]),
     "nnop_store_rows_from_f32": (_i, [_vp, _vp, _i, _i] + [_i64] * 4 + [_vp]),
+    "nnop_ring_attn_fwd_workspace_bytes": (_sz, [_i] * 8),
+    "nnop_ring_attn_fwd": (_i, [_pp] * 5 + [_ip] + [_i] * 8 + [_f, _pp, _sz, _pp]),
+    "nnop_ring_attn_bwd_workspace_bytes": (_sz, [_i] * 8),
+    "nnop_ring_attn_bwd": (_i, [_pp] * 9 + [_ip] + [_i] * 8 + [_f, _pp, _sz, _pp]),
     "nnop_softmax_fwd": (_i, [_vp, _vp, _i, _i64, _i64, _vp]),
     "nnop_softmax_bwd": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp]),
     "nnop_rms_norm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i64, _f, _f, _vp]),

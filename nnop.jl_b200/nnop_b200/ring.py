@@ -297,3 +297,62 @@ def ring_flash_attention(q, k, v, *, causal: bool, group=None, backend=None):
     """`flash_attention` over a sequence sharded across the ranks of `group` (differentiable).
     Causal inputs must be in zig-zag order (`zigzag_shard`)."""
     return _RingAttentionFn.apply(q, k, v, bool(causal), group, backend)
+
+
+# ------------------------------------------------------------------------------------------
+# single-process form: all ranks' shards in one process, K / V over NVLink P2P inside the library
+# (nnop_ring_attn_fwd / nnop_ring_attn_bwd, include/nnop_b200.h) -- what a Julia host calls
+# ------------------------------------------------------------------------------------------
+import ctypes as _C
+
+
+def _ptr_array(ts):
+    return (_C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+def _p2p_common(qs, ks, vs):
+    W = len(qs)
+    if not (len(ks) == len(vs) == W and W >= 1):
+        raise NNopError(6, "ring attention: q, k, v must be lists of one tensor per rank")
+    CudaBackend._need_cuda(*qs, *ks, *vs)
+    B, QH, Ll, E = qs[0].shape
+    KH = ks[0].shape[1]
+    for q, k, v in zip(qs, ks, vs):
+        if tuple(q.shape) != (B, QH, Ll, E) or tuple(k.shape) != (B, KH, Ll, E) or k.shape != v.shape:
+            raise NNopError(1, "ring attention: every rank must hold equally shaped shards")
+        if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
+            raise NNopError(6, "ring attention: shards must be contiguous")
+    devs = (_C.c_int * W)(*[q.device.index for q in qs])
+    streams = (_C.c_void_p * W)(*[torch.cuda.current_stream(q.device).cuda_stream for q in qs])
+    return W, B, QH, KH, Ll, E, devs, streams
+
+
+def p2p_ring_attention_forward(qs, ks, vs, *, causal: bool):
+    """Forward over per-rank shards ``qs[r] (B,QH,Ll,E)``, ``ks[r] / vs[r] (B,KH,Ll,E)`` living on (possibly
+    repeated) CUDA devices of this process; causal inputs in zig-zag order.  Returns ``(os, lses)``."""
+    W, B, QH, KH, Ll, E, devs, streams = _p2p_common(qs, ks, vs)
+    dt = ops._dt(qs[0])
+    os_ = [torch.empty_like(q) for q in qs]
+    lses = [torch.empty(B, QH, Ll, dtype=torch.float32, device=q.device) for q in qs]
+    nbytes = lib.nnop_ring_attn_fwd_workspace_bytes(dt, E, Ll, QH, KH, B, W, int(causal))
+    wss = [torch.empty(max(nbytes, 1), dtype=torch.uint8, device=q.device) for q in qs]
+    check(lib.nnop_ring_attn_fwd(_ptr_array(os_), _ptr_array(lses), _ptr_array(qs), _ptr_array(ks), _ptr_array(vs),
+                                 devs, W, dt, E, Ll, QH, KH, B, int(causal), 1.0 / E ** 0.5, _ptr_array(wss), nbytes,
+                                 streams))
+    return os_, lses
+
+
+def p2p_ring_attention_backward(dOs, os_, lses, qs, ks, vs, *, causal: bool):
+    """Backward of `p2p_ring_attention_forward`; returns per-rank ``(dqs, dks, dvs)``."""
+    W, B, QH, KH, Ll, E, devs, streams = _p2p_common(qs, ks, vs)
+    dt = ops._dt(qs[0])
+    dqs = [torch.empty_like(q) for q in qs]
+    dks = [torch.empty_like(k) for k in ks]
+    dvs = [torch.empty_like(v) for v in vs]
+    nbytes = lib.nnop_ring_attn_bwd_workspace_bytes(dt, E, Ll, QH, KH, B, W, int(causal))
+    wss = [torch.empty(max(nbytes, 1), dtype=torch.uint8, device=q.device) for q in qs]
+    dOs = [d.contiguous() for d in dOs]
+    check(lib.nnop_ring_attn_bwd(_ptr_array(dqs), _ptr_array(dks), _ptr_array(dvs), _ptr_array(dOs), _ptr_array(os_),
+                                 _ptr_array(lses), _ptr_array(qs), _ptr_array(ks), _ptr_array(vs), devs, W, dt, E, Ll,
+                                 QH, KH, B, int(causal), 1.0 / E ** 0.5, _ptr_array(wss), nbytes, streams))
+    return dqs, dks, dvs

@@ -103,12 +103,17 @@ def naive_attention(q, k, v, pair=None, *, causal: bool, kpad_mask=None, return_
 
 
 def naive_attention_bwd(dO, q, k, v, pair=None, *, causal: bool, kpad_mask=None,
-                        zero_masked_rows=False):
+                        zero_masked_rows=False, o=None):
     """Closed-form gradients of :func:`naive_attention` (the maths
     the reference realises at src/attention_bwd.jl:86-156 and :182-196):
 
         D = rowsum(dO ∘ O);  dV = Pᵀ dO;  dP = dO Vᵀ;  dS = P ∘ (dP − D);
         dpair = dS;  dQ = E^-1/2 dS K;  dK = E^-1/2 dSᵀ Q   (dK, dV summed over a GQA group)
+
+    ``o``: the forward output the pullback was handed.  The reference's backward is a function of
+    ``(Δ, o, ms, ls, q, k, v)`` (src/attention_bwd.jl:199-206) and its preprocess kernel takes D from
+    THAT ``o`` (src/attention_bwd.jl:182-196), which for 16-bit element types is the rounded forward
+    result; pass it to evaluate the same function of the same arguments.  ``None``: D from the exact P V.
 
     Returns ``(dq, dk, dv, dpair_or_None)``.
     """
@@ -128,8 +133,9 @@ def naive_attention_bwd(dO, q, k, v, pair=None, *, causal: bool, kpad_mask=None,
         p = e / l
     kk = k.repeat_interleave(g, dim=1) if g > 1 else k
     vv = v.repeat_interleave(g, dim=1) if g > 1 else v
-    o = torch.einsum("bhqk,bhke->bhqe", p, vv)
-    D = (dO * o).sum(dim=-1, keepdim=True)
+    if o is None:
+        o = torch.einsum("bhqk,bhke->bhqe", p, vv)
+    D = (dO * o.to(dO.dtype)).sum(dim=-1, keepdim=True)
     dv_full = torch.einsum("bhqk,bhqe->bhke", p, dO)
     dP = torch.einsum("bhqe,bhke->bhqk", dO, vv)
     dS = p * (dP - D)

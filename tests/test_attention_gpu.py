@@ -48,7 +48,11 @@ def _check(nnop, q, k, v, dO, pr, m, causal, tol, expect_path=None):
         or tol > 1e-3
     dq, dk, dv, dpair = nnop.grad_flash_attention(dev(dO), o, lse, dev(q), dev(k), dev(v), dev(pr),
                                                   causal=causal, kpad_mask=dev(m))
-    rq, rk, rv, rp = O.naive_attention_bwd(D(dO), D(q), D(k), D(v), D(pr), causal=causal, kpad_mask=m)
+    # the pullback is a function of (dO, o, lse, q, k, v): for 16-bit T the oracle takes delta = rowsum(dO o)
+    # from the same (rounded) o the kernel was handed, as the reference's preprocess kernel does
+    # (src/attention_bwd.jl:182-196); Float32 keeps the exact o
+    o_arg = o.double().cpu() if tol > 1e-3 else None
+    rq, rk, rv, rp = O.naive_attention_bwd(D(dO), D(q), D(k), D(v), D(pr), causal=causal, kpad_mask=m, o=o_arg)
     # BASELINE.json's bound (1e-4 Float32, 2e-2 16-bit) on the kernel's error: for 16-bit outputs that is the
     # error beyond the final rounding of the result to T (helpers.kernel_err).  Float32
     # keeps the plain max-abs 1e-4, also on the tensor-core path (E = 64): its dK / dV accumulators are

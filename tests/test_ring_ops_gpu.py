@@ -117,3 +117,61 @@ def test_ring_world_size_one_on_one_gpu(nnop, tmp_path, causal):
     rq, rk, rv, _ = O.naive_attention_bwd(D(dO), D(q), D(k), D(v), causal=causal)
     assert max_abs(o, ro) < 2e-2
     assert kernel_err(dq, rq) < 2e-2 and kernel_err(dk, rk) < 2e-2 and kernel_err(dv, rv) < 2e-2
+
+
+def _p2p_case(nnop, W, devices, shape, dtype, causal, tol=2e-2):
+    """W ranks on `devices` (repeats allowed): shard the full problem, run the single-process ring through
+    nnop_ring_attn_fwd / _bwd, gather, compare with the oracle's attention over the FULL sequence."""
+    B, QH, KH, L, E = shape
+    g = torch.Generator().manual_seed(L + W)
+    q, k, v, dO = (torch.randn(B, H, L, E, generator=g).to(dtype) for H in (QH, KH, KH, QH))
+    shard = (lambda t, r: nnop.zigzag_shard(t, r, W)) if causal else (lambda t, r: nnop.contiguous_shard(t, r, W))
+    put = lambda t, r: shard(t, r).to(f"cuda:{devices[r]}")
+    qs, ks, vs, dOs = ([put(t, r) for r in range(W)] for t in (q, k, v, dO))
+    os_, lses = nnop.p2p_ring_attention_forward(qs, ks, vs, causal=causal)
+    dqs, dks, dvs = nnop.p2p_ring_attention_backward(dOs, os_, lses, qs, ks, vs, causal=causal)
+    for d in set(devices):
+        torch.cuda.synchronize(d)
+    gather = (lambda ps: nnop.zigzag_unshard([p.cpu() for p in ps])) if causal else \
+        (lambda ps: torch.cat([p.cpu() for p in ps], dim=2))
+    o, lse, dq, dk, dv = gather(os_), gather([l.unsqueeze(-1) for l in lses]).squeeze(-1), gather(dqs), gather(dks), gather(dvs)
+    D = lambda t: t.double()
+    ro, rl = O.naive_attention(D(q), D(k), D(v), causal=causal, return_lse=True)
+    rq, rk, rv, _ = O.naive_attention_bwd(D(dO), D(q), D(k), D(v), causal=causal, o=D(o) if tol > 1e-3 else None)
+    assert max_abs(o, ro) < tol, "o"
+    assert max_abs(lse, rl) < 1e-3, "lse"
+    assert kernel_err(dq, rq) < tol, "dq"
+    assert kernel_err(dk, rk) < tol, "dk"
+    assert kernel_err(dv, rv) < tol, "dv"
+
+
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("W", [1, 2, 3, 4])
+def test_p2p_ring_virtual_ranks_on_one_gpu(nnop, W, causal):
+    """The C-ABI ring (nnop_ring_attn_fwd / _bwd) with W ranks that all live on device 0: the whole schedule,
+    the double-buffered landing areas, the event graph between compute and copy streams, the strided
+    merges / accumulations and the partial-gradient pushes run exactly as on W GPUs (cudaMemcpyPeerAsync
+    between two buffers of one device is an ordinary copy), so a 1-GPU box checks parity of the path."""
+    _p2p_case(nnop, W, [0] * W, (1, 4, 2, 256 * W, 128), torch.bfloat16, causal)
+    _p2p_case(nnop, W, [0] * W, (2, 2, 2, 192 * W, 64), torch.float16, causal)
+
+
+def test_p2p_ring_float32_and_errors(nnop):
+    _p2p_case(nnop, 2, [0, 0], (1, 2, 1, 256, 32), torch.float32, True, tol=1e-4)
+    q = torch.randn(1, 2, 255, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(nnop.NNopError, match="even local sequence length"):
+        nnop.p2p_ring_attention_forward([q, q], [q, q], [q, q], causal=True)
+    with pytest.raises(nnop.NNopError, match="equally shaped"):
+        nnop.p2p_ring_attention_forward([q, q[:, :, :128]], [q, q], [q, q], causal=False)
+    from nnop_b200._lib import lib
+    assert lib.nnop_ring_attn_fwd_workspace_bytes(2, 128, 1024, 8, 2, 1, 4, 1) > 0
+    assert lib.nnop_ring_attn_bwd_workspace_bytes(2, 128, 1024, 8, 3, 1, 4, 1) == 0    # QH % KH != 0
+
+
+@pytest.mark.parametrize("causal", [True, False])
+def test_p2p_ring_on_all_gpus(nnop, causal):
+    """Real peers: one rank per visible GPU (gpurun --gpus N), K / V and gradient partials over NVLink."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    _p2p_case(nnop, n, list(range(n)), (1, 8, 2, 512 * n, 128), torch.bfloat16, causal)
