@@ -7,8 +7,9 @@
 
 N > 1 is launched by torchrun (one rank per GPU, RANK/LOCAL_RANK/WORLD_SIZE from the env).  The
 path shards over the independent (head, batch) axis with no data-path collective:
-every rank runs its own B=8 slab of a global batch of 8*N ("scaling": "weak"); NCCL is used only
-for the barrier and the max-over-ranks reduction of the device-side time.
+every rank runs its own B=8 slab of a global batch of 8*N ("scaling": "weak"; `--scaling strong`
+shards the one B=8 batch instead, 8/N batch elements per rank); NCCL is used only for the barrier
+and the max-over-ranks reduction of the device-side time.
 
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: the same metric through
 the host-buffer entry point (pinned host q,k,v,dO in; o,dq,dk,dv out; copies inside the timed
@@ -209,8 +210,12 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    strong = args.scaling == "strong"
+    if strong and B % world:
+        raise SystemExit(f"--scaling strong shards the batch of {B} over the ranks: {world} does not divide it")
+    Bl = B // world if strong else B        # batch elements per rank: (head, batch) sharding, batch first
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    mk = lambda h: torch.randn(B, h, L, E, device=dev, dtype=torch.float32, generator=g).to(torch.bfloat16)
+    mk = lambda h: torch.randn(Bl, h, L, E, device=dev, dtype=torch.float32, generator=g).to(torch.bfloat16)
     q, k, v, dO = mk(H), mk(KH), mk(KH), mk(H)
 
     def step():
@@ -240,7 +245,7 @@ def run_ours(args, rank, local_rank, world):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / args.steps
-    f_fwd, f_bwd = flops()
+    f_fwd, f_bwd = flops(Bl)                # per rank
     value = world * (f_fwd + f_bwd) / (ms_step * 1e-3) / 1e12
 
     # ---- end to end through the host-buffer entry point --------------------------------
@@ -269,7 +274,7 @@ def run_ours(args, rank, local_rank, world):
         e2e = {"value": world * (f_fwd + f_bwd) / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                "ms_per_step": ms_e2e,
-               "pipeline": f"{B * (KH // pipe.kv_heads)} chunks of {pipe.kv_heads} kv heads x 1 batch element, "
+               "pipeline": f"{Bl * (KH // pipe.kv_heads)} chunks of {pipe.kv_heads} kv heads x 1 batch element, "
                            f"{len(pipe.slots)} device slots, H2D / compute / D2H on three streams",
                "pinned_host_memory": numa_note[0]}
         del hq, hk, hv, hdO, out, pipe
@@ -282,15 +287,21 @@ def run_ours(args, rank, local_rank, world):
 
     burst, sustained, src = measured_peaks()
     achieved = f_bwd / (kern_ms * 1e-3) / 1e12
-    traffic = None
+    # dram__bytes of the backward main kernel come from a separate `ncu --set full` capture of this same
+    # command (a run under a profiler is never a bench run); the figure is per launch at the weak-scaling
+    # shape (B = 8 per GPU) and is omitted for any other shape
+    traffic, traffic_source = None, None
     tf = ROOT / "profiles" / "roofline_traffic.json"
-    if tf.exists():
+    if tf.exists() and Bl == B:
         try:
-            traffic = json.loads(tf.read_text()).get("attn_bwd_sm100_kernel_dram_bytes_per_launch")
+            tj = json.loads(tf.read_text())
+            traffic = tj.get("attn_bwd_main_dram_bytes_per_launch")
+            traffic_source = tj.get("source")
         except Exception:
             traffic = None
     roofline = {"bound": "tensor", "kernel": "attn_bwd_sm100_persist_kernel<bf16,128>", "achieved": achieved,
                 "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": traffic,
+                "traffic_source": traffic_source,
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "frac_of_burst": achieved / burst, "frac_of_nominal_2250": achieved / 2250.0,
                 "kernel_ms": kern_ms, "algorithmic_flops_per_launch": f_bwd}
@@ -309,19 +320,30 @@ def run_ours(args, rank, local_rank, world):
                "sample": f"{reps} x (B={sb},H={sh}) units of the C2 shape (L={L},E={E},causal), Float32, "
                          "torch-CPU restatement of the reference's naive attention fwd+bwd"}
 
+    # ---- secondary metric: the HBM-bound ops at config C3's shapes, GB/s vs measured copy BW
+    secondary = None
+    if not args.no_secondary:
+        from nnop_b200 import bwbench
+        pk = ROOT / "MEASURED_PEAKS.json"
+        hbm = json.loads(pk.read_text()).get("hbm_gbs", 6548.0) if pk.exists() else 6548.0
+        secondary = {"unit": "GB/s", "peak": hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy)" if pk.exists()
+                     else "fallback", "method": "CUDA-graph replay, buffer sets rotated past the 126 MB L2, "
+                     "algorithmic bytes of SURVEY.md 8(d)", "ops": bwbench.secondary_block(hbm)}
+
     line = {
         "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "C2: BF16 causal E=128 L=8192 H=32 B=8 fwd+bwd per GPU",
-                   "global_batch": B * world, "heads": H, "kv_heads": KH, "seq_len": L, "head_dim": E,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"C2: BF16 causal E=128 L=8192 H=32 B={Bl} fwd+bwd per GPU" +
+                               (f" (B=8 in total, batch-sharded over {world})" if strong else ""),
+                   "global_batch": Bl * world, "heads": H, "kv_heads": KH, "seq_len": L, "head_dim": E,
                    "parallelism": f"(head,batch)-sharded x{world}, no collective",
-                   "l2_policy": "inputs (4 x 537 MB) exceed the 126 MB L2; no flush needed",
+                   "l2_policy": f"inputs (4 x {Bl * 67} MB) exceed the 126 MB L2; no flush needed",
                    "flops_convention": "4*B*H*L^2*E/2 fwd, x2.5 bwd (SURVEY.md 8d)"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": 4 * args.steps * world,
         "gpu_launches_per_step_per_rank": {"attn_fwd_sm100_kernel": 1, "attn_bwd_prep_kernel": 1,
                                            "attn_bwd_sm100_persist_kernel": 1, "attn_bwd_post_kernel": 1},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
         "fwd_bwd_tflops_frac_of_sustained_peak": value / world / sustained,
     }
     print(json.dumps(line), flush=True)
@@ -339,6 +361,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-kv-heads", type=int, default=16, help="kv heads per host-pipeline chunk")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the bandwidth-op block")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: B=8 per GPU (global batch 8*N); strong: the B=8 batch sharded over the N GPUs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -20,6 +20,11 @@ namespace nnop {
 namespace {
 
 constexpr int kThreads = 256;
+// resident CTAs per SM the short-row backward kernels are compiled for (3 => 80 registers and a few spilled
+// bytes in the layer-norm variant: measured slower, 64 vs 53 us at config C3; 2 => 110 registers, none)
+#ifndef NNOP_ROWWISE_BWD_MINB
+#define NNOP_ROWWISE_BWD_MINB 2
+#endif
 
 template <typename T>
 struct VecIO {
@@ -165,121 +170,250 @@ __device__ __forceinline__ float row_max(float v, RedBuf& red, int& parity) {
 }
 
 // ---------------------------------------------------------------------------------------
-// forward kernels (vector path).  MAXV vectors per thread are cached in registers.
-// OP: 0 = softmax, 1 = rms norm, 2 = layer norm
+// packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100: two lanes per issue slot).  The 16-bit
+// kernels below are issue-bound before they are HBM-bound (ncu r02a: layer-norm forward bf16 at 72 %
+// issue-slot utilisation for 38 % of DRAM throughput), so every element-wise step works on pairs.
 // ---------------------------------------------------------------------------------------
-template <typename T, int TPR, int MAXV, int OP>
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)),
+        "l"(reinterpret_cast<const uint64_t&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 f2_dup(float v) { return make_float2(v, v); }
+
+// 16-byte vector <-> NP = VE / 2 float pairs
+template <typename T>
+__device__ __forceinline__ void unpack_pairs(const uint4& v, float2 (&out)[VecIO<T>::N / 2]);
+template <>
+__device__ __forceinline__ void unpack_pairs<float>(const uint4& v, float2 (&out)[2]) {
+  out[0] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+  out[1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
+}
+template <>
+__device__ __forceinline__ void unpack_pairs<__half>(const uint4& v, float2 (&out)[4]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = __half22float2(h[i]);
+}
+template <>
+__device__ __forceinline__ void unpack_pairs<__nv_bfloat16>(const uint4& v, float2 (&out)[4]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+}
+template <typename T>
+__device__ __forceinline__ void store_pairs(T* p, const float2 (&in)[VecIO<T>::N / 2]) {
+  uint4 v;
+  if constexpr (sizeof(T) == 4) {
+    v = make_uint4(__float_as_uint(in[0].x), __float_as_uint(in[0].y), __float_as_uint(in[1].x),
+                   __float_as_uint(in[1].y));
+  } else {
+    v = make_uint4(pack2<T>(in[0].x, in[0].y), pack2<T>(in[1].x, in[1].y), pack2<T>(in[2].x, in[2].y),
+                   pack2<T>(in[3].x, in[3].y));
+  }
+  *reinterpret_cast<uint4*>(p) = v;
+}
+template <typename T>
+__device__ __forceinline__ void load_pairs(const T* p, float2 (&out)[VecIO<T>::N / 2]) {
+  unpack_pairs<T>(*reinterpret_cast<const uint4*>(p), out);
+}
+
+// ---------------------------------------------------------------------------------------
+// forward kernels (vector path).  OP: 0 = softmax, 1 = rms norm, 2 = layer norm.
+// Persistent grid (as many CTAs as are resident); CTA g handles row groups g, g+G, ...  Rows are
+// streamed through a 3-stage cp.async ring in shared memory -- every thread copies exactly the
+// vectors it later reads itself, so the ring needs no block barrier -- which keeps two row groups in
+// flight per CTA while it reduces the current one; w / b stay in registers across rows when the row is
+// short enough (MAXV <= 2), otherwise they are re-read from L1 / L2 per row.
+// ---------------------------------------------------------------------------------------
+template <typename T, int TPR, int MAXV, int OP, bool PERSIST>
 __global__ void __launch_bounds__(kThreads)
 rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict__ stat1,
                 const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b,
                 int64_t emb, int64_t n, float eps, float offset) {
   constexpr int VE = VecIO<T>::N;
+  constexpr int NP = VE / 2;
   constexpr int RPB = kThreads / TPR;
+  constexpr bool kCacheW = PERSIST && OP != 0 && MAXV <= 2;
   __shared__ RedBuf red;
   int parity = 0;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * RPB + threadIdx.x / TPR;
-  if (row >= n) return;  // TPR==256: whole CTA exits together; TPR==32: whole warp
   const int t = threadIdx.x % TPR;
+  const int sub = threadIdx.x / TPR;
   const int nvec = static_cast<int>(emb / VE);
-  const T* xr = x + row * emb;
-  T* yr = y + row * emb;
+  const float inv_n = 1.f / static_cast<float>(emb);
+  const int64_t n_groups = (n + RPB - 1) / RPB;
 
-  float xv[MAXV][VE];
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  float2 wv[kCacheW ? MAXV : 1][NP], bv[(kCacheW && OP == 2) ? MAXV : 1][NP];
+  auto load_wb = [&](int i, float2 (&wo)[NP], float2 (&bo)[NP]) {
     const int vi = t + i * TPR;
-    if (vi < nvec) {
-      load_vec<T>(xr + static_cast<int64_t>(vi) * VE, xv[i]);
-    } else {
+    load_pairs<T>(w + static_cast<int64_t>(vi) * VE, wo);
+    if constexpr (OP == 1) {
 #pragma unroll
-      for (int j = 0; j < VE; ++j) xv[i][j] = (OP == 0) ? -INFINITY : 0.f;
+      for (int j = 0; j < NP; ++j) wo[j] = f2_add(wo[j], f2_dup(offset));
+    }
+    if constexpr (OP == 2) load_pairs<T>(b + static_cast<int64_t>(vi) * VE, bo);
+  };
+  if constexpr (kCacheW) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (t + i * TPR < nvec) {
+        load_wb(i, wv[i], bv[OP == 2 ? i : 0]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) wv[i][j] = bv[OP == 2 ? i : 0][j] = f2_dup(0.f);
+      }
     }
   }
-  const float inv_n = 1.f / static_cast<float>(emb);
 
-  if constexpr (OP == 0) {
-    float m = -INFINITY;
+  extern __shared__ __align__(16) uint8_t ring[];  // PERSIST: [3 stages][MAXV][256 threads] x 16 B
+  auto slot = [&](int st, int i) {
+    return ring + ((static_cast<size_t>(st * MAXV + i) * kThreads + threadIdx.x) << 4);
+  };
+  auto fetch = [&](int64_t g, int st) {
+    const int64_t row = g * RPB + sub;
+    if (g < n_groups && row < n) {
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
-#pragma unroll
-      for (int j = 0; j < VE; ++j) m = fmaxf(m, xv[i][j]);
-    m = row_max<TPR>(m, red, parity);
-    const float ml2 = (m == -INFINITY) ? 0.f : m * 1.4426950408889634f;
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i)
-#pragma unroll
-      for (int j = 0; j < VE; ++j) {
-        xv[i][j] = fast_exp2(fmaf(xv[i][j], 1.4426950408889634f, -ml2));
-        s += xv[i][j];
-      }
-    s = row_sum<TPR>(s, red, parity);
-    const float inv = 1.f / s;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int vi = t + i * TPR;
-      if (vi < nvec) {
-#pragma unroll
-        for (int j = 0; j < VE; ++j) xv[i][j] *= inv;
-        store_vec<T>(yr + static_cast<int64_t>(vi) * VE, xv[i]);
+      for (int i = 0; i < MAXV; ++i) {
+        const int vi = t + i * TPR;
+        if (vi < nvec) cp_async16(slot(st, i), x + row * emb + static_cast<int64_t>(vi) * VE);
       }
     }
-  } else if constexpr (OP == 1) {
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i)
-#pragma unroll
-      for (int j = 0; j < VE; ++j) ss = fmaf(xv[i][j], xv[i][j], ss);
-    ss = row_sum<TPR>(ss, red, parity);
-    const float rstd = rsqrtf(ss * inv_n + eps);
-    if (t == 0) stat0[row] = rstd;
+    cp_async_commit();  // always commit so the group count is uniform
+  };
+  if constexpr (PERSIST) {
+    fetch(blockIdx.x, 0);
+    fetch(static_cast<int64_t>(blockIdx.x) + gridDim.x, 1);
+  }
+  int stage = 0;
+  // !PERSIST: one row group per CTA (grid = n_groups), the row loaded straight into registers
+  for (int64_t g = blockIdx.x; g < n_groups; g += PERSIST ? gridDim.x : n_groups) {
+    const int64_t row = g * RPB + sub;
+    const bool live = row < n;  // TPR==256: uniform per CTA; TPR==32: uniform per warp
+    if constexpr (PERSIST) {
+      fetch(g + 2 * static_cast<int64_t>(gridDim.x), stage == 0 ? 2 : stage - 1);
+      cp_async_wait<2>();  // everything but the two newest groups has landed
+    }
+    float2 xv[MAXV][NP];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      const int vi = t + i * TPR;
-      if (vi < nvec) {
-        float wv[VE];
-        load_vec<T>(w + static_cast<int64_t>(vi) * VE, wv);
+      if (live && t + i * TPR < nvec) {
+        if constexpr (PERSIST)
+          unpack_pairs<T>(*reinterpret_cast<const uint4*>(slot(stage, i)), xv[i]);
+        else
+          load_pairs<T>(x + row * emb + static_cast<int64_t>(t + i * TPR) * VE, xv[i]);
+      } else {
 #pragma unroll
-        for (int j = 0; j < VE; ++j) xv[i][j] = (wv[j] + offset) * xv[i][j] * rstd;
-        store_vec<T>(yr + static_cast<int64_t>(vi) * VE, xv[i]);
+        for (int j = 0; j < NP; ++j) xv[i][j] = f2_dup(OP == 0 ? -INFINITY : 0.f);
       }
     }
-  } else {
-    float s = 0.f;
+    stage = stage == 2 ? 0 : stage + 1;
+    if (!live) continue;  // (no block barrier is used when TPR == 32)
+    T* yr = y + row * emb;
+
+    if constexpr (OP == 0) {
+      float m = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
+      for (int i = 0; i < MAXV; ++i)
 #pragma unroll
-      for (int j = 0; j < VE; ++j) s += xv[i][j];
-    s = row_sum<TPR>(s, red, parity);
-    const float mu = s * inv_n;
-    float ss = 0.f;
+        for (int j = 0; j < NP; ++j) m = fmaxf(m, fmaxf(xv[i][j].x, xv[i][j].y));
+      m = row_max<TPR>(m, red, parity);
+      const float ml2 = (m == -INFINITY) ? 0.f : m * 1.4426950408889634f;
+      const float2 l2e = f2_dup(1.4426950408889634f), nm = f2_dup(-ml2);
+      float2 s2 = f2_dup(0.f);
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int vi = t + i * TPR;
-      if (vi < nvec) {
+      for (int i = 0; i < MAXV; ++i)
 #pragma unroll
-        for (int j = 0; j < VE; ++j) {
-          const float d = xv[i][j] - mu;
-          ss = fmaf(d, d, ss);
+        for (int j = 0; j < NP; ++j) {
+          const float2 a = f2_fma(xv[i][j], l2e, nm);
+          xv[i][j] = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+          s2 = f2_add(s2, xv[i][j]);
+        }
+      const float s = row_sum<TPR>(s2.x + s2.y, red, parity);
+      const float2 inv = f2_dup(1.f / s);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int vi = t + i * TPR;
+        if (vi < nvec) {
+#pragma unroll
+          for (int j = 0; j < NP; ++j) xv[i][j] = f2_mul(xv[i][j], inv);
+          store_pairs<T>(yr + static_cast<int64_t>(vi) * VE, xv[i]);
         }
       }
-    }
-    ss = row_sum<TPR>(ss, red, parity);
-    const float rstd = rsqrtf(ss * inv_n + eps);
-    if (t == 0) {
-      stat0[row] = mu;
-      stat1[row] = rstd;
-    }
+    } else if constexpr (OP == 1) {
+      float2 ss2 = f2_dup(0.f);
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int vi = t + i * TPR;
-      if (vi < nvec) {
-        float wv[VE], bv[VE];
-        load_vec<T>(w + static_cast<int64_t>(vi) * VE, wv);
-        load_vec<T>(b + static_cast<int64_t>(vi) * VE, bv);
+      for (int i = 0; i < MAXV; ++i)
 #pragma unroll
-        for (int j = 0; j < VE; ++j) xv[i][j] = fmaf((xv[i][j] - mu) * rstd, wv[j], bv[j]);
-        store_vec<T>(yr + static_cast<int64_t>(vi) * VE, xv[i]);
+        for (int j = 0; j < NP; ++j) ss2 = f2_fma(xv[i][j], xv[i][j], ss2);
+      const float ss = row_sum<TPR>(ss2.x + ss2.y, red, parity);
+      const float rstd = rsqrtf(ss * inv_n + eps);
+      if (t == 0) stat0[row] = rstd;
+      const float2 r2 = f2_dup(rstd);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int vi = t + i * TPR;
+        if (vi < nvec) {
+          float2 wl[NP], bl[NP];
+          if constexpr (!kCacheW) load_wb(i, wl, bl);
+#pragma unroll
+          for (int j = 0; j < NP; ++j) xv[i][j] = f2_mul(f2_mul(xv[i][j], r2), kCacheW ? wv[i][j] : wl[j]);
+          store_pairs<T>(yr + static_cast<int64_t>(vi) * VE, xv[i]);
+        }
+      }
+    } else {
+      float2 s2 = f2_dup(0.f);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i)
+#pragma unroll
+        for (int j = 0; j < NP; ++j) s2 = f2_add(s2, xv[i][j]);
+      const float mu = row_sum<TPR>(s2.x + s2.y, red, parity) * inv_n;
+      const float2 nmu = f2_dup(-mu);
+      float2 ss2 = f2_dup(0.f);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        if (t + i * TPR < nvec) {  // padding vectors hold 0, not mu: keep them out of the variance
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            xv[i][j] = f2_add(xv[i][j], nmu);
+            ss2 = f2_fma(xv[i][j], xv[i][j], ss2);
+          }
+        }
+      }
+      const float ss = row_sum<TPR>(ss2.x + ss2.y, red, parity);
+      const float rstd = rsqrtf(ss * inv_n + eps);
+      if (t == 0) {
+        stat0[row] = mu;
+        stat1[row] = rstd;
+      }
+      const float2 r2 = f2_dup(rstd);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int vi = t + i * TPR;
+        if (vi < nvec) {
+          float2 wl[NP], bl[NP];
+          if constexpr (!kCacheW) load_wb(i, wl, bl);
+#pragma unroll
+          for (int j = 0; j < NP; ++j)
+            xv[i][j] = f2_fma(f2_mul(xv[i][j], r2), kCacheW ? wv[i][j] : wl[j], kCacheW ? bv[i][j] : bl[j]);
+          store_pairs<T>(yr + static_cast<int64_t>(vi) * VE, xv[i]);
+        }
       }
     }
   }
@@ -345,12 +479,13 @@ rowwise_fwd_generic(T* __restrict__ y, float* __restrict__ stat0, float* __restr
 // partial layout: part0[g][emb] (dw), part1[g][emb] (db, layer norm only), fp32.
 // ---------------------------------------------------------------------------------------
 template <typename T, int TPR, int MAXV, int OP>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (MAXV <= 2 ? NNOP_ROWWISE_BWD_MINB : 1))
 rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict__ part1,
                 const T* __restrict__ dy, const T* __restrict__ x_or_y,
                 const float* __restrict__ stat0, const float* __restrict__ stat1,
                 const T* __restrict__ w, int64_t emb, int64_t n, float offset) {
   constexpr int VE = VecIO<T>::N;
+  constexpr int NP = VE / 2;
   constexpr int RPB = kThreads / TPR;
   __shared__ RedBuf red;
   int parity = 0;
@@ -360,24 +495,24 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
   const float inv_n = 1.f / static_cast<float>(emb);
   const int64_t n_groups = (n + RPB - 1) / RPB;
 
-  float wv[MAXV][VE];
-  float acc0[MAXV][VE];
-  float acc1[(OP == 2) ? MAXV : 1][VE];
+  float2 wv[MAXV][NP];
+  float2 acc0[MAXV][NP];
+  float2 acc1[(OP == 2) ? MAXV : 1][NP];
   if constexpr (OP != 0) {
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int vi = t + i * TPR;
       if (vi < nvec) {
-        load_vec<T>(w + static_cast<int64_t>(vi) * VE, wv[i]);
+        load_pairs<T>(w + static_cast<int64_t>(vi) * VE, wv[i]);
       } else {
 #pragma unroll
-        for (int j = 0; j < VE; ++j) wv[i][j] = 0.f;
+        for (int j = 0; j < NP; ++j) wv[i][j] = f2_dup(0.f);
       }
 #pragma unroll
-      for (int j = 0; j < VE; ++j) {
-        if (OP == 1) wv[i][j] += offset;
-        acc0[i][j] = 0.f;
-        if (OP == 2) acc1[i][j] = 0.f;
+      for (int j = 0; j < NP; ++j) {
+        if (OP == 1) wv[i][j] = f2_add(wv[i][j], f2_dup(offset));
+        acc0[i][j] = f2_dup(0.f);
+        if (OP == 2) acc1[i][j] = f2_dup(0.f);
       }
     }
   }
@@ -405,22 +540,32 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
   };
   fetch(blockIdx.x, 0);
   fetch(static_cast<int64_t>(blockIdx.x) + gridDim.x, 1);
+  // the row's saved statistics (rstd; mean, rstd) are fetched one row group ahead as well: read at the
+  // point of use they were a dependent L2 / HBM round trip at the head of every row's chain
+  auto stat = [&](const float* p, int64_t g) {
+    const int64_t row = g * RPB + sub;
+    return (OP != 0 && p != nullptr && g < n_groups && row < n) ? p[row] : 0.f;
+  };
+  float st0_next = stat(stat0, blockIdx.x), st1_next = OP == 2 ? stat(stat1, blockIdx.x) : 0.f;
   int stage = 0;
   for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
     const int64_t row = g * RPB + sub;
     const bool live = row < n;  // TPR==256: uniform per CTA; TPR==32: uniform per warp
     fetch(g + 2 * static_cast<int64_t>(gridDim.x), stage == 0 ? 2 : stage - 1);
+    const float st0_cur = st0_next, st1_cur = st1_next;
+    st0_next = stat(stat0, g + gridDim.x);
+    if (OP == 2) st1_next = stat(stat1, g + gridDim.x);
     cp_async_wait<2>();  // everything but the two newest groups has landed
-    float av[MAXV][VE], dv[MAXV][VE];
+    float2 av[MAXV][NP], dv[MAXV][NP];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int vi = t + i * TPR;
       if (live && vi < nvec) {
-        unpack_raw<T>(*reinterpret_cast<const uint4*>(slot(stage, 0, i)), av[i]);
-        unpack_raw<T>(*reinterpret_cast<const uint4*>(slot(stage, 1, i)), dv[i]);
+        unpack_pairs<T>(*reinterpret_cast<const uint4*>(slot(stage, 0, i)), av[i]);
+        unpack_pairs<T>(*reinterpret_cast<const uint4*>(slot(stage, 1, i)), dv[i]);
       } else {
 #pragma unroll
-        for (int j = 0; j < VE; ++j) av[i][j] = dv[i][j] = 0.f;
+        for (int j = 0; j < NP; ++j) av[i][j] = dv[i][j] = f2_dup(0.f);
       }
     }
     stage = stage == 2 ? 0 : stage + 1;
@@ -428,73 +573,75 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
     T* dxr = dx + row * emb;
     if constexpr (OP == 0) {
       // dx = y*dy - y*sum(y*dy)              (src/softmax.jl:70-80)
-      float s = 0.f;
+      float2 s2 = f2_dup(0.f);
 #pragma unroll
       for (int i = 0; i < MAXV; ++i)
 #pragma unroll
-        for (int j = 0; j < VE; ++j) s = fmaf(av[i][j], dv[i][j], s);
-      s = row_sum<TPR>(s, red, parity);
+        for (int j = 0; j < NP; ++j) s2 = f2_fma(av[i][j], dv[i][j], s2);
+      const float2 ns = f2_dup(-row_sum<TPR>(s2.x + s2.y, red, parity));
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
         if (vi < nvec) {
 #pragma unroll
-          for (int j = 0; j < VE; ++j) av[i][j] = av[i][j] * (dv[i][j] - s);
-          store_vec<T>(dxr + static_cast<int64_t>(vi) * VE, av[i]);
+          for (int j = 0; j < NP; ++j) av[i][j] = f2_mul(av[i][j], f2_add(dv[i][j], ns));
+          store_pairs<T>(dxr + static_cast<int64_t>(vi) * VE, av[i]);
         }
       }
     } else if constexpr (OP == 1) {
       // dx = r*d*(w+off) - r^3*x*sum(d*(w+off)*x)/N ; dw += d*x*r   (src/rms_norm.jl:72-101)
-      const float r = stat0[row];
-      float dd = 0.f;
+      const float r = st0_cur;
+      float2 dd2 = f2_dup(0.f);
 #pragma unroll
       for (int i = 0; i < MAXV; ++i)
 #pragma unroll
-        for (int j = 0; j < VE; ++j) dd = fmaf(dv[i][j] * wv[i][j], av[i][j], dd);
-      dd = row_sum<TPR>(dd, red, parity);
-      const float c = r * r * r * dd * inv_n;
+        for (int j = 0; j < NP; ++j) dd2 = f2_fma(f2_mul(dv[i][j], wv[i][j]), av[i][j], dd2);
+      const float dd = row_sum<TPR>(dd2.x + dd2.y, red, parity);
+      const float2 r2 = f2_dup(r), nc = f2_dup(-(r * r * r * dd * inv_n));
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
         if (vi < nvec) {
-          float o[VE];
+          float2 o[NP];
 #pragma unroll
-          for (int j = 0; j < VE; ++j) {
-            acc0[i][j] = fmaf(dv[i][j] * av[i][j], r, acc0[i][j]);
-            o[j] = fmaf(r * dv[i][j], wv[i][j], -c * av[i][j]);
+          for (int j = 0; j < NP; ++j) {
+            const float2 dr = f2_mul(dv[i][j], r2);
+            acc0[i][j] = f2_fma(dr, av[i][j], acc0[i][j]);
+            o[j] = f2_fma(dr, wv[i][j], f2_mul(nc, av[i][j]));
           }
-          store_vec<T>(dxr + static_cast<int64_t>(vi) * VE, o);
+          store_pairs<T>(dxr + static_cast<int64_t>(vi) * VE, o);
         }
       }
     } else {
       // xh=(x-mu)r; c1=mean(w d xh); c2=mean(w d); dx=(w d-(xh c1+c2)) r   (src/layer_norm.jl:95-136)
-      const float mu = stat0[row];
-      const float r = stat1[row];
-      float s1 = 0.f, s2 = 0.f;
+      const float mu = st0_cur;
+      const float r = st1_cur;
+      const float2 r2 = f2_dup(r), nmu = f2_dup(-mu);
+      float2 s1 = f2_dup(0.f), s2 = f2_dup(0.f);
 #pragma unroll
       for (int i = 0; i < MAXV; ++i)
 #pragma unroll
-        for (int j = 0; j < VE; ++j) {
-          av[i][j] = (av[i][j] - mu) * r;  // xh
-          const float wd = dv[i][j] * wv[i][j];
-          s1 = fmaf(wd, av[i][j], s1);
-          s2 += wd;
+        for (int j = 0; j < NP; ++j) {
+          av[i][j] = f2_mul(f2_add(av[i][j], nmu), r2);  // xh (padding vectors: w = d = 0 below)
+          const float2 wd = f2_mul(dv[i][j], wv[i][j]);
+          s1 = f2_fma(wd, av[i][j], s1);
+          s2 = f2_add(s2, wd);
         }
-      row_sum2<TPR>(s1, s2, red, parity);
-      s1 *= inv_n;
-      s2 *= inv_n;
+      float c1 = s1.x + s1.y, c2 = s2.x + s2.y;
+      row_sum2<TPR>(c1, c2, red, parity);
+      const float2 nc1 = f2_dup(-c1 * inv_n), nc2 = f2_dup(-c2 * inv_n);
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
         if (vi < nvec) {
-          float o[VE];
+          float2 o[NP];
 #pragma unroll
-          for (int j = 0; j < VE; ++j) {
-            acc0[i][j] = fmaf(dv[i][j], av[i][j], acc0[i][j]);
-            acc1[i][j] += dv[i][j];
-            o[j] = (dv[i][j] * wv[i][j] - fmaf(av[i][j], s1, s2)) * r;
+          for (int j = 0; j < NP; ++j) {
+            acc0[i][j] = f2_fma(dv[i][j], av[i][j], acc0[i][j]);
+            acc1[i][j] = f2_add(acc1[i][j], dv[i][j]);
+            o[j] = f2_mul(f2_fma(dv[i][j], wv[i][j], f2_fma(av[i][j], nc1, nc2)), r2);
           }
-          store_vec<T>(dxr + static_cast<int64_t>(vi) * VE, o);
+          store_pairs<T>(dxr + static_cast<int64_t>(vi) * VE, o);
         }
       }
     }
@@ -508,12 +655,12 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
       const int vi = t + i * TPR;
       if (vi < nvec) {
 #pragma unroll
-        for (int j = 0; j < VE; j += 4) {
-          *reinterpret_cast<float4*>(part0 + prow * emb + static_cast<int64_t>(vi) * VE + j) =
-              make_float4(acc0[i][j], acc0[i][j + 1], acc0[i][j + 2], acc0[i][j + 3]);
+        for (int j = 0; j < NP; j += 2) {
+          *reinterpret_cast<float4*>(part0 + prow * emb + static_cast<int64_t>(vi) * VE + 2 * j) =
+              make_float4(acc0[i][j].x, acc0[i][j].y, acc0[i][j + 1].x, acc0[i][j + 1].y);
           if (OP == 2)
-            *reinterpret_cast<float4*>(part1 + prow * emb + static_cast<int64_t>(vi) * VE + j) =
-                make_float4(acc1[i][j], acc1[i][j + 1], acc1[i][j + 2], acc1[i][j + 3]);
+            *reinterpret_cast<float4*>(part1 + prow * emb + static_cast<int64_t>(vi) * VE + 2 * j) =
+                make_float4(acc1[i][j].x, acc1[i][j].y, acc1[i][j + 1].x, acc1[i][j + 1].y);
         }
       }
     }
@@ -584,21 +731,34 @@ rowwise_bwd_generic(T* __restrict__ dx, float* __restrict__ part0, float* __rest
   }
 }
 
-// out[e] = sum_g part[g][e]; blockDim (32, 8), grid ceil(emb/32)
+// out{0,1}[e] = sum_g part{0,1}[g][e]; blockDim (32, 32), grid (ceil(emb/32), 1 or 2): blockIdx.y picks
+// dw / db, the 32 thread rows walk the partial rows with four independent sums each (the r01 kernel --
+// 8 thread rows, one dependent chain of n_part / 8 loads -- took 8.5-11 us for 5 MB: latency, not bytes)
 template <typename TO>
-__global__ void reduce_partials(TO* __restrict__ out, const float* __restrict__ part,
-                                int64_t n_part, int64_t emb) {
-  __shared__ float sm[8][33];
+__global__ void __launch_bounds__(1024)
+reduce_partials(TO* __restrict__ out0, TO* __restrict__ out1, const float* __restrict__ part0,
+                const float* __restrict__ part1, int64_t n_part, int64_t emb) {
+  __shared__ float sm[32][33];
+  const float* part = blockIdx.y ? part1 : part0;
+  TO* out = blockIdx.y ? out1 : out0;
   const int64_t e = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x;
-  float s = 0.f;
-  if (e < emb)
-    for (int64_t g = threadIdx.y; g < n_part; g += 8) s += part[g * emb + e];
-  sm[threadIdx.y][threadIdx.x] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (e < emb) {
+    int64_t g = threadIdx.y;
+    for (; g + 96 < n_part; g += 128) {
+      s0 += part[g * emb + e];
+      s1 += part[(g + 32) * emb + e];
+      s2 += part[(g + 64) * emb + e];
+      s3 += part[(g + 96) * emb + e];
+    }
+    for (; g < n_part; g += 32) s0 += part[g * emb + e];
+  }
+  sm[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (threadIdx.y == 0 && e < emb) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    for (int i = 0; i < 32; ++i) t += sm[i][threadIdx.x];
     out[e] = from_f32<TO>(t);
   }
 }
@@ -651,26 +811,45 @@ int launch_fwd(void* y, float* s0, float* s1, const void* x, const void* w, cons
   const T* xx = static_cast<const T*>(x);
   const T* ww = static_cast<const T*>(w);
   const T* bb = static_cast<const T*>(b);
-  // smallest register cache (MAXV vectors per thread) that holds the row: fewer registers ->
-  // more resident CTAs -> more bytes in flight
-#define NNOP_FWD_LAUNCH(TPR_, MAXV_, GRID_)                                                    \
-  rowwise_fwd_vec<T, TPR_, MAXV_, OP><<<static_cast<unsigned>(GRID_), kThreads, 0, st>>>(      \
-      yy, s0, s1, xx, ww, bb, emb, n, eps, offset)
+  // smallest register cache (MAXV vectors per thread) that holds the row.  Two launch shapes, chosen
+  // by how many waves the rows make (measured, profiles/r02_perf_rowwise.txt): one row group per CTA
+  // when all of them are resident at once (no CTA then does two rows while another does one) or when
+  // there are so many waves that the tail does not matter and full occupancy (more warps per SM) wins;
+  // in between, a persistent grid of resident CTAs with a cp.async prefetch ring and w / b kept in
+  // registers (no wave quantisation, no per-row reload of the weights).
+  auto run = [&](auto kern_p, auto kern_1, int rows_per_cta, int maxv) {
+    const int smem = 3 * maxv * kThreads * 16;
+    if (smem > 32 * 1024) cudaFuncSetAttribute(kern_p, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int occ_p = 1, occ_1 = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, kern_p, kThreads, smem) != cudaSuccess || occ_p < 1)
+      occ_p = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_1, kern_1, kThreads, 0) != cudaSuccess || occ_1 < 1)
+      occ_1 = 1;
+    if (occ_p > 8) occ_p = 8;
+    const int64_t groups = (n + rows_per_cta - 1) / rows_per_cta;
+    const int64_t cap_p = static_cast<int64_t>(sm_count()) * occ_p, cap_1 = static_cast<int64_t>(sm_count()) * occ_1;
+    if (groups <= cap_1 || groups >= 16 * cap_p) {
+      kern_1<<<static_cast<unsigned>(groups), kThreads, 0, st>>>(yy, s0, s1, xx, ww, bb, emb, n, eps, offset);
+    } else {
+      kern_p<<<static_cast<unsigned>(cap_p), kThreads, smem, st>>>(yy, s0, s1, xx, ww, bb, emb, n, eps, offset);
+    }
+  };
+#define NNOP_FWD(TPR_, MAXV_, RPC_) \
+  run(rowwise_fwd_vec<T, TPR_, MAXV_, OP, true>, rowwise_fwd_vec<T, TPR_, MAXV_, OP, false>, RPC_, MAXV_)
   if (al && nvec <= 32 * 8) {
-    const int64_t grid = (n + 7) / 8;
-    if (nvec <= 32) NNOP_FWD_LAUNCH(32, 1, grid);
-    else if (nvec <= 64) NNOP_FWD_LAUNCH(32, 2, grid);
-    else if (nvec <= 128) NNOP_FWD_LAUNCH(32, 4, grid);
-    else NNOP_FWD_LAUNCH(32, 8, grid);
+    if (nvec <= 32) NNOP_FWD(32, 1, 8);
+    else if (nvec <= 64) NNOP_FWD(32, 2, 8);
+    else if (nvec <= 128) NNOP_FWD(32, 4, 8);
+    else NNOP_FWD(32, 8, 8);
   } else if (al && nvec <= 256 * 8) {
-    if (nvec <= 512) NNOP_FWD_LAUNCH(256, 2, n);
-    else if (nvec <= 1024) NNOP_FWD_LAUNCH(256, 4, n);
-    else NNOP_FWD_LAUNCH(256, 8, n);
+    if (nvec <= 512) NNOP_FWD(256, 2, 1);
+    else if (nvec <= 1024) NNOP_FWD(256, 4, 1);
+    else NNOP_FWD(256, 8, 1);
+#undef NNOP_FWD
   } else {
     rowwise_fwd_generic<T, OP><<<static_cast<unsigned>(n), kThreads, 0, st>>>(
         yy, s0, s1, xx, ww, bb, emb, n, eps, offset);
   }
-#undef NNOP_FWD_LAUNCH
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
 }
@@ -732,11 +911,9 @@ int launch_bwd(void* dx, TW* dw, TW* db, const void* dy, const void* a, const fl
   NNOP_LAUNCH_CHECK();
   if (OP != 0) {
     // every (CTA, sub-row) writes its partial row (zeros if it never saw a live row)
-    const int64_t live_part = n_part;
-    const dim3 blk(32, 8);
-    const unsigned grid = static_cast<unsigned>((emb + 31) / 32);
-    reduce_partials<TW><<<grid, blk, 0, st>>>(dw, p0, live_part, emb);
-    if (OP == 2) reduce_partials<TW><<<grid, blk, 0, st>>>(db, p1, live_part, emb);
+    const dim3 blk(32, 32);
+    const dim3 rgrid(static_cast<unsigned>((emb + 31) / 32), OP == 2 ? 2 : 1);
+    reduce_partials<TW><<<rgrid, blk, 0, st>>>(dw, db, p0, p1, n_part, emb);
     NNOP_LAUNCH_CHECK();
   }
   return NNOP_OK;
