@@ -134,8 +134,8 @@ extern "C" int nnop_set_fwd_mode(int mode) {
   return NNOP_OK;
 }
 extern "C" int nnop_set_bwd_pair_mode(int mode) {
-  if (mode < 0 || (mode > 3 && mode < 101) || mode > 100 + 65535)
-    return fail(NNOP_ERR_ARG, "backward kernel mode must be 0..3 or 100+n");
+  if (mode < 0 || (mode > 4 && mode < 101) || mode > 100 + 65535)
+    return fail(NNOP_ERR_ARG, "backward kernel mode must be 0..4 or 100+n");
   attn_sm100_set_bwd_pair_mode(mode);
   return NNOP_OK;
 }

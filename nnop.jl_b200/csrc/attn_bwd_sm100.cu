@@ -112,7 +112,7 @@ struct BwdSmem {
   static constexpr int kdQs = kdS + 2 * kBox;   // 2 x (128 rows x 32 fp32)
   static constexpr int kStat = kdQs + 2 * 16384;  // lse2[2][128], delta[2][128]
   static constexpr int kBar = kStat + 2048;
-  static constexpr int kNumBars = 28;  // 14 used by the plain kernel, 24 (+ 32 bytes of tile ring) by the persistent one
+  static constexpr int kNumBars = 32;  // 14 used by the plain kernel, 26 (+ 32 bytes of tile ring) by the persistent one
   static constexpr int kTotal = kBar + kNumBars * 8 + 16;
 };
 
@@ -639,12 +639,22 @@ struct PersistBars {
     kSFull = 14, kPFull = 15, kDpFull = 16, kDsFull = 17, kDqFull = 18, kDqEmpty = 19,
     kDkDvFull = 20, kDvEmpty = 21, kDkEmpty = 22,
     kSchedGo = 23,   // producer -> scheduler: the current tile is nearly loaded, claim the next one
-    kCount = 24
+    kXFull = 24,     // DUO: the peer CTA's half of dQ_i has landed in this CTA's staging buffer (4 warp arrivals)
+    kXFree = 25,     // DUO: the peer CTA's staging buffer may be overwritten (1 arrival, from the peer)
+    kCount = 26
   };
 };
 static_assert(PersistBars::kCount + 4 <= BwdSmem<128>::kNumBars, "barrier area too small for the tile ring");
 
-template <typename T, int D>
+// DUO = true (launched as clusters of two CTAs): the pair shares one tile record (batch, kv head, PAIR of
+// kv blocks 2*jp, 2*jp + 1); CTA r of the pair owns kv block 2*jp + r and both walk the same q blocks
+// i >= 2*jp (CTA 1's first causal step lies above its diagonal: fully masked, contributes zeros).  Each
+// CTA's dQ_i partial is halved by columns: the half the peer reduces goes straight from registers into
+// the peer's staging buffer over distributed shared memory, the other half is summed with what the peer
+// sent and leaves in ONE bulk reduce-add of half the width -- the fp32 read-modify-write traffic into L2
+// (148 SMs x 64 KB per step, the 650-clk item of profiles/r01c_bwd_knockouts.txt) is cut in two.  The MMA
+// chain never waits on the peer: the drain warpgroup releases dQ's TMEM columns before it exchanges.
+template <typename T, int D, bool DUO = false>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
                               const __grid_constant__ CUtensorMap tm_k,
@@ -673,14 +683,16 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int g = p.QH / p.KH;
-  const bool packed = p.cu_q != nullptr;
+  const bool packed = !DUO && p.cu_q != nullptr;
+  const uint32_t crank = DUO ? cluster_ctarank() : 0u;   // CTA of the pair (DUO), else 0
 
   // everything a role needs to know about a tile, derived from its ring record
   struct Tile {
     int b, j, hk, k0, QL, KL, q_off, k_off, st_off, i0, nqi, n_it, bh_kv;
   };
-  auto make_tile = [&](int zb, int j, int hk) -> Tile {
+  auto make_tile = [&](int zb, int jrec, int hk) -> Tile {
     Tile t;
+    const int j = DUO ? 2 * jrec + static_cast<int>(crank) : jrec;   // DUO: the record names the pair
     t.j = j; t.hk = hk; t.k0 = j * 128;
     if (packed) {
       t.q_off = p.cu_q[zb];
@@ -693,11 +705,20 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
       t.b = zb; t.QL = p.QL; t.KL = p.KL; t.q_off = 0; t.k_off = 0; t.st_off = 0;
     }
     const int nq = (t.QL + 127) >> 7;
-    t.i0 = p.causal ? j : 0;
+    t.i0 = p.causal ? (DUO ? 2 * jrec : j) : 0;   // DUO: both CTAs walk the q blocks of the pair's first kv block
     t.nqi = nq > t.i0 ? nq - t.i0 : 0;
     t.n_it = t.nqi * g;
     t.bh_kv = t.b * p.KH + hk;
     return t;
+  };
+  // consumers of a tile record release its ring slot to the scheduler, which lives in CTA 0 of a pair
+  auto release_tile_slot = [&](int slot) {
+    if (DUO && crank != 0) mbar_arrive_cluster(bars + PB::kTileEmpty + slot, 0);
+    else mbar_arrive(bars + PB::kTileEmpty + slot);
+  };
+  auto wait_tile_full = [&](int slot, uint32_t parity) {
+    if constexpr (DUO) mbar_wait_cluster(bars + PB::kTileFull + slot, parity);   // record written by CTA 0 over DSMEM
+    else mbar_wait(bars + PB::kTileFull + slot, parity);
   };
 
   if (threadIdx.x == 0) {
@@ -714,9 +735,9 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
     tma_prefetch_desc(&tm_dv);
     for (int i = 0; i < PB::kCount; ++i) {
       uint32_t cnt = 1;
-      if (i == PB::kTileEmpty || i == PB::kTileEmpty + 1) cnt = 14;  // TMA + MMA + 8 compute + 4 drain
+      if (i == PB::kTileEmpty || i == PB::kTileEmpty + 1) cnt = DUO ? 28 : 14;  // TMA + MMA + 8 compute + 4 drain (per CTA)
       if (i == PB::kPFull || i == PB::kDsFull) cnt = 8;              // one arrival per compute warp
-      if (i == PB::kDqEmpty || i == PB::kDvEmpty || i == PB::kDkEmpty) cnt = 4;  // per drain warp
+      if (i == PB::kDqEmpty || i == PB::kDvEmpty || i == PB::kDkEmpty || i == PB::kXFull) cnt = 4;  // per drain warp
       mbar_init(bars + i, cnt);
     }
     fence_mbar_init();
@@ -725,25 +746,26 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (DUO) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 256 + D;
 
   // every consumer role fetches the n-th tile record the same way (false = queue empty)
   auto next_tile = [&](int n, Tile& t) -> bool {
     const int slot = n & 1;
-    mbar_wait(bars + PB::kTileFull + slot, (n >> 1) & 1);
+    wait_tile_full(slot, (n >> 1) & 1);
     const int zb = s_tile[4 * slot], j = s_tile[4 * slot + 1], hk = s_tile[4 * slot + 2];
     const int flag = s_tile[4 * slot + 3];
     __syncwarp();
-    if (lane == 0) mbar_arrive(bars + PB::kTileEmpty + slot);
+    if (lane == 0) release_tile_slot(slot);
     if (flag < 0) return false;
     t = make_tile(zb, j, hk);
     return true;
   };
 
   if (warp < 4) {
-    setmaxnreg_dec<88>();
-    if (warp == 3) {
+    if constexpr (DUO) setmaxnreg_dec<64>(); else setmaxnreg_dec<88>();   // DUO: the drain warpgroup holds all of dQ_i while it exchanges
+    if (warp == 3 && crank == 0) {
       // ================================ tile scheduler ===============================
       // The whole warp runs it (uniformly); lane 0 claims and publishes.  Dense: tile t = ((b * KH +
       // hk) * nkv + j).  Packed: sequence z by binary search in tile_pre, then hk-major, j fastest.
@@ -805,6 +827,11 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
         }
         if (lane == 0) {
           s_tile[4 * slot] = zb; s_tile[4 * slot + 1] = j; s_tile[4 * slot + 2] = hk; s_tile[4 * slot + 3] = flag;
+          if constexpr (DUO) {   // the same record into the peer's ring, then its tile_full (release at cluster scope)
+            st_cluster_v4(mapa_u32(smem_u32(const_cast<int*>(s_tile) + 4 * slot), 1), static_cast<uint32_t>(zb),
+                          static_cast<uint32_t>(j), static_cast<uint32_t>(hk), static_cast<uint32_t>(flag));
+            mbar_arrive_cluster(bars + PB::kTileFull + slot, 1);
+          }
           mbar_arrive(bars + PB::kTileFull + slot);
         }
         if (flag < 0) break;
@@ -815,10 +842,10 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
         int gs = 0;
         for (int tl = 0;; ++tl) {
           const int slot = tl & 1;
-          mbar_wait(bars + PB::kTileFull + slot, (tl >> 1) & 1);
+          wait_tile_full(slot, (tl >> 1) & 1);
           const int zb = s_tile[4 * slot], tj = s_tile[4 * slot + 1], thk = s_tile[4 * slot + 2];
           const int flag = s_tile[4 * slot + 3];
-          mbar_arrive(bars + PB::kTileEmpty + slot);
+          release_tile_slot(slot);
           if (flag < 0) break;
           const Tile ti = make_tile(zb, tj, thk);
           const int hk = ti.hk, b = ti.b, k0 = ti.k0, bh_kv = ti.bh_kv, i0 = ti.i0, nqi = ti.nqi, n_it = ti.n_it;
@@ -848,7 +875,7 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
               tma_load_3d(sdO + bx * S::kBox, &tm_do, bars + PB::kDoFull, bx * 64, q_off + q0, bh_q);
           };
           const int go_at = n_it > 2 ? n_it - 2 : 0;  // step whose loads trigger the next claim
-          if (go_at == 0) mbar_arrive(bars + PB::kSchedGo);
+          if (go_at == 0 && crank == 0) mbar_arrive(bars + PB::kSchedGo);
           // in the order the previous tile releases them: V, Q ring slot, dO, K
           mbar_wait(bars + PB::kVEmpty, (tl & 1) ^ 1);
           mbar_arrive_expect_tx(bars + PB::kVFull, S::kTile);
@@ -864,7 +891,7 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
             tma_load_3d(sK + bx * S::kBox, &tm_k, bars + PB::kKFull, bx * 64, k_off + k0, bh_kv);
           if (n_it > 1) load_q(1);
           for (int it = 1; it < n_it; ++it) {
-            if (it == go_at) mbar_arrive(bars + PB::kSchedGo);
+            if (it == go_at && crank == 0) mbar_arrive(bars + PB::kSchedGo);
             load_do(it);
             if (it + 1 < n_it) load_q(it + 1);
           }
@@ -1071,6 +1098,10 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
           for (int c = 0; c < 64; ++c)
             if (row > c0 + c) pf[c] = 0.f;
         }
+        if (DUO && p.causal && i < j) {  // CTA 1 of a pair, first step: the whole block lies above the diagonal
+#pragma unroll
+          for (int c = 0; c < 64; ++c) pf[c] = 0.f;
+        }
         if (key_dead) {
 #pragma unroll
           for (int c = 0; c < 64; ++c) pf[c] = 0.f;
@@ -1128,7 +1159,7 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
     }
   } else {
     // ========================= dQ drain + dK / dV epilogue warpgroup ====================
-    setmaxnreg_inc<152>();
+    if constexpr (DUO) setmaxnreg_inc<176>(); else setmaxnreg_inc<152>();
     const int wq = warp & 3;
     const int row = wq * 32 + lane;  // query row (dQ) / key row (dK, dV) within the block
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
@@ -1154,6 +1185,56 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + PB::kDqEmpty);
 #ifndef NNOP_BWD_NO_DQ   // (timing experiments: knock out the dQ staging + bulk reduce)
+        if constexpr (DUO) {
+          // This CTA reduces columns [crank * D/2, +D/2) of dQ_i for BOTH kv blocks of the pair; the other
+          // half of its partial goes to the peer.  X = the 32 KB staging buffer: landing area for the peer's
+          // half, then (summed in place) the source of the bulk reduce-add.
+          constexpr int NCH = D / 64;   // 32-column (16 KB) boxes per half
+          const uint32_t peer = crank ^ 1u;
+          if (issuer) {                 // my X has been read by its last bulk op: the peer may overwrite it
+            bulk_wait_read<0>();
+            mbar_arrive_cluster(bars + PB::kXFree, peer);
+          }
+          mbar_wait_cluster(bars + PB::kXFree, gi & 1);   // ... and the peer's X is free for my half
+          const uint32_t xpeer = mapa_u32(smem_u32(sdQ), peer);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int u4 = 0; u4 < 8; ++u4) {
+              const uint32_t off = c * 16384 + row * 128 + ((u4 ^ (row & 7)) << 4);
+              if (crank == 0)   // (static register indices in both branches: no local-memory indexing)
+                st_cluster_v4(xpeer + off, r[NCH + c][4 * u4], r[NCH + c][4 * u4 + 1], r[NCH + c][4 * u4 + 2],
+                              r[NCH + c][4 * u4 + 3]);
+              else
+                st_cluster_v4(xpeer + off, r[c][4 * u4], r[c][4 * u4 + 1], r[c][4 * u4 + 2], r[c][4 * u4 + 3]);
+            }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(bars + PB::kXFull, peer);
+          mbar_wait_cluster(bars + PB::kXFull, gi & 1);   // the peer's half of MY columns has landed in X
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int u4 = 0; u4 < 8; ++u4) {
+              float4* xp = reinterpret_cast<float4*>(sdQ + c * 16384 + row * 128 + ((u4 ^ (row & 7)) << 4));
+              float4 v = *xp;
+              if (crank == 0) {
+                v.x += __uint_as_float(r[c][4 * u4]); v.y += __uint_as_float(r[c][4 * u4 + 1]);
+                v.z += __uint_as_float(r[c][4 * u4 + 2]); v.w += __uint_as_float(r[c][4 * u4 + 3]);
+              } else {
+                v.x += __uint_as_float(r[NCH + c][4 * u4]); v.y += __uint_as_float(r[NCH + c][4 * u4 + 1]);
+                v.z += __uint_as_float(r[NCH + c][4 * u4 + 2]); v.w += __uint_as_float(r[NCH + c][4 * u4 + 3]);
+              }
+              *xp = v;
+            }
+          fence_proxy_async_smem();
+          named_bar_sync(3, 128);
+          if (issuer) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+              tma_reduce_add_3d(&tm_dqa, sdQ + c * 16384, static_cast<int>(crank) * (D / 2) + c * 32, q_off + q0, bh_q);
+            bulk_commit();
+          }
+        } else {
 #pragma unroll
         for (int c = 0; c < D / 32; ++c) {
           uint8_t* stage = sdQ + (nred & 1) * 16384;
@@ -1181,6 +1262,7 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
           }
 #endif
           ++nred;
+        }
         }
 #endif
       }
@@ -1251,6 +1333,7 @@ attn_bwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
   // ---- teardown -------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if constexpr (DUO) cluster_sync_all();   // no CTA leaves while its peer may still write into it / arrive on it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -1927,9 +2010,36 @@ int launch_bwd(const AttnParams& a) {
   const int num_sms = sm_count();
   const bool persist_ok = !bias && a.kpad == nullptr && (packed || !a.causal || nq_blocks >= nkv) &&
                           n_tiles < (1LL << 30);
-  const bool use_persist = !use_pair && persist_ok &&
+  // 4 = persistent CTA pairs that exchange dQ halves over distributed shared memory (one L2 reduce-add of
+  // half the width per CTA and step); dense problems with at least two kv blocks
+  const bool use_duo = !use_pair && persist_ok && !packed && nkv >= 2 && mode == 4;
+  const bool use_persist = !use_pair && !use_duo && persist_ok &&
                            (mode == 3 || mode >= 100 || (mode == 0 && n_tiles >= 2LL * num_sms));
-  if (use_pair) {
+  if (use_duo) {
+    auto kern = attn_bwd_sm100_persist_kernel<T, D, true>;
+    NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    const int npairs = (nkv + 1) / 2;
+    const int64_t n_pair_tiles = static_cast<int64_t>(npairs) * a.KH * a.B;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kBwdThreads); cfg.dynamicSmemBytes = S::kTotal; cfg.stream = a.stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(2 * (num_sms / 2));
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+      (void)cudaGetLastError();
+      max_clusters = num_sms / 2;
+    }
+    const int64_t clusters = n_pair_tiles < max_clusters ? n_pair_tiles : max_clusters;
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+    const int n_t = static_cast<int>(n_pair_tiles);
+    timing_begin(1, a.stream);
+    NNOP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, tdo, tdk, tdv, tdqa, bp, tile_counter, n_t, npairs));
+    timing_end(1, a.stream);
+    NNOP_LAUNCH_CHECK();
+  } else if (use_pair) {
     if constexpr (D == 128) {
       alignas(64) CUtensorMap tq64, tdo64;
       if (int rc = make_tmap_3d(&tq64, a.q, a.dtype, D, rows_q, bhq, 64, 64)) return rc;

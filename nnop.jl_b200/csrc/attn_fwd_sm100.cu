@@ -258,7 +258,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    setmaxnreg_dec<80>();  // 128*80 + 256*208 = 63488 <= 64K registers
+    setmaxnreg_dec<96>();  // 128*96 + 256*208 = 65536 = 64K registers (at 80 the issuer warp spilled: 152 / 348 B)
     if (warp == 0 && lane == 0 && nblk > 0) {
       // ================================ TMA producer =================================
       mbar_arrive_expect_tx(&q_full[0], S::kTileBytes);
@@ -885,7 +885,7 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
   };
 
   if (warp < 4) {
-    setmaxnreg_dec<80>();
+    setmaxnreg_dec<96>();
     if (warp == 3) {
       // ================================ tile scheduler ===============================
       // Dense: tile t = (batch * QH + head) * nqt + r.  Packed: sequences in order, within a sequence

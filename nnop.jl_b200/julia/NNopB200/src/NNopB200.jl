@@ -323,6 +323,10 @@ function online_softmax(x::CuMatrix{T}) where T <: FloatT
 end
 
 function ∇online_softmax(Δ::CuMatrix{T}, y::CuMatrix{T}) where T <: FloatT
+    if within_gradient(y)      # second-order AD: stay differentiable, exactly as the reference (src/softmax.jl:71-74)
+        tmp = Δ .* y
+        return tmp .- y .* sum(tmp; dims=1)
+    end
     dx = similar(y)
     check(ccall((:nnop_softmax_bwd, libnnop_b200), Cint,
         (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}),

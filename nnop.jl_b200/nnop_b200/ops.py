@@ -290,6 +290,31 @@ def grad_online_softmax(dy, y):
     return dx
 
 
+class _SoftmaxBwdFn(torch.autograd.Function):
+    """`∇online_softmax(Δ, y)` as a differentiable node, so that second-order AD works as in the reference,
+    whose pullback switches to plain differentiable broadcasts when it is itself being differentiated
+    (`within_gradient(y)`, src/softmax.jl:70-74).  First order: the fused kernel.  Its own pullback, for an
+    upstream cotangent g of dx = y∘(Δ − s), s = Σ y∘Δ:
+        dΔ = y∘(g − a),  a = Σ y∘g      -- the same operator applied to g: the fused kernel again
+        dy = g∘(Δ − s) − a·Δ            -- element-wise + two row sums (torch ops stand in for the GPUArrays
+                                           broadcasts the reference uses on this path)"""
+
+    @staticmethod
+    def forward(ctx, dy, y):
+        ctx.save_for_backward(dy, y)
+        return grad_online_softmax(dy.contiguous(), y)
+
+    @staticmethod
+    def backward(ctx, g):
+        dy, y = ctx.saved_tensors
+        g = g.contiguous()
+        d_dy = grad_online_softmax(g, y)
+        yf, gf, df = y.float(), g.float(), dy.float()
+        s = (yf * df).sum(dim=-1, keepdim=True)
+        a = (yf * gf).sum(dim=-1, keepdim=True)
+        return d_dy, (gf * (df - s) - a * df).to(y.dtype)
+
+
 class _SoftmaxFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -300,6 +325,8 @@ class _SoftmaxFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         (y,) = ctx.saved_tensors
+        if torch.is_grad_enabled() and (dy.requires_grad or y.requires_grad):
+            return _SoftmaxBwdFn.apply(dy, y)   # being differentiated again (create_graph=True)
         return grad_online_softmax(dy.contiguous(), y)
 
 

@@ -1,5 +1,5 @@
 """A/B timing of the backward kernel variants (nnop_set_bwd_pair_mode) inside one process:
-2 = one CTA per tile, 3 = persistent.  Interleaved repeats, CUDA events, backward only."""
+2 = one CTA per tile, 3 = persistent, 4 = persistent CTA pairs exchanging dQ halves (DUO).  Interleaved repeats, CUDA events, backward only."""
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -34,6 +34,9 @@ def run(B, H, KH, L, E, causal, modes=(2, 3), iters=5, rounds=3, dtype=torch.bfl
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:   # python scripts/perf_bwd_modes.py 3,4  -> compare these modes
+        import functools
+        run = functools.partial(run, modes=tuple(int(x) for x in sys.argv[1].split(",")))
     run(8, 32, 32, 8192, 128, True)
     run(4, 32, 8, 8192, 128, True)
     run(8, 32, 32, 2048, 128, True)

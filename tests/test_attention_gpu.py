@@ -521,3 +521,33 @@ def test_automatic_kernel_choice_is_transparent(nnop, E, L):
     assert torch.equal(o, o_ref) and torch.equal(lse, lse_ref)
     assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
     assert max_abs(got[0], ref[0]) <= 2 ** -7 * max(1.0, ref[0].abs().max().item())
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("E", [64, 128])
+def test_duo_backward_matches_one_cta_per_tile(nnop, causal, E):
+    """Backward mode 4: persistent CTA pairs (clusters of two) that own kv blocks (2jp, 2jp+1), walk the same
+    q blocks and exchange halves of their dQ_i partials over distributed shared memory, so that each CTA
+    issues one L2 reduce-add of half the width.  dK / dV keep the per-tile summation order (CTA 1's extra,
+    fully masked first causal step adds exact zeros): bit for bit; dQ up to the order of its fp32 adds.
+    Shapes cover an odd number of kv blocks (the last pair's second block is out of range), ragged lengths,
+    QL != KL, GQA and many tiles per cluster."""
+    try:
+        for trial, (B, QH, KH, QL, KL) in enumerate([(1, 1, 1, 512, 256), (2, 4, 2, 1024, 1024), (1, 2, 2, 300, 700),
+                                                     (1, 2, 1, 1000, 1000), (3, 2, 2, 640, 640), (1, 1, 1, 384, 384),
+                                                     (2, 3, 3, 257, 257), (1, 6, 2, 2048, 2048), (4, 8, 8, 1536, 1536)]):
+            if causal and QL != KL:
+                continue
+            dtype = torch.bfloat16 if trial % 2 == 0 else torch.float16
+            q, k, v, dO, _, _ = _inputs(B, QH, KH, QL, KL, E, dtype, 400 + trial)
+            qd, kd, vd, dOd = q.cuda(), k.cuda(), v.cuda(), dO.cuda()
+            o, lse = nnop._flash_attention(qd, kd, vd, causal=causal)
+            nnop.set_bwd_pair_mode(2)
+            ref = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=causal)
+            nnop.set_bwd_pair_mode(4)
+            for rep in range(2):
+                got = nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=causal)
+                assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]), (rep, B, QH, KH, QL, KL)
+                assert max_abs(got[0], ref[0]) <= 2 ** -7 * max(1.0, ref[0].abs().max().item()), (B, QH, KH, QL, KL)
+    finally:
+        nnop.set_bwd_pair_mode(0)

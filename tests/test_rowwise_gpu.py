@@ -147,3 +147,26 @@ def test_softmax_rows_sum_to_one_at_bench_size(nnop):
     assert torch.equal(y.argmax(-1), x.argmax(-1))
     # shift invariance
     assert (nnop.online_softmax(x + 3.0) - y).abs().max().item() < 1e-6
+
+
+def test_softmax_second_order(nnop):
+    """Second-order AD through `online_softmax` (the reference keeps its pullback differentiable when it is
+    itself under differentiation: `within_gradient(y)`, src/softmax.jl:70-74): the gradient of a function of
+    the first gradient, against torch autograd on the oracle's fp64 softmax."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(7, 257, generator=g)
+    w = torch.randn(7, 257, generator=g)
+    u = torch.randn(7, 257, generator=g)
+
+    def second(xx, softmax, ww, uu):
+        y = softmax(xx)
+        (gx,) = torch.autograd.grad((y * ww).sum(), xx, create_graph=True)   # first-order gradient, kept in the graph
+        (hx,) = torch.autograd.grad((gx * uu).sum() + (gx * gx).sum(), xx)
+        return gx.detach(), hx
+
+    xr = x.double().requires_grad_(True)
+    g_ref, h_ref = second(xr, O.naive_softmax, w.double(), u.double())
+    xd = x.cuda().requires_grad_(True)
+    g_got, h_got = second(xd, nnop.online_softmax, w.cuda(), u.cuda())
+    assert max_abs(g_got, g_ref) < 1e-6
+    assert max_abs(h_got, h_ref) < 1e-5
