@@ -15,6 +15,11 @@
  *  - Return value: 0 (NNOP_OK) on success, otherwise an nnop_status_t; a human-readable
  *    message for the calling thread is available from nnop_last_error_string().
  *  - dtype: element type T of q/k/v/x...; softmax statistics, lse, rstd, mean are float.
+ *  - State: none.  The library keeps no device memory and no mutable process state behind these entry
+ *    points (scratch, including the tile counters of the persistent kernels, lives in the caller's
+ *    workspace); every call may run concurrently with any other on any stream.  The process-wide kernel
+ *    selection switches and the measurement hooks used by tests and A/B timing are NOT part of this ABI:
+ *    they are declared in nnop_b200_diag.h.
  */
 #ifndef NNOP_B200_H
 #define NNOP_B200_H
@@ -57,32 +62,6 @@ const char* nnop_last_error_string(void);
 /* Replaces NNop.shared_memory / _shared_memory (src/NNop.jl:27-30, ext/NNopCUDAExt.jl:6-9). */
 int nnop_device_info(int device, nnop_device_info_t* out);
 
-/* Attention kernel selection (diagnostics / tests).  0 = auto (tcgen05 path whenever the
- * problem qualifies), 1 = force the generic SIMT path, 2 = require the tcgen05 path (returns
- * NNOP_ERR_ARG if the problem does not qualify).  Process-wide. */
-int nnop_set_attention_path(int mode);
-/* 1 if the last flash-attention call on this thread ran the tcgen05 path, else 0. */
-int nnop_last_attention_path(void);
-/* Backward kernel selection on the tcgen05 path (diagnostics / A-B timing), process-wide; env
- * NNOP_BWD_PAIR gives the initial value.  0 (default): automatic -- dense problems without a key
- * padding mask whose tile queue is at least two rounds deep run the persistent kernel (one CTA per
- * SM, dynamic queue of (kv block, kv head, batch) tiles, epilogue overlapped with the next tile),
- * everything else one CTA per tile; 1: E = 128 dense problems run the experimental CTA-pair kernel
- * (tcgen05 cta_group::2; same results, currently slower); 2: always one CTA per tile; 3: persistent
- * wherever eligible; 100+n: persistent on n CTAs (tests).  dK / dV are bit-identical across modes. */
-int nnop_set_bwd_pair_mode(int mode);
-/* Forward kernel selection on the tcgen05 path (diagnostics / A-B timing), process-wide; env
- * NNOP_FWD_MODE gives the initial value.  0 (default): automatic -- dense 16-bit problems without
- * key padding mask or pair bias whose queue of (256-row q tile, head, batch) tiles is at least two
- * rounds deep and whose tiles are short enough for the per-tile fixed cost to matter (E = 64, or
- * QL <= 2048) run the persistent kernel (one CTA per SM, dynamic tile queue, Q / K / V of the next
- * tile loaded under the current one, O stored through private staging); 1: always one CTA per q
- * tile; 2: persistent wherever eligible; 100+n: persistent on n CTAs (tests).  O and lse are
- * bit-identical across modes.  The persistent forward keeps its tile counter in one of 256 library-owned
- * device slots, taken round-robin and zeroed on the call's stream: calls on one stream never share a
- * live slot; do not replay one captured CUDA graph containing it on several streams at once. */
-int nnop_set_fwd_mode(int mode);
-
 /* ---------------------------------------------------------------------------------------
  * flash attention forward.  Replaces `_flash_attention` + kernel `_flash_attention_fwd!`
  * (src/attention.jl:133-177, :1-131).
@@ -103,7 +82,9 @@ int nnop_flash_attn_fwd(void* o, float* lse, const void* q, const void* k, const
                         int KL, int QH, int KH, int B, int causal, float scale, void* stream);
 
 /* Forward with an optional caller-owned workspace.  With a workspace of at least
- * nnop_flash_attn_fwd_workspace_bytes(...) bytes (256-byte aligned), Float32 problems with E = 64
+ * nnop_flash_attn_fwd_workspace_bytes(...) bytes (256-byte aligned), 16-bit problems whose tile queue is deep
+ * and short-tiled enough may run the persistent forward kernel (its tile counter lives in the workspace;
+ * O and lse are bit-identical either way), and Float32 problems with E = 64
  * run on the tensor cores: q, k, v are split into two fp16 terms each (x ~ hi + lo,
  * 22 significant bits), S = Qh Kh^T + Qh Kl^T + Ql Kh^T and O = (Ph + Pl)(Vh + Vl) accumulate in fp32;
  * max abs error vs an fp64 evaluation stays below 1e-4.  Without it (or for other shapes) the call
@@ -167,6 +148,14 @@ int nnop_flash_attn_varlen_fwd(void* o, float* lse, const void* q, const void* k
                                int max_seqlen_q, int max_seqlen_k, int64_t total_q, int64_t total_k,
                                int dtype, int E, int QH, int KH, int causal, float scale,
                                void* stream);
+/* Same with a caller-owned workspace (>= nnop_flash_attn_varlen_fwd_workspace_bytes, 256-byte aligned):
+ * batches of short sequences then run the persistent forward kernel, whose tile counter lives there. */
+size_t nnop_flash_attn_varlen_fwd_workspace_bytes(int dtype, int E, int nseq, int64_t total_q, int QH);
+int nnop_flash_attn_varlen_fwd_ws(void* o, float* lse, const void* q, const void* k, const void* v,
+                                  const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int nseq,
+                                  int max_seqlen_q, int max_seqlen_k, int64_t total_q, int64_t total_k,
+                                  int dtype, int E, int QH, int KH, int causal, float scale,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 size_t nnop_flash_attn_varlen_bwd_workspace_bytes(int dtype, int E, int nseq, int64_t total_q,
                                                   int QH);
 int nnop_flash_attn_varlen_bwd(void* dq, void* dk, void* dv, const void* dO, const void* o,
@@ -274,24 +263,6 @@ int nnop_layer_norm_bwd(void* dx, void* dw, void* db, const void* dy, const floa
 int nnop_llama_rope(void* q_out, void* k_out, const void* q_in, const void* k_in,
                     const float* cos, const float* sin, int dtype, int E, int64_t L, int QH,
                     int KH, int B, float sin_sign, void* stream);
-
-/* ---------------------------------------------------------------------------------------
- * Measurement hook (bench.py): the next tcgen05 attention launch of kind `which` (0 = forward
- * kernel, 1 = backward main kernel) made by the calling thread records `start_event` right
- * before and `stop_event` right after that one kernel, on the launch stream.  Events are
- * cudaEvent_t handles passed as void*; the hook is one-shot (cleared once used); NULLs clear it.
- */
-int nnop_set_timing_events(int which, void* start_event, void* stop_event);
-
-/* ---------------------------------------------------------------------------------------
- * Hardware self-test of the tcgen05/TMA building blocks (diagnostics; used by tests).
- * Runs one 128x128x128 bf16 GEMM through an operand form the attention kernels use and
- * writes the 128x128 fp32 result to d_out; a, b are 128x128 bf16 row-major device buffers.
- *   which 0: A B^T, TMA + K-major smem operands        which 1: A B, A in TMEM, B MN-major
- *   which 2: A B^T, thread-written swizzled smem       which 3: A^T B, both MN-major
- *   which 4: A B, A K-major, B MN-major
- */
-int nnop_selftest_umma(float* d_out, const void* a, const void* b, int which, void* stream);
 
 #ifdef __cplusplus
 }

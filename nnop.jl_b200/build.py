@@ -35,7 +35,7 @@ def _stale(target: Path, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     LIB.parent.mkdir(exist_ok=True)
-    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [HERE.parent / "include" / "nnop_b200.h"]
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [HERE.parent / "include" / "nnop_b200.h", HERE.parent / "include" / "nnop_b200_diag.h"]
 
     def compile_one(src: str):
         s = CSRC / src

@@ -31,18 +31,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static EncodeTiledFn lookup_encode_fn() {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    return reinterpret_cast<EncodeTiledFn>(p);
+  return nullptr;
+}
 static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
-            cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
+  static const EncodeTiledFn fn = lookup_encode_fn();   // initialised once, thread-safe (C++11 static)
   return fn;
 }
 
@@ -206,7 +204,7 @@ extern "C" size_t nnop_flash_attn_bwd_workspace_bytes(int dtype, int E, int QL, 
   // delta (B,QH,QL) fp32, 256-byte aligned, then the fp32 dQ accumulator of the tcgen05 path
   size_t delta = (static_cast<size_t>(B) * QH * QL * sizeof(float) + 255) & ~static_cast<size_t>(255);
   size_t rest = attn_sm100_bwd_workspace_bytes(E, QL, QH, B);
-  if (dtype == NNOP_F32 && E == 64 && KL > 0 && KH > 0) {  // split-bf16 copies of q, k, v, dO (tensor-core Float32 path)
+  if (dtype == NNOP_F32 && (E == 16 || E == 32 || E == 64) && KL > 0 && KH > 0) {  // split-bf16 copies of q, k, v, dO (tensor-core Float32 path)
     const size_t f32 = attn_f32_bwd_workspace_bytes(QL, KL, QH, KH, B);
     if (f32 > rest) rest = f32;
   }
@@ -265,7 +263,7 @@ static int flash_attn_bwd_impl(void* dq, void* dk, void* dv, void* dpair, const 
                       reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dO) |
                       reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
                       reinterpret_cast<uintptr_t>(dv)) & 15) == 0;
-  const bool f32_tc = dtype == NNOP_F32 && E == 64 && (!pair || p.pair_t) && QL > 0 && KL > 0 && al16 &&
+  const bool f32_tc = dtype == NNOP_F32 && (E == 16 || E == 32 || E == 64) && (!pair || p.pair_t) && QL > 0 && KL > 0 && al16 &&
                       QH <= 65535 && B <= 65535;
   const bool fast_ok = f32_tc || attn_sm100_supported(p, true);
   if (mode == 2 && !fast_ok)
@@ -332,12 +330,12 @@ extern "C" int nnop_flash_attn_bwd_reuse_pair(void* dq, void* dk, void* dv, void
                              KH, B, causal, scale, workspace, workspace_bytes, stream, pair_head_major);
 }
 
-extern "C" int nnop_flash_attn_varlen_fwd(void* o, float* lse, const void* q, const void* k,
+extern "C" int nnop_flash_attn_varlen_fwd_ws(void* o, float* lse, const void* q, const void* k,
                                           const void* v, const int32_t* cu_seqlens_q,
                                           const int32_t* cu_seqlens_k, int nseq, int max_seqlen_q,
                                           int max_seqlen_k, int64_t total_q, int64_t total_k,
                                           int dtype, int E, int QH, int KH, int causal, float scale,
-                                          void* stream) {
+                                          void* workspace, size_t workspace_bytes, void* stream) {
   clear_error();
   if (int rc = validate_varlen(dtype, E, nseq, max_seqlen_q, max_seqlen_k, total_q, total_k, QH, KH))
     return rc;
@@ -351,10 +349,26 @@ extern "C" int nnop_flash_attn_varlen_fwd(void* o, float* lse, const void* q, co
   p.stream = static_cast<cudaStream_t>(stream);
   p.cu_q = cu_seqlens_q; p.cu_k = cu_seqlens_k; p.nseq = nseq; p.total_q = total_q;
   p.total_k = total_k > 0 ? total_k : 1;  // a TMA map needs a non-empty extent; no key is ever read
+  if (workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && workspace_bytes >= kFwdCounterBytes)
+    p.fwd_ws = workspace;   // tile counter: lets batches of short sequences take the persistent forward
   if (!attn_sm100_supported(p, false))
     return fail(NNOP_ERR_ARG, "packed attention: pointers must be 16-byte aligned, heads <= 65535");
   g_last_path = 1;
   return attn_sm100_fwd(p);
+}
+
+extern "C" size_t nnop_flash_attn_varlen_fwd_workspace_bytes(int dtype, int E, int nseq, int64_t total_q, int QH) {
+  (void)dtype;
+  if (E <= 0 || nseq <= 0 || total_q <= 0 || QH <= 0) return 0;
+  return kFwdCounterBytes;
+}
+
+extern "C" int nnop_flash_attn_varlen_fwd(void* o, float* lse, const void* q, const void* k, const void* v,
+                                          const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int nseq,
+                                          int max_seqlen_q, int max_seqlen_k, int64_t total_q, int64_t total_k,
+                                          int dtype, int E, int QH, int KH, int causal, float scale, void* stream) {
+  return nnop_flash_attn_varlen_fwd_ws(o, lse, q, k, v, cu_seqlens_q, cu_seqlens_k, nseq, max_seqlen_q, max_seqlen_k,
+                                       total_q, total_k, dtype, E, QH, KH, causal, scale, nullptr, 0, stream);
 }
 
 extern "C" size_t nnop_flash_attn_varlen_bwd_workspace_bytes(int dtype, int E, int nseq,

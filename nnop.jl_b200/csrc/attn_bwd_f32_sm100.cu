@@ -532,23 +532,23 @@ __global__ void __launch_bounds__(256)
 attn_bwd_f32_prep_kernel(float* __restrict__ deltap, float* __restrict__ lse2p, float* __restrict__ dq,
                          const float* __restrict__ dO, const float* __restrict__ o,
                          const float* __restrict__ lse, int QL, int QLp, int64_t n_rows_p,
-                         const float* __restrict__ mult) {
+                         const float* __restrict__ mult, int E) {
+  const int lpr = E >> 2;         // lanes (one float4 each) per E-float row: 16, 8 or 4
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  const int64_t rowp = gid >> 4;  // 16 lanes (one float4 each) per 64-float row
-  const int li = static_cast<int>(gid & 15);
+  const int64_t rowp = gid / lpr;
+  const int li = static_cast<int>(gid % lpr);
   if (rowp >= n_rows_p) return;
   const int64_t bh = rowp / QLp;
   const int q = static_cast<int>(rowp % QLp);
   float acc = 0.f;
   if (q < QL) {
-    const int64_t off = (bh * QL + q) * 64 + li * 4;
+    const int64_t off = (bh * QL + q) * E + li * 4;
     const float4 a = *reinterpret_cast<const float4*>(dO + off);
     const float4 c = *reinterpret_cast<const float4*>(o + off);
     acc = a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
     *reinterpret_cast<float4*>(dq + off) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-#pragma unroll
-  for (int sft = 1; sft < 16; sft <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+  for (int sft = 1; sft < lpr; sft <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
   if (li == 0) {
     const float l = q < QL ? lse[bh * QL + q] : INFINITY;
     deltap[rowp] = q < QL ? acc * __ldg(mult + F32Mult::kDeltaInv) : 0.f;   // delta' pairs with dP' = dO' v'^T
@@ -579,32 +579,33 @@ int attn_f32_bwd(const AttnParams& a) {
   T* ks = dos + BH * a.QL * 128;
   T* vs = ks + BHk * a.KL * 128;
   void* blk = vs + BHk * a.KL * 128;   // scale block: |x|max, exponents, multipliers (internal.h)
-  if (int rc = attn_f32_scales(blk, a.q, BH * a.QL * 64, a.k, BHk * a.KL * 64, a.v, BHk * a.KL * 64, a.dO,
-                               BH * a.QL * 64, a.stream))
+  const int E = a.E;   // 16 / 32 / 64: narrower rows are zero-padded into the same [hi(64) | lo(64)] operand rows
+  if (int rc = attn_f32_scales(blk, a.q, BH * a.QL * E, a.k, BHk * a.KL * E, a.v, BHk * a.KL * E, a.dO,
+                               BH * a.QL * E, a.stream))
     return rc;
   {
     const int64_t n_rows_p = BH * QLp;
-    const int64_t threads = n_rows_p * 16;
+    const int64_t threads = n_rows_p * (a.E / 4);
     attn_bwd_f32_prep_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, a.stream>>>(
         deltap, lse2p, static_cast<float*>(a.dq), static_cast<const float*>(a.dO),
-        static_cast<const float*>(a.o), a.lse, a.QL, QLp, n_rows_p, f32_mults(blk));
+        static_cast<const float*>(a.o), a.lse, a.QL, QLp, n_rows_p, f32_mults(blk), a.E);
     NNOP_LAUNCH_CHECK();
   }
-  NNOP_CUDA_CHECK(cudaMemsetAsync(a.dk, 0, static_cast<size_t>(BHk) * a.KL * 64 * sizeof(float), a.stream));
-  NNOP_CUDA_CHECK(cudaMemsetAsync(a.dv, 0, static_cast<size_t>(BHk) * a.KL * 64 * sizeof(float), a.stream));
-  if (int rc = attn_split_f32_rows(qs, a.q, BH * a.QL, f32_exp_slot(blk, 0), a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(dos, a.dO, BH * a.QL, f32_exp_slot(blk, 3), a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(ks, a.k, BHk * a.KL, f32_exp_slot(blk, 1), a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(vs, a.v, BHk * a.KL, f32_exp_slot(blk, 2), a.stream)) return rc;
+  NNOP_CUDA_CHECK(cudaMemsetAsync(a.dk, 0, static_cast<size_t>(BHk) * a.KL * E * sizeof(float), a.stream));
+  NNOP_CUDA_CHECK(cudaMemsetAsync(a.dv, 0, static_cast<size_t>(BHk) * a.KL * E * sizeof(float), a.stream));
+  if (int rc = attn_split_f32_rows(qs, a.q, BH * a.QL, E, f32_exp_slot(blk, 0), a.stream)) return rc;
+  if (int rc = attn_split_f32_rows(dos, a.dO, BH * a.QL, E, f32_exp_slot(blk, 3), a.stream)) return rc;
+  if (int rc = attn_split_f32_rows(ks, a.k, BHk * a.KL, E, f32_exp_slot(blk, 1), a.stream)) return rc;
+  if (int rc = attn_split_f32_rows(vs, a.v, BHk * a.KL, E, f32_exp_slot(blk, 2), a.stream)) return rc;
   alignas(64) CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdq;
   const uint64_t bhq = static_cast<uint64_t>(BH), bhk = static_cast<uint64_t>(BHk);
   if (int rc = make_tmap_3d(&tq, qs, NNOP_F16, 128, a.QL, bhq, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&tdo, dos, NNOP_F16, 128, a.QL, bhq, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&tk, ks, NNOP_F16, 128, a.KL, bhk, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&tv, vs, NNOP_F16, 128, a.KL, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tdk, a.dk, NNOP_F32, 64, a.KL, bhk, 32, 128)) return rc;
-  if (int rc = make_tmap_3d(&tdv, a.dv, NNOP_F32, 64, a.KL, bhk, 32, 128)) return rc;
-  if (int rc = make_tmap_3d(&tdq, a.dq, NNOP_F32, 64, a.QL, bhq, 32, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdk, a.dk, NNOP_F32, E, a.KL, bhk, 32, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdv, a.dv, NNOP_F32, E, a.KL, bhk, 32, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdq, a.dq, NNOP_F32, E, a.QL, bhq, 32, 128)) return rc;
   const bool bias = a.pair != nullptr;
   auto kern = bias ? attn_bwd_f32_kernel<true> : attn_bwd_f32_kernel<false>;
   NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));

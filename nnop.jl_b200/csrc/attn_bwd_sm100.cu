@@ -1944,8 +1944,12 @@ int launch_bwd(const AttnParams& a) {
   float* dqa = reinterpret_cast<float*>(ws + 2 * stat_bytes);
   // the persistent kernel's tile counter (and, packed, the per-sequence tile prefix) sit behind the
   // dQ accumulator
+  // (a.E < D: embedding dims 16 / 32 run the D = 64 kernels -- the TMA maps below describe the real E-wide
+  // rows and the boxes stay 64 wide, so columns >= E arrive as zeros in shared memory and are clipped on
+  // the way out; every plain-pointer access uses the real E)
+  const int E = a.E;
   int* tile_counter = reinterpret_cast<int*>(
-      ws + 2 * stat_bytes + align256(static_cast<size_t>(BH) * rows_q * D * sizeof(float)));
+      ws + 2 * stat_bytes + align256(static_cast<size_t>(BH) * rows_q * E * sizeof(float)));
   int* tile_pre = tile_counter + 64;
 
   if (packed) {
@@ -1957,8 +1961,9 @@ int launch_bwd(const AttnParams& a) {
     NNOP_LAUNCH_CHECK();
   } else {
     const int64_t n_rows_p = BH * QLp;
-    const int64_t threads = n_rows_p * (D / 8);
-    attn_bwd_prep_kernel<T, D><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, a.stream>>>(
+    const int64_t threads = n_rows_p * (E / 8);
+    auto prep = E == D ? attn_bwd_prep_kernel<T, D> : (E == 32 ? attn_bwd_prep_kernel<T, 32> : attn_bwd_prep_kernel<T, 16>);
+    prep<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, a.stream>>>(
         deltap, lse2p, dqa, static_cast<const T*>(a.dO), static_cast<const T*>(a.o), a.lse, a.QL,
         static_cast<int>(QLp), n_rows_p, tile_counter);
     NNOP_LAUNCH_CHECK();
@@ -1966,13 +1971,13 @@ int launch_bwd(const AttnParams& a) {
   alignas(64) CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdqa;
   const uint64_t bhq = static_cast<uint64_t>(BH);
   const uint64_t bhk = packed ? a.KH : static_cast<uint64_t>(a.B) * a.KH;
-  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tdo, a.dO, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tdk, a.dk, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tdv, a.dv, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tdqa, dqa, NNOP_F32, D, rows_q, bhq, 32, 128)) return rc;
+  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, E, rows_q, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, E, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, E, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdo, a.dO, a.dtype, E, rows_q, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdk, a.dk, a.dtype, E, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdv, a.dv, a.dtype, E, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tdqa, dqa, NNOP_F32, E, rows_q, bhq, 32, 128)) return rc;
   BwdParams bp;
   bp.lse2p = lse2p; bp.deltap = deltap;
   bp.QL = a.QL; bp.KL = a.KL; bp.QH = a.QH; bp.KH = a.KH; bp.QLp = static_cast<int>(QLp);
@@ -2076,7 +2081,7 @@ int launch_bwd(const AttnParams& a) {
     NNOP_LAUNCH_CHECK();
   }
   {
-    const int64_t n8 = BH * rows_q * D / 8;
+    const int64_t n8 = BH * rows_q * E / 8;
     attn_bwd_post_kernel<T><<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, a.stream>>>(
         static_cast<T*>(a.dq), dqa, n8, a.scale);
     NNOP_LAUNCH_CHECK();
@@ -2120,6 +2125,7 @@ size_t attn_sm100_bwd_packed_workspace_bytes(int E, int64_t total_q, int nseq, i
 }
 
 int attn_sm100_bwd(const AttnParams& a) {
+  // E = 128 -> the D = 128 kernels; E in {16, 32, 64} -> the D = 64 kernels (narrower rows are zero-padded by TMA)
   if (a.dtype == NNOP_BF16)
     return a.E == 128 ? launch_bwd<__nv_bfloat16, 128>(a) : launch_bwd<__nv_bfloat16, 64>(a);
   return a.E == 128 ? launch_bwd<__half, 128>(a) : launch_bwd<__half, 64>(a);

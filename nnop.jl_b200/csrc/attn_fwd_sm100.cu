@@ -258,7 +258,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    setmaxnreg_dec<96>();  // 128*96 + 256*208 = 65536 = 64K registers (at 80 the issuer warp spilled: 152 / 348 B)
+    setmaxnreg_dec<88>();  // launch: 384 x 168; warps 0-3 give back 128 x 80 = 10240 registers, exactly what 256 x (208 - 168) takes
     if (warp == 0 && lane == 0 && nblk > 0) {
       // ================================ TMA producer =================================
       mbar_arrive_expect_tx(&q_full[0], S::kTileBytes);
@@ -748,7 +748,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
 //     softmax warpgroup to have pulled O out of TMEM (o_empty);
 //   * each softmax warpgroup stores its O tile through a private 16 KB staging buffer (one 64-column
 //     box at a time), so Q never waits for a store;
-//   * warp 3 claims tiles with atomicAdd on a per-launch counter slot (see launch_fwd_persist) and
+//   * warp 3 claims tiles with atomicAdd on a counter in the caller's workspace (see launch_fwd_persist) and
 //     publishes them through a two-slot ring, late, as in the persistent backward.
 // The softmax code is the one-tile kernel's, so O and lse are bit-identical (test).
 // =========================================================================================
@@ -885,7 +885,7 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
   };
 
   if (warp < 4) {
-    setmaxnreg_dec<96>();
+    setmaxnreg_dec<88>();
     if (warp == 3) {
       // ================================ tile scheduler ===============================
       // Dense: tile t = (batch * QH + head) * nqt + r.  Packed: sequences in order, within a sequence
@@ -1267,27 +1267,30 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
 // percent.  The power of two is exact; the kernels undo it with the multipliers below.
 __global__ void __launch_bounds__(256)
 split_f32_kernel(__half* __restrict__ out, const float* __restrict__ in, int64_t n4,
-                 const int* __restrict__ exp_slot) {
+                 const int* __restrict__ exp_slot, int per_row) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;  // one float4 per thread
   if (i >= n4) return;
   const int e = exp_slot ? -__ldg(exp_slot) : 0;
   float4 x = reinterpret_cast<const float4*>(in)[i];
   x.x = ldexpf(x.x, e); x.y = ldexpf(x.y, e); x.z = ldexpf(x.z, e); x.w = ldexpf(x.w, e);
-  const int64_t row = i >> 4;          // 16 float4 per 64-float row
-  const int c4 = static_cast<int>(i & 15);
+  // per_row = E / 4 float4 per E-float row (16 for E = 64); narrower rows leave the rest of each 64-wide
+  // half zero, which is what lets E = 16 / 32 ride the same 128-wide kernels
+  const int64_t row = i / per_row;
+  const int c4 = static_cast<int>(i % per_row);
   const uint32_t h0 = pack2<__half>(x.x, x.y), h1 = pack2<__half>(x.z, x.w);
   const uint32_t l0 = pack2<__half>(x.x - unpack_lo<__half>(h0), x.y - unpack_hi<__half>(h0));
   const uint32_t l1 = pack2<__half>(x.z - unpack_lo<__half>(h1), x.w - unpack_hi<__half>(h1));
   uint2* o = reinterpret_cast<uint2*>(out + row * 128);
   o[c4] = make_uint2(h0, h1);
   o[16 + c4] = make_uint2(l0, l1);
+  for (int z = c4 + per_row; z < 16; z += per_row) o[z] = o[16 + z] = make_uint2(0u, 0u);
 }
 
-int launch_split(__half* out, const void* in, int64_t rows, const int* exp_slot, cudaStream_t st) {
-  const int64_t n4 = rows * 16;
+int launch_split(__half* out, const void* in, int64_t rows, int E, const int* exp_slot, cudaStream_t st) {
+  const int64_t n4 = rows * (E / 4);
   if (n4 == 0) return NNOP_OK;
   split_f32_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(out, static_cast<const float*>(in), n4,
-                                                                           exp_slot);
+                                                                           exp_slot, E / 4);
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
 }
@@ -1351,16 +1354,16 @@ int launch_fwd_f32(const AttnParams& a) {
   T* ks = qs + rq * 128;
   T* vs = ks + rk * 128;
   void* blk = vs + rk * 128;   // scale block (256-byte aligned: every copy is a multiple of 256 bytes)
-  if (int rc = attn_f32_scales(blk, a.q, rq * 64, a.k, rk * 64, a.v, rk * 64, nullptr, 0, a.stream)) return rc;
-  if (int rc = launch_split(qs, a.q, rq, f32_exp_slot(blk, 0), a.stream)) return rc;
-  if (int rc = launch_split(ks, a.k, rk, f32_exp_slot(blk, 1), a.stream)) return rc;
-  if (int rc = launch_split(vs, a.v, rk, f32_exp_slot(blk, 2), a.stream)) return rc;
+  if (int rc = attn_f32_scales(blk, a.q, rq * a.E, a.k, rk * a.E, a.v, rk * a.E, nullptr, 0, a.stream)) return rc;
+  if (int rc = launch_split(qs, a.q, rq, a.E, f32_exp_slot(blk, 0), a.stream)) return rc;
+  if (int rc = launch_split(ks, a.k, rk, a.E, f32_exp_slot(blk, 1), a.stream)) return rc;
+  if (int rc = launch_split(vs, a.v, rk, a.E, f32_exp_slot(blk, 2), a.stream)) return rc;
   alignas(64) CUtensorMap tq, tk, tv, to;
   const uint64_t bhq = static_cast<uint64_t>(a.B) * a.QH, bhk = static_cast<uint64_t>(a.B) * a.KH;
   if (int rc = make_tmap_3d(&tq, qs, NNOP_F16, D, a.QL, bhq, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&tk, ks, NNOP_F16, D, a.KL, bhk, 64, 128)) return rc;
   if (int rc = make_tmap_3d(&tv, vs, NNOP_F16, D, a.KL, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&to, a.o, NNOP_F32, 64, a.QL, bhq, 32, 128)) return rc;
+  if (int rc = make_tmap_3d(&to, a.o, NNOP_F32, a.E, a.QL, bhq, 32, 128)) return rc;   // E < 64: columns >= E clipped
   alignas(64) CUtensorMap tb = to;  // unused without a bias
   if constexpr (BIAS)
     if (int rc = make_tmap_3d(&tb, a.pair_t, NNOP_F32, a.KLp, a.QL, bhq, 32, 128)) return rc;
@@ -1392,10 +1395,12 @@ int launch_fwd(const AttnParams& a) {
   const uint64_t bhk = packed ? a.KH : static_cast<uint64_t>(a.B) * a.KH;
   const uint64_t rows_q = packed ? static_cast<uint64_t>(a.total_q) : a.QL;
   const uint64_t rows_k = packed ? static_cast<uint64_t>(a.total_k) : a.KL;
-  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&to, a.o, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
+  // a.E < D (embedding dims 16 / 32 on the D = 64 kernels): the maps describe the real E-wide rows, the
+  // boxes stay 64 wide -- TMA zero-fills columns >= E on the way in and clips them on the way out
+  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, a.E, rows_q, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, a.E, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, a.E, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&to, a.o, a.dtype, a.E, rows_q, bhq, 64, 128)) return rc;
   alignas(64) CUtensorMap tb = to;  // unused without a bias
   if constexpr (BIAS)
     if (int rc = make_tmap_3d(&tb, a.pair_t, a.dtype, a.KLp, a.QL, bhq, 64, 128)) return rc;
@@ -1425,11 +1430,6 @@ int launch_fwd(const AttnParams& a) {
   return NNOP_OK;
 }
 
-// per-launch tile counters of the persistent forward: a launch takes the next slot round-robin and
-// zeroes it on its own stream first, so stream-ordered launches never share a live slot (launches
-// on different streams would have to be 256 launches apart and still running to collide)
-__device__ int g_fwd_tile_counters[256];
-std::atomic<unsigned> g_fwd_slot{0};
 std::atomic<int> g_fwd_mode{-1};
 
 inline int fwd_mode() {
@@ -1451,10 +1451,12 @@ int launch_fwd_persist(const AttnParams& a, int ctas) {
   const uint64_t bhk = packed ? a.KH : static_cast<uint64_t>(a.B) * a.KH;
   const uint64_t rows_q = packed ? static_cast<uint64_t>(a.total_q) : a.QL;
   const uint64_t rows_k = packed ? static_cast<uint64_t>(a.total_k) : a.KL;
-  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, D, rows_k, bhk, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&to, a.o, a.dtype, D, rows_q, bhq, 64, 128)) return rc;
+  // a.E < D (embedding dims 16 / 32 on the D = 64 kernels): the maps describe the real E-wide rows, the
+  // boxes stay 64 wide -- TMA zero-fills columns >= E on the way in and clips them on the way out
+  if (int rc = make_tmap_3d(&tq, a.q, a.dtype, a.E, rows_q, bhq, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tk, a.k, a.dtype, a.E, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&tv, a.v, a.dtype, a.E, rows_k, bhk, 64, 128)) return rc;
+  if (int rc = make_tmap_3d(&to, a.o, a.dtype, a.E, rows_q, bhq, 64, 128)) return rc;
   auto kern = attn_fwd_sm100_persist_kernel<T, D>;
   NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynBytes));
   FwdParams fp;
@@ -1465,9 +1467,9 @@ int launch_fwd_persist(const AttnParams& a, int ctas) {
   fp.cu_q = a.cu_q; fp.cu_k = a.cu_k; fp.o_ptr = a.o; fp.total_q = a.total_q; fp.kpad = nullptr;
   fp.nseq = a.nseq;
   fp.lpt_group = 0;
-  int* counters = nullptr;
-  NNOP_CUDA_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&counters), g_fwd_tile_counters));
-  int* counter = counters + (g_fwd_slot.fetch_add(1) & 255u);
+  // the tile counter lives in the caller's workspace (the library keeps no device state of its own):
+  // zeroed on the call's stream, so concurrent launches and replayed graphs each use their own
+  int* counter = static_cast<int*>(a.fwd_ws);
   NNOP_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), a.stream));
   const int nqt = (a.QL + 255) / 256;
   // packed: the exact tile count is only known on the device; this is its upper bound (for the grid)
@@ -1492,9 +1494,13 @@ extern "C" int nnop_debug_fwd_trace(long long* host_out, int n) {
 
 bool attn_sm100_supported(const AttnParams& a, bool backward) {
   if (backward && !attn_sm100_bwd_available()) return false;
-  const bool f32_split = a.dtype == NNOP_F32 && a.E == 64 && !backward && a.fwd_ws != nullptr && !a.cu_q;
+  const bool f32_split = a.dtype == NNOP_F32 && (a.E == 16 || a.E == 32 || a.E == 64) && !backward &&
+                         a.fwd_ws != nullptr && !a.cu_q;
   if (a.dtype != NNOP_F16 && a.dtype != NNOP_BF16 && !f32_split) return false;
-  if (a.E != 64 && a.E != 128) return false;
+  if (a.E != 64 && a.E != 128) {
+    // 16 / 32: dense 16-bit problems only (the packed kernels address partial tiles with plain pointers)
+    if ((a.E != 16 && a.E != 32) || a.cu_q != nullptr) return false;
+  }
   // the additive bias needs its head-major copy (and, backward, a dpair staging area) in the
   // workspace (nnop_flash_attn_pair_workspace_bytes); without it the generic path serves it
   if (a.pair && (a.pair_t == nullptr || a.cu_q != nullptr)) return false;
@@ -1507,9 +1513,9 @@ bool attn_sm100_supported(const AttnParams& a, bool backward) {
   return true;
 }
 
-int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, const int* exp_slot,
+int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, int E, const int* exp_slot,
                         cudaStream_t st) {
-  return launch_split(static_cast<__half*>(out_bf16x2), in_f32, rows, exp_slot, st);
+  return launch_split(static_cast<__half*>(out_bf16x2), in_f32, rows, E, exp_slot, st);
 }
 
 int attn_f32_scales(void* block, const void* q, int64_t nq, const void* k, int64_t nk, const void* v,
@@ -1534,7 +1540,9 @@ int attn_f32_scales(void* block, const void* q, int64_t nq, const void* k, int64
 }
 
 size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B) {
-  if (dtype != NNOP_F32 || E != 64) return 0;
+  // 16-bit: the persistent forward's tile counter; Float32 E = 64: the [hi | lo] copies + scale block
+  if (dtype != NNOP_F32) return (E == 16 || E == 32 || E == 64 || E == 128) ? kFwdCounterBytes : 0;
+  if (E != 16 && E != 32 && E != 64) return 0;
   return (static_cast<size_t>(B) * QH * QL + 2 * static_cast<size_t>(B) * KH * KL) * 128 * 2 + kF32ScaleBytes;
 }
 
@@ -1553,11 +1561,11 @@ int attn_sm100_fwd(const AttnParams& a) {
   const bool packed = a.cu_q != nullptr;
   const int64_t n_tiles = packed ? (a.total_q / 256 + a.nseq) * a.QH
                                  : static_cast<int64_t>((a.QL + 255) / 256) * a.QH * a.B;
-  const bool persist_ok = a.kpad == nullptr && (packed || a.KL >= 1) && n_tiles < (1LL << 30);
+  const bool persist_ok = a.fwd_ws != nullptr && a.kpad == nullptr && (packed || a.KL >= 1) && n_tiles < (1LL << 30);
   // automatic choice, from measurement (profiles/r01d_perf_fwd_modes.txt): the persistent kernel wins
   // where the per-tile fixed cost matters -- E = 64 (+15 %) and short sequences (L = 2 048: +6 %) --
   // and is neutral (bench.py regime) to slower (back-to-back launches) on long E = 128 tiles
-  const bool persist_pays = a.E == 64 || a.QL <= 2048;
+  const bool persist_pays = a.E <= 64 || a.QL <= 2048;
   if (persist_ok && (mode == 2 || mode >= 100 || (mode == 0 && persist_pays && n_tiles >= 2LL * sm_count()))) {
     const int ctas = mode >= 100 ? (mode - 100 < 1 ? 1 : mode - 100) : sm_count();
     if (a.dtype == NNOP_BF16)

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "../../include/nnop_b200.h"
+#include "../../include/nnop_b200_diag.h"
 
 namespace nnop {
 
@@ -68,7 +69,8 @@ struct AttnParams {
   const int* cu_k;
   int nseq;
   int64_t total_q, total_k;
-  // forward workspace (nnop_flash_attn_fwd_ws): [hi | lo] bf16 copies of q, k, v for the Float32 path
+  // forward workspace (nnop_flash_attn_fwd_ws): [hi | lo] fp16 copies of q, k, v for the Float32 path; 16-bit:
+  // the persistent forward's tile counter (nullptr => one CTA per q tile)
   void* fwd_ws;
   // pair bias on the tcgen05 path: head-major copy of pair (B, QH, QL, KLp) and, backward, the staging
   // area dpair is produced in (same layout); KLp = KL rounded up to 32 elements
@@ -98,6 +100,7 @@ size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, 
 // the end of the Float32 workspaces holds |x|max bit patterns [u32 0..3: q, k, v, dO], the exponents
 // [i32 4..7] and the multipliers the kernels apply to undo the scaling [f32 8 + F32Mult::k*].
 constexpr size_t kF32ScaleBytes = 256;
+constexpr size_t kFwdCounterBytes = 256;   // 16-bit forward workspace: tile counter of the persistent kernel
 struct F32Mult {
   enum : int {
     kLogits = 0,    // 2^(e_q + e_k): S = kLogits * q' k'^T           (on top of scale * log2e)
@@ -114,8 +117,9 @@ inline const float* f32_mults(const void* block) { return static_cast<const floa
 // memset + |x|max of q, k, v (and dO, may be NULL) + exponents / multipliers; n* = element counts
 int attn_f32_scales(void* block, const void* q, int64_t nq, const void* k, int64_t nk, const void* v,
                     int64_t nv, const void* dO, int64_t ndo, cudaStream_t st);
-// (rows, 64) fp32 -> (rows, 128) fp16 rows [hi(64) | lo(64)] with x * 2^-(*exp_slot) ~ hi + lo
-int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, const int* exp_slot,
+// (rows, E) fp32, E in {16, 32, 64} -> (rows, 128) fp16 rows [hi(64) | lo(64)] with x * 2^-(*exp_slot) ~ hi + lo
+// (columns >= E of each half are written as zeros)
+int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, int E, const int* exp_slot,
                         cudaStream_t st);
 // attn_bwd_f32_sm100.cu -- Float32 (E = 64) backward on the tensor cores (split-bf16 operands)
 size_t attn_f32_bwd_workspace_bytes(int QL, int KL, int QH, int KH, int B);

@@ -172,12 +172,16 @@ function _flash_attention_varlen(
     nseq = length(cu_seqlens_q) - 1
     o = similar(q)
     lse = CUDA.zeros(Float32, TQ, QH)
-    check(ccall((:nnop_flash_attn_varlen_fwd, libnnop_b200), Cint,
+    nbytes = ccall((:nnop_flash_attn_varlen_fwd_workspace_bytes, libnnop_b200), Csize_t,
+        (Cint, Cint, Cint, Int64, Cint), dtype_code(T), E, nseq, TQ, QH)
+    ws = nbytes > 0 ? CuArray{UInt8}(undef, nbytes) : nothing     # tile counter of the persistent forward
+    check(ccall((:nnop_flash_attn_varlen_fwd_ws, libnnop_b200), Cint,
         (CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid},
-         Cint, Cint, Cint, Int64, Int64, Cint, Cint, Cint, Cint, Cint, Cfloat, Ptr{Cvoid}),
+         Cint, Cint, Cint, Int64, Int64, Cint, Cint, Cint, Cint, Cint, Cfloat, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
         ptr(o), ptr(lse), ptr(q), ptr(k), ptr(v), ptr(cu_seqlens_q), ptr(cu_seqlens_k),
         nseq, max_seqlen_q, max_seqlen_k, TQ, TK, dtype_code(T), E, QH, KH, causal,
-        Float32(inv(sqrt(E))), stream()))
+        Float32(inv(sqrt(E))), ptr(ws), nbytes, stream()))
+    release!(ws)
     return o, lse
 end
 
@@ -474,7 +478,8 @@ function CRC.rrule(::typeof(llama_rope), q, k; cos, sin)                   # :94
 end
 
 # ------------------------------------------------------------------ diagnostics
-# kernel-variant switches of the tcgen05 attention path (process-wide; see include/nnop_b200.h)
+# kernel-variant switches of the tcgen05 attention path (process-wide; include/nnop_b200_diag.h -- not part of
+# the drop-in ABI)
 set_attention_path(mode::Integer) = check(ccall((:nnop_set_attention_path, libnnop_b200), Cint, (Cint,), mode))
 last_attention_path() = ccall((:nnop_last_attention_path, libnnop_b200), Cint, ())
 set_fwd_mode(mode::Integer) = check(ccall((:nnop_set_fwd_mode, libnnop_b200), Cint, (Cint,), mode))

@@ -39,7 +39,7 @@ lib = C.CDLL(str(LIB_PATH))
 
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 _pp, _ip = C.POINTER(C.c_void_p), C.POINTER(C.c_int)   # host arrays: per-rank device pointers / device ids
-# name -> (restype, argtypes); must list every symbol include/nnop_b200.h declares
+# name -> (restype, argtypes); must list every symbol include/nnop_b200.h and nnop_b200_diag.h declare
 SIGNATURES = {
     "nnop_version": (_i, []),
     "nnop_last_error_string": (C.c_char_p, []),
@@ -56,6 +56,8 @@ SIGNATURES = {
     "nnop_flash_attn_bwd": (_i, [_vp] * 12 + [_i] * 8 + [_f, _vp, _sz, _vp]),
     "nnop_flash_attn_bwd_reuse_pair": (_i, [_vp] * 12 + [_i] * 8 + [_f, _vp, _sz, _vp, _vp]),
     "nnop_flash_attn_varlen_fwd": (_i, [_vp] * 7 + [_i] * 3 + [_i64, _i64] + [_i] * 5 + [_f, _vp]),
+    "nnop_flash_attn_varlen_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i64, _i]),
+    "nnop_flash_attn_varlen_fwd_ws": (_i, [_vp] * 7 + [_i] * 3 + [_i64, _i64] + [_i] * 5 + [_f, _vp, _sz, _vp]),
     "nnop_flash_attn_varlen_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i64, _i]),
     "nnop_flash_attn_varlen_bwd": (_i, [_vp] * 11 + [_i] * 3 + [_i64, _i64] + [_i] * 5 + [_f, _vp, _sz, _vp]),
     "nnop_attn_merge": (_i, [_vp] * 5 + [_i, _i, _i64, _i, _vp]),

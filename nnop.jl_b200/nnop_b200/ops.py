@@ -217,10 +217,12 @@ def _flash_attention_varlen(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q: i
     QH, TQ, E, KH, TK, nseq = _varlen_dims(q, k, v, cu_seqlens_q, cu_seqlens_k)
     o = torch.empty_like(q)
     lse = torch.empty((QH, TQ), dtype=torch.float32, device=q.device)
-    check(lib.nnop_flash_attn_varlen_fwd(_p(o), _p(lse), _p(q), _p(k), _p(v), _p(cu_seqlens_q),
-                                         _p(cu_seqlens_k), nseq, int(max_seqlen_q), int(max_seqlen_k),
-                                         TQ, TK, _dt(q), E, QH, KH, int(bool(causal)),
-                                         1.0 / math.sqrt(E), _stream()))
+    ws_bytes = lib.nnop_flash_attn_varlen_fwd_workspace_bytes(_dt(q), E, nseq, TQ, QH)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if ws_bytes else None
+    check(lib.nnop_flash_attn_varlen_fwd_ws(_p(o), _p(lse), _p(q), _p(k), _p(v), _p(cu_seqlens_q),
+                                            _p(cu_seqlens_k), nseq, int(max_seqlen_q), int(max_seqlen_k),
+                                            TQ, TK, _dt(q), E, QH, KH, int(bool(causal)),
+                                            1.0 / math.sqrt(E), _p(ws), ws_bytes, _stream()))
     return o, lse
 
 

@@ -1,4 +1,4 @@
-"""The C-ABI library loads and exports every symbol include/nnop_b200.h declares (no compute,
+"""The C-ABI library loads and exports every symbol include/nnop_b200.h (and nnop_b200_diag.h) declares (no compute,
 no GPU needed), and the product package has no route into oracle/."""
 import ctypes
 import re
@@ -8,7 +8,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def _declared_symbols():
-    text = (ROOT / "include" / "nnop_b200.h").read_text()
+    text = (ROOT / "include" / "nnop_b200.h").read_text() + (ROOT / "include" / "nnop_b200_diag.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(nnop_[a-z0-9_]+)\s*\(", text)))
 
@@ -68,5 +68,11 @@ def test_workspace_queries_need_no_gpu(nnop):
     # bf16, E=128, QL=KL=1000, QH=8, KH=2, B=2: delta + 2 x padded stats + dQ accumulator + counter
     need = lib.nnop_flash_attn_bwd_workspace_bytes(2, 128, 1000, 1000, 8, 2, 2)
     assert need == up(2 * 8 * 1000 * 4) + 2 * up(2 * 8 * 1024 * 4) + up(2 * 8 * 1000 * 128 * 4) + 256
-    assert lib.nnop_set_bwd_pair_mode(4) != 0 and lib.nnop_set_bwd_pair_mode(103) == 0
+    assert lib.nnop_set_bwd_pair_mode(5) != 0 and lib.nnop_set_bwd_pair_mode(103) == 0
     assert lib.nnop_set_bwd_pair_mode(0) == 0
+    # forward: 16-bit problems get a 256-byte workspace (tile counter of the persistent kernel), Float32 E = 64
+    # the [hi | lo] fp16 copies of q, k, v plus the 256-byte scale block, Float32 of any other E nothing
+    assert lib.nnop_flash_attn_fwd_workspace_bytes(2, 128, 1000, 1000, 8, 2, 2) == 256
+    assert lib.nnop_flash_attn_fwd_workspace_bytes(0, 64, 1000, 1000, 8, 2, 2) == (2 * 8 * 1000 + 2 * 2 * 2 * 1000) * 256 + 256
+    assert lib.nnop_flash_attn_fwd_workspace_bytes(0, 128, 1000, 1000, 8, 2, 2) == 0
+    assert lib.nnop_flash_attn_varlen_fwd_workspace_bytes(2, 128, 3, 1000, 8) == 256

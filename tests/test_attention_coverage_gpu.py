@@ -1,7 +1,8 @@
 """Parity rows the round-1 suite left open ("Next round" 1):
 
-* every (dtype, E) the SIMT kernels serve -- bf16 / f16 with E in {16, 32, 256}, Float32 with
-  E in {128, 256} -- causal and non-causal, GQA, ragged lengths, pair and key padding mask;
+* every (dtype, E) outside the round-1 tensor-core set -- bf16 / f16 with E in {16, 32, 256}, Float32 with
+  E in {128, 256} -- causal and non-causal, GQA, ragged lengths, pair and key padding mask, on whichever
+  kernels serve them (E = 16 / 32 on both the tcgen05 and the SIMT kernels);
 * BASELINE config C1 at its full shape (Float32 E=64 L=4096 H=4 B=4 non-causal, README.md:32-42),
   forward AND backward, every (b, h) slab against the fp64 oracle;
 * BASELINE config C3 at L = 8192 (GQA 32 / 8, E = 128, bf16 causal): one kv-head group against the oracle;
@@ -17,28 +18,84 @@ from test_attention_gpu import F32_TOL, H16_TOL, _check, _inputs
 pytestmark = pytest.mark.gpu
 
 
+def _expected_path(dtype, E):
+    """1 = tcgen05 kernels: 16-bit E in {16, 32, 64, 128}, Float32 E in {16, 32, 64}; everything else SIMT."""
+    return int(E <= (64 if dtype == torch.float32 else 128))
+
+
+@pytest.mark.parametrize("forced_simt", [False, True])
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("dtype,E", [(torch.bfloat16, 16), (torch.bfloat16, 32), (torch.bfloat16, 256),
                                      (torch.float16, 16), (torch.float16, 32), (torch.float16, 256),
                                      (torch.float32, 128), (torch.float32, 256)])
-def test_simt_served_dtype_E_grid(nnop, dtype, E, causal):
-    """Shapes follow the reference grids (test/attention_tests.jl:13-18, test/gqa_attention_tests.jl:8-12):
-    ragged and tile-multiple L, QL != KL when not causal, GQA 4/1 and 6/2, then pair + kpad_mask."""
+def test_small_and_large_E_dtype_grid(nnop, dtype, E, causal, forced_simt):
+    """Every (dtype, E) outside the round-1 tensor-core set.  16-bit E in {16, 32} now run the E = 64 tcgen05
+    kernels (TMA zero-pads the narrower rows) and are ALSO checked on the SIMT kernels they used to take
+    (`forced_simt`); E = 256 and Float32 E >= 128 are served by the SIMT kernels only.  Shapes follow the
+    reference grids (test/attention_tests.jl:13-18, test/gqa_attention_tests.jl:8-12): ragged and
+    tile-multiple L, QL != KL when not causal, GQA 4/1 and 6/2, then pair + kpad_mask."""
     tol = F32_TOL if dtype == torch.float32 else H16_TOL
+    path = 0 if forced_simt else _expected_path(dtype, E)
+    if forced_simt and _expected_path(dtype, E) == 0:
+        pytest.skip("already covered: this (dtype, E) only has the SIMT path")
     shapes = [(2, 2, 2, 255, 255), (1, 4, 1, 257, 257), (1, 6, 2, 512, 512), (2, 2, 2, 256, 511), (1, 2, 1, 1, 1),
               (1, 2, 2, 130, 3)]
     if E == 256:   # keep the E = 256 SIMT runs short
         shapes = [(2, 2, 2, 255, 255), (1, 4, 1, 257, 257), (1, 2, 2, 130, 300), (1, 2, 1, 1, 1)]
-    for (B, QH, KH, QL, KL) in shapes:
-        if causal and QL != KL:
-            continue
-        q, k, v, dO, _, _ = _inputs(B, QH, KH, QL, KL, E, dtype, QL + 3 * KL + E)
-        try:
-            _check(nnop, q, k, v, dO, None, None, causal, tol, expect_path=0)
-        except AssertionError as e:
-            raise AssertionError(f"{dtype} E={E} shape {(B, QH, KH, QL, KL)}: {e}") from e
-    q, k, v, dO, pr, m = _inputs(2, 4, 2, 255, 255, E, dtype, 5 + E, pair=True, mask=True)
-    _check(nnop, q, k, v, dO, pr, m, causal, tol, expect_path=0)
+    try:
+        if forced_simt:
+            nnop.set_attention_path(1)
+        for (B, QH, KH, QL, KL) in shapes:
+            if causal and QL != KL:
+                continue
+            q, k, v, dO, _, _ = _inputs(B, QH, KH, QL, KL, E, dtype, QL + 3 * KL + E)
+            try:
+                _check(nnop, q, k, v, dO, None, None, causal, tol, expect_path=path)
+            except AssertionError as e:
+                raise AssertionError(f"{dtype} E={E} shape {(B, QH, KH, QL, KL)}: {e}") from e
+        q, k, v, dO, pr, m = _inputs(2, 4, 2, 255, 255, E, dtype, 5 + E, pair=True, mask=True)
+        _check(nnop, q, k, v, dO, pr, m, causal, tol, expect_path=path)
+    finally:
+        nnop.set_attention_path(0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("E", [16, 32])
+def test_small_E_tensor_cores_vs_simt_speed(nnop, dtype, E):
+    """E = 16 / 32 on the tensor cores (VERDICT r01 "Next round" 8): same results as the SIMT kernels within
+    tolerance and at least 3x faster forward + backward at L = 1024 (device time, CUDA events)."""
+    B, H, L = 4, 8, 1024
+    q, k, v, dO, _, _ = _inputs(B, H, H, L, L, E, dtype, 7 * E)
+    qd, kd, vd, dOd = (t.cuda() for t in (q, k, v, dO))
+
+    def run():
+        o, lse = nnop._flash_attention(qd, kd, vd, causal=True)
+        return (o, lse) + tuple(nnop.grad_flash_attention(dOd, o, lse, qd, kd, vd, causal=True)[:3])
+
+    def timed():
+        for _ in range(2):
+            out = run()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(5):
+            out = run()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / 5, out
+
+    t_tc, out_tc = timed()
+    assert nnop.last_attention_path() == 1
+    try:
+        nnop.set_attention_path(1)
+        t_simt, out_simt = timed()
+        assert nnop.last_attention_path() == 0
+    finally:
+        nnop.set_attention_path(0)
+    tol = F32_TOL if dtype == torch.float32 else H16_TOL
+    for a, b in zip(out_tc, out_simt):
+        assert kernel_err(a, b) < 2 * tol
+    assert t_simt > 3 * t_tc, (t_simt, t_tc)
 
 
 def test_config_c1_full_shape_fwd_bwd(nnop):

@@ -17,6 +17,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 HEADER = ROOT / "include" / "nnop_b200.h"
+DIAG_HEADER = ROOT / "include" / "nnop_b200_diag.h"   # switches / hooks: not part of the drop-in ABI
 SHIM_DIR = ROOT / "nnop.jl_b200" / "julia" / "NNopB200"
 SHIM = SHIM_DIR / "src" / "NNopB200.jl"
 EXT = SHIM_DIR / "ext" / "NNopB200NNopExt.jl"
@@ -42,8 +43,8 @@ def _c_kind(ctype, name):
     return {"int": "int", "int64_t": "int64", "size_t": "size", "float": "float"}[t]
 
 
-def header_prototypes():
-    src = _strip_c_comments(HEADER.read_text())
+def header_prototypes(with_diag=True):
+    src = _strip_c_comments(HEADER.read_text() + (DIAG_HEADER.read_text() if with_diag else ""))
     protos = {}
     for m in re.finditer(r"(?m)^\s*(int|size_t|const char\s*\*)\s+(nnop_\w+)\s*\(([^;{]*)\)\s*;", src):
         ret, name, params = m.group(1), m.group(2), m.group(3)
@@ -143,12 +144,13 @@ def test_every_ccall_matches_its_prototype(path):
 
 
 def test_shim_binds_every_product_entry_point():
-    """Every non-diagnostic symbol of the header is reachable from the shim."""
-    protos = header_prototypes()
+    """Every entry point of the product header (nnop_b200.h; the diagnostics live in nnop_b200_diag.h) is
+    reachable from the shim."""
+    protos = header_prototypes(with_diag=False)
     used = {c["sym"] for c in julia_ccalls(SHIM)}
-    diagnostics = {"nnop_version", "nnop_set_timing_events", "nnop_selftest_umma", "nnop_flash_attn_fwd",
-                   "nnop_flash_attn_bwd"}   # the _ws / _reuse_pair forms are supersets of the last two
-    missing = set(protos) - used - diagnostics
+    # the _ws / _reuse_pair forms are supersets of the plain ones
+    supersets = {"nnop_version", "nnop_flash_attn_fwd", "nnop_flash_attn_bwd", "nnop_flash_attn_varlen_fwd"}
+    missing = set(protos) - used - supersets
     assert not missing, missing
 
 
