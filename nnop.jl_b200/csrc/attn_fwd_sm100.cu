@@ -70,6 +70,7 @@ struct FwdParams {
   const int* cu_q;
   const int* cu_k;
   void* o_ptr;       // raw output pointer for partial tiles (a TMA store would spill into the next sequence)
+  int o_row_bytes;   // bytes of one output row as the caller sees it: E x sizeof(output element) (E may be < D)
   int64_t total_q;
   const uint8_t* kpad;  // (B, KL) key padding mask, 1 = attend, or nullptr (dense mode only)
   int nseq;             // packed mode: number of sequences
@@ -718,9 +719,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       if (q_row < QL) {
         const int64_t ri = packed ? static_cast<int64_t>(h) * p.total_q + q_off + q_row
                                   : static_cast<int64_t>(bh_q) * QL + q_row;
-        uint4* orow = reinterpret_cast<uint4*>(static_cast<T*>(p.o_ptr) + ri * D);
-#pragma unroll
-        for (int c = 0; c < D / 8; ++c) orow[c] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* orow = reinterpret_cast<uint4*>(static_cast<char*>(p.o_ptr) + ri * p.o_row_bytes);
+        for (int c = 0; c < p.o_row_bytes / 16; ++c) orow[c] = make_uint4(0u, 0u, 0u, 0u);
         p.lse[ri] = -INFINITY;
       }
     }
@@ -1375,6 +1375,7 @@ int launch_fwd_f32(const AttnParams& a) {
   fp.scale_log2 = a.scale * kLog2e;
   fp.f32_mult = f32_mults(blk);
   fp.cu_q = nullptr; fp.cu_k = nullptr; fp.o_ptr = a.o; fp.total_q = 0; fp.nseq = 0;
+  fp.o_row_bytes = a.E * static_cast<int>(sizeof(float));
   fp.lpt_group = 0;
   fp.kpad = a.kpad;
   dim3 grid((a.QL + 255) / 256, a.QH, a.B);
@@ -1412,6 +1413,7 @@ int launch_fwd(const AttnParams& a) {
   fp.scale_log2 = a.scale * kLog2e;
   fp.f32_mult = nullptr;
   fp.cu_q = a.cu_q; fp.cu_k = a.cu_k; fp.o_ptr = a.o; fp.total_q = a.total_q;
+  fp.o_row_bytes = a.E * static_cast<int>(sizeof(T));
   fp.kpad = packed ? nullptr : a.kpad;
   fp.nseq = a.nseq;
   fp.lpt_group = 0;
@@ -1465,6 +1467,7 @@ int launch_fwd_persist(const AttnParams& a, int ctas) {
   fp.scale_log2 = a.scale * kLog2e;
   fp.f32_mult = nullptr;
   fp.cu_q = a.cu_q; fp.cu_k = a.cu_k; fp.o_ptr = a.o; fp.total_q = a.total_q; fp.kpad = nullptr;
+  fp.o_row_bytes = a.E * static_cast<int>(sizeof(T));
   fp.nseq = a.nseq;
   fp.lpt_group = 0;
   // the tile counter lives in the caller's workspace (the library keeps no device state of its own):

@@ -119,8 +119,8 @@ __device__ __forceinline__ void store_vec<__nv_bfloat16>(__nv_bfloat16* p, const
 // are a dependent chain load -> reduce -> normalise -> store with few warps per SM, so each
 // barrier removed is latency off the chain (r01: two barriers per reduction, four per
 // layer-norm row).
-using RedBuf = float[2][2][kThreads / 32];
-template <int TPR>
+using RedBuf = float[2][2][16];   // up to 16 warps per CTA (the 512-thread backward)
+template <int TPR, int NW = kThreads / 32>
 __device__ __forceinline__ float row_sum(float v, RedBuf& red, int& parity) {
   v = warp_sum(v);
   if constexpr (TPR == 32) return v;
@@ -130,16 +130,16 @@ __device__ __forceinline__ float row_sum(float v, RedBuf& red, int& parity) {
   __syncthreads();
   float t = 0.f;
 #pragma unroll
-  for (int i = 0; i < kThreads / 32; ++i) t += r[i];
+  for (int i = 0; i < NW; ++i) t += r[i];
   return t;
 }
 // two sums in one hop (layer-norm backward: mean(w d xh) and mean(w d))
-template <int TPR>
+template <int TPR, int NW = kThreads / 32>
 __device__ __forceinline__ void row_sum2(float& a, float& b, RedBuf& red, int& parity) {
   a = warp_sum(a);
   b = warp_sum(b);
   if constexpr (TPR == 32) return;
-  float(*r)[kThreads / 32] = red[parity];
+  float(*r)[16] = red[parity];
   parity ^= 1;
   if ((threadIdx.x & 31) == 0) {
     r[0][threadIdx.x >> 5] = a;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void row_sum2(float& a, float& b, RedBuf& red, int& p
   __syncthreads();
   float ta = 0.f, tb = 0.f;
 #pragma unroll
-  for (int i = 0; i < kThreads / 32; ++i) {
+  for (int i = 0; i < NW; ++i) {
     ta += r[0][i];
     tb += r[1][i];
   }
@@ -478,15 +478,19 @@ rowwise_fwd_generic(T* __restrict__ y, float* __restrict__ stat0, float* __restr
 // backward kernels (vector path).  Persistent grid; CTA g handles row groups g, g+G, ...
 // partial layout: part0[g][emb] (dw), part1[g][emb] (db, layer norm only), fp32.
 // ---------------------------------------------------------------------------------------
-template <typename T, int TPR, int MAXV, int OP>
-__global__ void __launch_bounds__(kThreads, (MAXV <= 2 ? NNOP_ROWWISE_BWD_MINB : 1))
+// NT = threads per CTA.  Rows of more than 256 vectors run 512-thread CTAs (TPR = NT = 512): half the columns,
+// accumulators and registers per thread of a 256-thread CTA, twice the warps per SM to hide a row's dependent
+// chain (r02: layer-norm backward bf16 at emb 4096 sat at two 8-warp CTAs per SM with 110 registers).
+template <typename T, int TPR, int MAXV, int OP, int NT = kThreads>
+__global__ void __launch_bounds__(NT, (NT == 512 ? 2 : (MAXV <= 2 ? NNOP_ROWWISE_BWD_MINB : 1)))
 rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict__ part1,
                 const T* __restrict__ dy, const T* __restrict__ x_or_y,
                 const float* __restrict__ stat0, const float* __restrict__ stat1,
                 const T* __restrict__ w, int64_t emb, int64_t n, float offset) {
   constexpr int VE = VecIO<T>::N;
   constexpr int NP = VE / 2;
-  constexpr int RPB = kThreads / TPR;
+  constexpr int RPB = NT / TPR;
+  constexpr int NW = NT / 32;
   __shared__ RedBuf red;
   int parity = 0;
   const int t = threadIdx.x % TPR;
@@ -520,9 +524,9 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
   // Row groups are streamed through a 3-stage cp.async ring in shared memory.  Every thread
   // copies exactly the vectors it later reads itself, so the ring needs no block barrier, and a
   // CTA keeps two row groups of x and dy in flight while it reduces the current one.
-  extern __shared__ __align__(16) uint8_t ring[];  // [3 stages][x|dy][MAXV][256 threads] x 16 B
+  extern __shared__ __align__(16) uint8_t ring[];  // [3 stages][x|dy][MAXV][NT threads] x 16 B
   auto slot = [&](int st, int which, int i) {
-    return ring + ((static_cast<size_t>((st * 2 + which) * MAXV + i) * kThreads + threadIdx.x) << 4);
+    return ring + ((static_cast<size_t>((st * 2 + which) * MAXV + i) * NT + threadIdx.x) << 4);
   };
   auto fetch = [&](int64_t g, int st) {
     const int64_t row = g * RPB + sub;
@@ -578,7 +582,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
       for (int i = 0; i < MAXV; ++i)
 #pragma unroll
         for (int j = 0; j < NP; ++j) s2 = f2_fma(av[i][j], dv[i][j], s2);
-      const float2 ns = f2_dup(-row_sum<TPR>(s2.x + s2.y, red, parity));
+      const float2 ns = f2_dup(-row_sum<TPR, NW>(s2.x + s2.y, red, parity));
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
@@ -596,7 +600,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
       for (int i = 0; i < MAXV; ++i)
 #pragma unroll
         for (int j = 0; j < NP; ++j) dd2 = f2_fma(f2_mul(dv[i][j], wv[i][j]), av[i][j], dd2);
-      const float dd = row_sum<TPR>(dd2.x + dd2.y, red, parity);
+      const float dd = row_sum<TPR, NW>(dd2.x + dd2.y, red, parity);
       const float2 r2 = f2_dup(r), nc = f2_dup(-(r * r * r * dd * inv_n));
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
@@ -628,7 +632,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
           s2 = f2_add(s2, wd);
         }
       float c1 = s1.x + s1.y, c2 = s2.x + s2.y;
-      row_sum2<TPR>(c1, c2, red, parity);
+      row_sum2<TPR, NW>(c1, c2, red, parity);
       const float2 nc1 = f2_dup(-c1 * inv_n), nc2 = f2_dup(-c2 * inv_n);
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
@@ -882,19 +886,19 @@ int launch_bwd(void* dx, TW* dw, TW* db, const void* dy, const void* a, const fl
   // CTA streams rows back to back with its prefetch pipeline full
   int grid = plan.grid;
   int64_t n_part = plan.n_part;
-  auto run = [&](auto kern, int rows_per_cta, int maxv) {
-    const int smem = maxv > 0 ? 3 * 2 * maxv * kThreads * 16 : 0;
+  auto run = [&](auto kern, int rows_per_cta, int maxv, int nt = kThreads) {
+    const int smem = maxv > 0 ? 3 * 2 * maxv * nt * 16 : 0;
     if (smem > 32 * 1024)  // static smem (reduction scratch) counts against the 48 KB default too
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem) != cudaSuccess || occ < 1)
       occ = 1;
     if (occ > 4) occ = 4;
     const int64_t groups = (n + rows_per_cta - 1) / rows_per_cta;
     const int64_t cap = static_cast<int64_t>(sm_count()) * occ;
     grid = static_cast<int>(groups < cap ? groups : cap);
     n_part = static_cast<int64_t>(grid) * rows_per_cta;
-    kern<<<grid, kThreads, smem, st>>>(dxx, p0, p1, dyy, aa, s0, s1, ww, emb, n, offset);
+    kern<<<grid, nt, smem, st>>>(dxx, p0, p1, dyy, aa, s0, s1, ww, emb, n, offset);
   };
   if (plan.mode == 1) {
     if (nvec <= 32) run(rowwise_bwd_vec<T, 32, 1, OP>, 8, 1);
@@ -902,9 +906,9 @@ int launch_bwd(void* dx, TW* dw, TW* db, const void* dy, const void* a, const fl
     else run(rowwise_bwd_vec<T, 32, 4, OP>, 8, 4);
   } else if (plan.mode == 2) {
     if (nvec <= 256) run(rowwise_bwd_vec<T, 256, 1, OP>, 1, 1);
-    else if (nvec <= 512) run(rowwise_bwd_vec<T, 256, 2, OP>, 1, 2);
-    else if (nvec <= 1024) run(rowwise_bwd_vec<T, 256, 4, OP>, 1, 4);
-    else if constexpr (OP == 0) run(rowwise_bwd_vec<T, 256, 8, OP>, 1, 8);
+    else if (nvec <= 512) run(rowwise_bwd_vec<T, 512, 1, OP, 512>, 1, 1, 512);
+    else if (nvec <= 1024) run(rowwise_bwd_vec<T, 512, 2, OP, 512>, 1, 2, 512);
+    else if constexpr (OP == 0) run(rowwise_bwd_vec<T, 512, 4, OP, 512>, 1, 4, 512);
   } else {
     run(rowwise_bwd_generic<T, OP>, 1, 0);
   }

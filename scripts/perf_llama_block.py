@@ -38,3 +38,10 @@ for B in (1, 4):
           f"rope fwd {t_rope*1e3:.0f} us ({b_rope/t_rope/1e6:.0f} GB/s, {100*b_rope/t_rope/1e6/PK['hbm_gbs']:.0f}%) | "
           f"attn fwd {t_af:.3f} ms {f/t_af/1e9:.0f} TF/s bwd {t_ab:.3f} ms {2.5*f/t_ab/1e9:.0f} TF/s fwd+bwd {3.5*f/(t_af+t_ab)/1e9:.0f} TF/s "
           f"({100*3.5*f/(t_af+t_ab)/1e9/PK['bf16_tflops']:.0f}% of measured burst bf16)", flush=True)
+    # what fusing RoPE into the attention block could save at most = the RoPE launches themselves
+    # (forward: one launch on q, k; backward: one more on dq, dk), against the block with them
+    t_rope_b = T(lambda: nn.grad_llama_rope(q, k, cos=cos, sin=sin))
+    fwd_blk, trn_blk = t_rf + t_rope + t_af, t_rf + t_rope + t_af + t_ab + t_rope_b + t_rb
+    print(f"   f2 ceiling B={B}: forward-only block (rms_norm + rope + attention) {fwd_blk*1e3:.0f} us, rope {t_rope*1e3:.0f} us = "
+          f"{100*t_rope/fwd_blk:.1f}% | forward+backward block {trn_blk*1e3:.0f} us, rope fwd+bwd {(t_rope+t_rope_b)*1e3:.0f} us = "
+          f"{100*(t_rope+t_rope_b)/trn_blk:.1f}% (the backward needs the rotated q, k in HBM: not fusable there)", flush=True)
