@@ -478,9 +478,8 @@ rowwise_fwd_generic(T* __restrict__ y, float* __restrict__ stat0, float* __restr
 // backward kernels (vector path).  Persistent grid; CTA g handles row groups g, g+G, ...
 // partial layout: part0[g][emb] (dw), part1[g][emb] (db, layer norm only), fp32.
 // ---------------------------------------------------------------------------------------
-// NT = threads per CTA.  Rows of more than 256 vectors run 512-thread CTAs (TPR = NT = 512): half the columns,
-// accumulators and registers per thread of a 256-thread CTA, twice the warps per SM to hide a row's dependent
-// chain (r02: layer-norm backward bf16 at emb 4096 sat at two 8-warp CTAs per SM with 110 registers).
+// NT = threads per CTA (256 in production; the 512-thread form -- half the columns, accumulators and registers
+// per thread, twice the warps per SM -- is kept for the A/B recorded in launch_bwd: it lost).
 template <typename T, int TPR, int MAXV, int OP, int NT = kThreads>
 __global__ void __launch_bounds__(NT, (NT == 512 ? 2 : (MAXV <= 2 ? NNOP_ROWWISE_BWD_MINB : 1)))
 rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict__ part1,
@@ -905,10 +904,15 @@ int launch_bwd(void* dx, TW* dw, TW* db, const void* dy, const void* a, const fl
     else if (nvec <= 64) run(rowwise_bwd_vec<T, 32, 2, OP>, 8, 2);
     else run(rowwise_bwd_vec<T, 32, 4, OP>, 8, 4);
   } else if (plan.mode == 2) {
+    // (512-thread CTAs -- rowwise_bwd_vec<T, 512, MAXV / 2, OP, 512>: half the registers, twice the warps per
+    // SM -- were measured SLOWER for rows of 257..1024 vectors: layer-norm backward bf16 at emb 4096 59.6 vs
+    // 52.4 us at 8192 rows, 404 vs 350 us at 65536.  The kernel is bound by instruction issue (10 packed FP
+    // ops per element pair against 6 for RMS norm, which runs at 95 %), not by latency, so more warps only add
+    // barrier width.  profiles/r02_perf_rowwise_nt512.txt)
     if (nvec <= 256) run(rowwise_bwd_vec<T, 256, 1, OP>, 1, 1);
-    else if (nvec <= 512) run(rowwise_bwd_vec<T, 512, 1, OP, 512>, 1, 1, 512);
-    else if (nvec <= 1024) run(rowwise_bwd_vec<T, 512, 2, OP, 512>, 1, 2, 512);
-    else if constexpr (OP == 0) run(rowwise_bwd_vec<T, 512, 4, OP, 512>, 1, 4, 512);
+    else if (nvec <= 512) run(rowwise_bwd_vec<T, 256, 2, OP>, 1, 2);
+    else if (nvec <= 1024) run(rowwise_bwd_vec<T, 256, 4, OP>, 1, 4);
+    else if constexpr (OP == 0) run(rowwise_bwd_vec<T, 256, 8, OP>, 1, 8);
   } else {
     run(rowwise_bwd_generic<T, OP>, 1, 0);
   }
