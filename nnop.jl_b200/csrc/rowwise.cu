@@ -617,22 +617,25 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
       }
     } else {
       // xh=(x-mu)r; c1=mean(w d xh); c2=mean(w d); dx=(w d-(xh c1+c2)) r   (src/layer_norm.jl:95-136)
+      // The kernel is issue-bound for 16-bit rows, so the operation count per element pair matters: 8 packed
+      // ops here (xh 1, w*dy 1, two row sums 2, two accumulators 2, dx 2), w*dy kept in registers between phases.
       const float mu = st0_cur;
       const float r = st1_cur;
-      const float2 r2 = f2_dup(r), nmu = f2_dup(-mu);
+      const float2 r2 = f2_dup(r), nmur = f2_dup(-mu * r);
       float2 s1 = f2_dup(0.f), s2 = f2_dup(0.f);
+      float2 wd[MAXV][NP];
 #pragma unroll
       for (int i = 0; i < MAXV; ++i)
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
-          av[i][j] = f2_mul(f2_add(av[i][j], nmu), r2);  // xh (padding vectors: w = d = 0 below)
-          const float2 wd = f2_mul(dv[i][j], wv[i][j]);
-          s1 = f2_fma(wd, av[i][j], s1);
-          s2 = f2_add(s2, wd);
+          av[i][j] = f2_fma(av[i][j], r2, nmur);  // xh = (x - mu) r  (padding vectors: w = d = 0 below)
+          wd[i][j] = f2_mul(dv[i][j], wv[i][j]);
+          s1 = f2_fma(wd[i][j], av[i][j], s1);
+          s2 = f2_add(s2, wd[i][j]);
         }
       float c1 = s1.x + s1.y, c2 = s2.x + s2.y;
       row_sum2<TPR, NW>(c1, c2, red, parity);
-      const float2 nc1 = f2_dup(-c1 * inv_n), nc2 = f2_dup(-c2 * inv_n);
+      const float2 nc1r = f2_dup(-c1 * inv_n * r), nc2r = f2_dup(-c2 * inv_n * r);
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
@@ -642,7 +645,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
           for (int j = 0; j < NP; ++j) {
             acc0[i][j] = f2_fma(dv[i][j], av[i][j], acc0[i][j]);
             acc1[i][j] = f2_add(acc1[i][j], dv[i][j]);
-            o[j] = f2_mul(f2_fma(dv[i][j], wv[i][j], f2_fma(av[i][j], nc1, nc2)), r2);
+            o[j] = f2_fma(wd[i][j], r2, f2_fma(av[i][j], nc1r, nc2r));   // (w d - (xh c1 + c2)) r
           }
           store_pairs<T>(dxr + static_cast<int64_t>(vi) * VE, o);
         }

@@ -15,7 +15,11 @@ What pins this oracle instead:
     (RoPE on all-ones q/k, ``test/rope_tests.jl:21-56``; see tests/test_oracle.py);
   * an independent implementation (``torch.nn.functional.scaled_dot_product_attention``,
     ``torch.nn.functional.layer_norm`` / ``rms_norm`` / ``softmax``) and torch autograd
-    on the fp64 graph for every closed-form gradient.
+    on the fp64 graph for every closed-form gradient;
+  * ``oracle/ref_kernels.py``: a NumPy restatement of the reference's FUSED KERNELS, tile loop by
+    tile loop, which must -- and does, to 1e-11 (tests/test_oracle_vs_reference_kernels.py) -- equal
+    these naive functions on the reference's test shapes: the equality the reference's own suite
+    asserts on a GPU.
 
 Layout.  Julia arrays are column-major; a Julia ``(E, L, H, B)`` array is byte-identical
 to a contiguous row-major tensor of shape ``(B, H, L, E)``.  Everything here uses the
