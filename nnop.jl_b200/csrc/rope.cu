@@ -12,6 +12,23 @@
 namespace nnop {
 namespace {
 
+// packed fp32x2 arithmetic (two lanes per issue slot on sm_100)
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)),
+        "l"(reinterpret_cast<const uint64_t&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return d;
+}
+
 template <typename T, int VE>
 __device__ __forceinline__ void ld(const T* p, float (&o)[VE]) {
   if constexpr (VE == 1) {
@@ -53,48 +70,60 @@ __device__ __forceinline__ void ldf(const float* p, float (&o)[VE]) {
   }
 }
 
+// Thread mapping (r02; the r01 kernel spent 72 % of its issue slots, mostly on three 64-bit divisions per
+// vector): a thread keeps ONE vector position j of the half row for its whole life and a CTA owns a block of
+// sequence positions of ONE (batch, head) -- blockIdx.x = (b * HT + hh) * nlb + lb -- so the only divisions
+// are two 32-bit ones per thread, once.  Rows are then walked with constant strides.
 template <typename T, int VE>
 __global__ void __launch_bounds__(256)
 llama_rope_kernel(T* q_out, T* k_out, const T* q_in, const T* k_in,
                   const float* __restrict__ cosp, const float* __restrict__ sinp, int E, int64_t L,
-                  int QH, int KH, int B, float sin_sign) {
+                  int QH, int KH, int B, float sin_sign, int HV, int rpb, int nlb, int rows_per_cta) {
   const int half = E / 2;
-  const int HV = half / VE;
   const int HT = QH + KH;
-  const int64_t total = static_cast<int64_t>(B) * HT * L * HV;
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int j = static_cast<int>(idx % HV);
-    int64_t r = idx / HV;
-    const int64_t l = r % L;
-    r /= L;
-    const int hh = static_cast<int>(r % HT);
-    const int64_t b = r / HT;
-    const T* src;
-    T* dst;
-    if (hh < QH) {
-      const int64_t off = ((b * QH + hh) * L + l) * E;
-      src = q_in + off;
-      dst = q_out + off;
-    } else {
-      const int64_t off = ((b * KH + (hh - QH)) * L + l) * E;
-      src = k_in + off;
-      dst = k_out + off;
-    }
-    const int64_t coff = (b * L + l) * E + static_cast<int64_t>(j) * VE;
-    float x1[VE], x2[VE], c[VE], s[VE], o1[VE], o2[VE];
-    ld<T, VE>(src + j * VE, x1);
-    ld<T, VE>(src + half + j * VE, x2);
-    ldf<VE>(cosp + coff, c);
-    ldf<VE>(sinp + coff, s);
+  const int j = threadIdx.x % HV;
+  const int rl = threadIdx.x / HV;            // row of the CTA's current group of rpb rows
+  if (rl >= rpb) return;
+  const unsigned bh = blockIdx.x / nlb, lb = blockIdx.x - bh * nlb;
+  const int b = bh / HT, hh = bh - b * HT;
+  const bool is_q = hh < QH;
+  const int64_t head_off = is_q ? (static_cast<int64_t>(b) * QH + hh) * L * E
+                                : (static_cast<int64_t>(b) * KH + (hh - QH)) * L * E;
+  const T* src = (is_q ? q_in : k_in) + head_off + j * VE;
+  T* dst = (is_q ? q_out : k_out) + head_off + j * VE;
+  const float* cp = cosp + static_cast<int64_t>(b) * L * E + j * VE;
+  const float* sp = sinp + static_cast<int64_t>(b) * L * E + j * VE;
+  const int64_t l0 = static_cast<int64_t>(lb) * rows_per_cta;
+  const int64_t l1 = l0 + rows_per_cta < L ? l0 + rows_per_cta : L;
+  for (int64_t l = l0 + rl; l < l1; l += rpb) {
+    const int64_t ro = l * E;
+    float x1[VE], x2[VE], c[VE], sn[VE], o1[VE], o2[VE];
+    ld<T, VE>(src + ro, x1);
+    ld<T, VE>(src + ro + half, x2);
+    ldf<VE>(cp + ro, c);
+    ldf<VE>(sp + ro, sn);
+    if constexpr (VE % 2 == 0) {   // packed fp32x2: 6 operations per element pair instead of 10
+      const float2 sg = make_float2(sin_sign, sin_sign), nsg = make_float2(-sin_sign, -sin_sign);
 #pragma unroll
-    for (int i = 0; i < VE; ++i) {
-      const float sv = s[i] * sin_sign;
-      o1[i] = x1[i] * c[i] - x2[i] * sv;
-      o2[i] = x2[i] * c[i] + x1[i] * sv;
+      for (int i = 0; i < VE; i += 2) {
+        const float2 a = make_float2(x1[i], x1[i + 1]), bb = make_float2(x2[i], x2[i + 1]);
+        const float2 cc = make_float2(c[i], c[i + 1]), ss = make_float2(sn[i], sn[i + 1]);
+        const float2 sv = f2_mul(ss, sg), nsv = f2_mul(ss, nsg);
+        const float2 r1 = f2_fma(bb, nsv, f2_mul(a, cc));     // x1 c - x2 s
+        const float2 r2 = f2_fma(a, sv, f2_mul(bb, cc));      // x2 c + x1 s
+        o1[i] = r1.x; o1[i + 1] = r1.y;
+        o2[i] = r2.x; o2[i + 1] = r2.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VE; ++i) {
+        const float sv = sn[i] * sin_sign;
+        o1[i] = x1[i] * c[i] - x2[i] * sv;
+        o2[i] = x2[i] * c[i] + x1[i] * sv;
+      }
     }
-    st<T, VE>(dst + j * VE, o1);
-    st<T, VE>(dst + half + j * VE, o2);
+    st<T, VE>(dst + ro, o1);
+    st<T, VE>(dst + ro + half, o2);
   }
 }
 
@@ -108,19 +137,29 @@ int launch_rope(void* q_out, void* k_out, const void* q_in, const void* k_in, co
   const bool vec = half % VEC == 0 && al(q_out) && al(k_out) && al(q_in) && al(k_in) && al(cosp) &&
                    al(sinp);
   const int ve = vec ? VEC : 1;
-  const int64_t total = static_cast<int64_t>(B) * (QH + KH) * L * (half / ve);
+  const int HV = half / ve;
+  if (HV > 256) return fail(NNOP_ERR_UNSUPPORTED_E, "RoPE head dim `%d` is not supported.", E);
+  const int64_t total = static_cast<int64_t>(B) * (QH + KH) * L * HV;
   if (total == 0) return NNOP_OK;
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
-  if (blocks > cap) blocks = cap;
+  const int rpb = 256 / HV;                       // rows a CTA covers per pass
+  // rows per CTA: enough passes to amortise the setup, enough CTAs (>= ~8 per SM) to fill the machine
+  const int64_t bh = static_cast<int64_t>(B) * (QH + KH);
+  int64_t passes = 8;
+  while (passes > 1 && bh * ((L + rpb * passes - 1) / (rpb * passes)) < 8LL * sm_count()) passes >>= 1;
+  const int rows_per_cta = static_cast<int>(rpb * passes);
+  const int64_t nlb = (L + rows_per_cta - 1) / rows_per_cta;
+  if (bh * nlb >= (1LL << 31)) return fail(NNOP_ERR_SHAPE, "RoPE problem too large for one launch");
+  const unsigned blocks = static_cast<unsigned>(bh * nlb);
   if (vec)
-    llama_rope_kernel<T, VEC><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+    llama_rope_kernel<T, VEC><<<blocks, 256, 0, st>>>(
         static_cast<T*>(q_out), static_cast<T*>(k_out), static_cast<const T*>(q_in),
-        static_cast<const T*>(k_in), cosp, sinp, E, L, QH, KH, B, sin_sign);
+        static_cast<const T*>(k_in), cosp, sinp, E, L, QH, KH, B, sin_sign, HV, rpb, static_cast<int>(nlb),
+        rows_per_cta);
   else
-    llama_rope_kernel<T, 1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+    llama_rope_kernel<T, 1><<<blocks, 256, 0, st>>>(
         static_cast<T*>(q_out), static_cast<T*>(k_out), static_cast<const T*>(q_in),
-        static_cast<const T*>(k_in), cosp, sinp, E, L, QH, KH, B, sin_sign);
+        static_cast<const T*>(k_in), cosp, sinp, E, L, QH, KH, B, sin_sign, HV, rpb, static_cast<int>(nlb),
+        rows_per_cta);
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
 }
