@@ -144,8 +144,8 @@ int launch_rope(void* q_out, void* k_out, const void* q_in, const void* k_in, co
   const int rpb = 256 / HV;                       // rows a CTA covers per pass
   // rows per CTA: enough passes to amortise the setup, enough CTAs (>= ~8 per SM) to fill the machine
   const int64_t bh = static_cast<int64_t>(B) * (QH + KH);
-  int64_t passes = 8;
-  while (passes > 1 && bh * ((L + rpb * passes - 1) / (rpb * passes)) < 8LL * sm_count()) passes >>= 1;
+  int64_t passes = 4;   // measured: 2-4 passes best at config C3 (profiles/r02_perf_rope_passes.txt)
+  while (passes > 1 && bh * ((L + rpb * passes - 1) / (rpb * passes)) < 24LL * sm_count()) passes >>= 1;
   const int rows_per_cta = static_cast<int>(rpb * passes);
   const int64_t nlb = (L + rows_per_cta - 1) / rows_per_cta;
   if (bh * nlb >= (1LL << 31)) return fail(NNOP_ERR_SHAPE, "RoPE problem too large for one launch");

@@ -492,6 +492,9 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
   constexpr int NW = NT / 32;
   __shared__ RedBuf red;
   int parity = 0;
+  // the partial-reduction kernel that follows may be scheduled as soon as SMs free up (it waits for this
+  // grid's completion itself: griddepcontrol.wait); a no-op when nothing depends programmatically
+  if constexpr (OP != 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int t = threadIdx.x % TPR;
   const int sub = threadIdx.x / TPR;
   const int nvec = static_cast<int>(emb / VE);

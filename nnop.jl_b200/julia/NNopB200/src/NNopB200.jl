@@ -13,15 +13,16 @@
 module NNopB200
 
 using CUDA
+using BFloat16s: BFloat16        # the element type CUDA.jl itself uses for bf16 CuArrays
 import ChainRulesCore as CRC
 
 const libnnop_b200 = get(ENV, "NNOP_B200_LIB", joinpath(@__DIR__, "..", "..", "..", "lib", "libnnop_b200.so"))
 const Maybe{T} = Union{Nothing, T}                                   # src/NNop.jl:13
-const FloatT = Union{Float32, Float16, CUDA.BFloat16}
+const FloatT = Union{Float32, Float16, BFloat16}
 
 dtype_code(::Type{Float32}) = Cint(0)
 dtype_code(::Type{Float16}) = Cint(1)
-dtype_code(::Type{CUDA.BFloat16}) = Cint(2)
+dtype_code(::Type{BFloat16}) = Cint(2)
 
 function check(status::Cint)
     status == 0 && return
@@ -164,7 +165,7 @@ function _flash_attention_varlen(
     q::CuArray{T,3}, k::CuArray{T,3}, v::CuArray{T,3},
     cu_seqlens_q::CuVector{Int32}, cu_seqlens_k::CuVector{Int32},
     max_seqlen_q::Integer, max_seqlen_k::Integer; causal::Bool,
-) where T <: Union{Float16, CUDA.BFloat16}
+) where T <: Union{Float16, BFloat16}
     E, TQ, QH = size(q)
     KE, TK, KH = size(k)
     E == KE || error("Embedding dim of Q `$E` must be the same as of K `$KE`.")
@@ -189,7 +190,7 @@ function ∇flash_attention_varlen(
     Δ::CuArray{T,3}, o::CuArray{T,3}, lse, q::CuArray{T,3}, k::CuArray{T,3}, v::CuArray{T,3},
     cu_seqlens_q::CuVector{Int32}, cu_seqlens_k::CuVector{Int32},
     max_seqlen_q::Integer, max_seqlen_k::Integer; causal::Bool,
-) where T <: Union{Float16, CUDA.BFloat16}
+) where T <: Union{Float16, BFloat16}
     E, TQ, QH = size(q)
     _, TK, KH = size(k)
     nseq = length(cu_seqlens_q) - 1
