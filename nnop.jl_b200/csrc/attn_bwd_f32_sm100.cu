@@ -593,10 +593,10 @@ int attn_f32_bwd(const AttnParams& a) {
   }
   NNOP_CUDA_CHECK(cudaMemsetAsync(a.dk, 0, static_cast<size_t>(BHk) * a.KL * E * sizeof(float), a.stream));
   NNOP_CUDA_CHECK(cudaMemsetAsync(a.dv, 0, static_cast<size_t>(BHk) * a.KL * E * sizeof(float), a.stream));
-  if (int rc = attn_split_f32_rows(qs, a.q, BH * a.QL, E, f32_exp_slot(blk, 0), a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(dos, a.dO, BH * a.QL, E, f32_exp_slot(blk, 3), a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(ks, a.k, BHk * a.KL, E, f32_exp_slot(blk, 1), a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(vs, a.v, BHk * a.KL, E, f32_exp_slot(blk, 2), a.stream)) return rc;
+  if (int rc = attn_split_f32_rows(qs, a.q, BH * a.QL, E, f32_in_scale(blk, 0), a.stream)) return rc;
+  if (int rc = attn_split_f32_rows(dos, a.dO, BH * a.QL, E, f32_in_scale(blk, 3), a.stream)) return rc;
+  if (int rc = attn_split_f32_rows(ks, a.k, BHk * a.KL, E, f32_in_scale(blk, 1), a.stream)) return rc;
+  if (int rc = attn_split_f32_rows(vs, a.v, BHk * a.KL, E, f32_in_scale(blk, 2), a.stream)) return rc;
   alignas(64) CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdq;
   const uint64_t bhq = static_cast<uint64_t>(BH), bhk = static_cast<uint64_t>(BHk);
   if (int rc = make_tmap_3d(&tq, qs, NNOP_F16, 128, a.QL, bhq, 64, 128)) return rc;

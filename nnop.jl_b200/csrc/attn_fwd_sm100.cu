@@ -1267,12 +1267,12 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
 // percent.  The power of two is exact; the kernels undo it with the multipliers below.
 __global__ void __launch_bounds__(256)
 split_f32_kernel(__half* __restrict__ out, const float* __restrict__ in, int64_t n4,
-                 const int* __restrict__ exp_slot, int per_row) {
+                 const float* __restrict__ scale_slot, int per_row) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;  // one float4 per thread
   if (i >= n4) return;
-  const int e = exp_slot ? -__ldg(exp_slot) : 0;
+  const float sc = scale_slot ? __ldg(scale_slot) : 1.f;   // 2^-e_x: an exact power of two
   float4 x = reinterpret_cast<const float4*>(in)[i];
-  x.x = ldexpf(x.x, e); x.y = ldexpf(x.y, e); x.z = ldexpf(x.z, e); x.w = ldexpf(x.w, e);
+  x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
   // per_row = E / 4 float4 per E-float row (16 for E = 64); narrower rows leave the rest of each 64-wide
   // half zero, which is what lets E = 16 / 32 ride the same 128-wide kernels
   const int64_t row = i / per_row;
@@ -1286,24 +1286,27 @@ split_f32_kernel(__half* __restrict__ out, const float* __restrict__ in, int64_t
   for (int z = c4 + per_row; z < 16; z += per_row) o[z] = o[16 + z] = make_uint2(0u, 0u);
 }
 
-int launch_split(__half* out, const void* in, int64_t rows, int E, const int* exp_slot, cudaStream_t st) {
+int launch_split(__half* out, const void* in, int64_t rows, int E, const float* scale_slot, cudaStream_t st) {
   const int64_t n4 = rows * (E / 4);
   if (n4 == 0) return NNOP_OK;
   split_f32_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(out, static_cast<const float*>(in), n4,
-                                                                           exp_slot, E / 4);
+                                                                           scale_slot, E / 4);
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
 }
 
 // ---- Float32 scale block (kF32ScaleBytes at the end of the Float32 workspaces) ----
-//   u32[0..3]  bit patterns of |q|max, |k|max, |v|max, |dO|max (atomicMax; non-negative floats order as uints)
-//   i32[4..7]  their binary exponents e_q, e_k, e_v, e_dO (0 for an all-zero or non-finite tensor)
-//   f32[8..14] multipliers, see F32Mult in internal.h
+//   u32[0..3]   bit patterns of |q|max, |k|max, |v|max, |dO|max (atomicMax; non-negative floats order as uints)
+//   i32[4..7]   their binary exponents e_q, e_k, e_v, e_dO (0 for an all-zero or non-finite tensor), clamped to
+//               [-120, 120] so that 2^-e stays a normal float
+//   f32[8..14]  multipliers, see F32Mult in internal.h
+//   f32[16..19] 2^-e_x, what the split kernels multiply the inputs by
+//   u32[20]     blocks of the |x|max pass that have finished: the last one writes [4..19] (no extra launch)
 struct AbsmaxArgs {
   const float* ptr[4];
   int64_t n4[4];
 };
-__global__ void __launch_bounds__(256) absmax_f32_kernel(uint32_t* __restrict__ slots, const AbsmaxArgs a) {
+__global__ void __launch_bounds__(256) absmax_f32_kernel(uint32_t* __restrict__ blk, const AbsmaxArgs a) {
   const int which = blockIdx.y;
   const float4* in = reinterpret_cast<const float4*>(a.ptr[which]);
   const int64_t n4 = a.n4[which];
@@ -1317,22 +1320,25 @@ __global__ void __launch_bounds__(256) absmax_f32_kernel(uint32_t* __restrict__ 
   __shared__ float red[8];
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x != 0) return;
 #pragma unroll
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
-    if (m > 0.f) atomicMax(slots + which, __float_as_uint(m));
-  }
-}
-__global__ void f32_scales_finalize_kernel(uint32_t* __restrict__ blk) {
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  if (m > 0.f) atomicMax(blk + which, __float_as_uint(m));
+  __threadfence();
+  if (atomicAdd(blk + 20, 1u) != gridDim.x * gridDim.y - 1) return;
+  // last block: exponents, input scales and the multipliers that undo them
+  __threadfence();
   int e[4];
+  float* f = reinterpret_cast<float*>(blk);
   for (int i = 0; i < 4; ++i) {
-    const float m = __uint_as_float(blk[i]);
+    const float mx = __uint_as_float(atomicOr(blk + i, 0u));   // (atomic read: the other blocks' maxima)
     int ex = 0;
-    if (m > 0.f && m <= 3.4028234e38f) frexpf(m, &ex);
+    if (mx > 0.f && mx <= 3.4028234e38f) frexpf(mx, &ex);
+    ex = ex < -120 ? -120 : (ex > 120 ? 120 : ex);
     e[i] = ex;
     reinterpret_cast<int*>(blk)[4 + i] = ex;
+    f[16 + i] = ldexpf(1.f, -ex);
   }
-  float* f = reinterpret_cast<float*>(blk);
   const int eq = e[0], ek = e[1], ev = e[2], edo = e[3];
   f[8 + F32Mult::kLogits] = ldexpf(1.f, eq + ek);
   f[8 + F32Mult::kO] = ldexpf(1.f, ev);
@@ -1355,9 +1361,9 @@ int launch_fwd_f32(const AttnParams& a) {
   T* vs = ks + rk * 128;
   void* blk = vs + rk * 128;   // scale block (256-byte aligned: every copy is a multiple of 256 bytes)
   if (int rc = attn_f32_scales(blk, a.q, rq * a.E, a.k, rk * a.E, a.v, rk * a.E, nullptr, 0, a.stream)) return rc;
-  if (int rc = launch_split(qs, a.q, rq, a.E, f32_exp_slot(blk, 0), a.stream)) return rc;
-  if (int rc = launch_split(ks, a.k, rk, a.E, f32_exp_slot(blk, 1), a.stream)) return rc;
-  if (int rc = launch_split(vs, a.v, rk, a.E, f32_exp_slot(blk, 2), a.stream)) return rc;
+  if (int rc = launch_split(qs, a.q, rq, a.E, f32_in_scale(blk, 0), a.stream)) return rc;
+  if (int rc = launch_split(ks, a.k, rk, a.E, f32_in_scale(blk, 1), a.stream)) return rc;
+  if (int rc = launch_split(vs, a.v, rk, a.E, f32_in_scale(blk, 2), a.stream)) return rc;
   alignas(64) CUtensorMap tq, tk, tv, to;
   const uint64_t bhq = static_cast<uint64_t>(a.B) * a.QH, bhk = static_cast<uint64_t>(a.B) * a.KH;
   if (int rc = make_tmap_3d(&tq, qs, NNOP_F16, D, a.QL, bhq, 64, 128)) return rc;
@@ -1516,9 +1522,9 @@ bool attn_sm100_supported(const AttnParams& a, bool backward) {
   return true;
 }
 
-int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, int E, const int* exp_slot,
+int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, int E, const float* scale_slot,
                         cudaStream_t st) {
-  return launch_split(static_cast<__half*>(out_bf16x2), in_f32, rows, E, exp_slot, st);
+  return launch_split(static_cast<__half*>(out_bf16x2), in_f32, rows, E, scale_slot, st);
 }
 
 int attn_f32_scales(void* block, const void* q, int64_t nq, const void* k, int64_t nk, const void* v,
@@ -1537,7 +1543,6 @@ int attn_f32_scales(void* block, const void* q, int64_t nq, const void* k, int64
   if (gx < 1) gx = 1;
   if (gx > 4 * sm_count()) gx = 4 * sm_count();
   absmax_f32_kernel<<<dim3(static_cast<unsigned>(gx), dO ? 4 : 3), 256, 0, st>>>(static_cast<uint32_t*>(block), a);
-  f32_scales_finalize_kernel<<<1, 1, 0, st>>>(static_cast<uint32_t*>(block));
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
 }

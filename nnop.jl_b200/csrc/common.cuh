@@ -196,8 +196,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > NNOP_MBAR_TIMEOUT_CYCLES) {
+#ifndef NNOP_MBAR_NO_PRINTF   // (the printf call's ABI -- argument buffer, caller-saved registers -- is what
+                              // ptxas reports as most of these kernels' "spill" bytes; it only runs here)
       printf("nnop: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+#endif
       __trap();
     }
   }

@@ -98,7 +98,8 @@ size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, 
 // Float32 tensor-core path (E = 64): every operand tensor is carried as two fp16 terms of x * 2^-e, e the
 // tensor's own binary exponent, so that fp16's range never clips or flushes it.  The 256-byte scale block at
 // the end of the Float32 workspaces holds |x|max bit patterns [u32 0..3: q, k, v, dO], the exponents
-// [i32 4..7] and the multipliers the kernels apply to undo the scaling [f32 8 + F32Mult::k*].
+// [i32 4..7], the multipliers the kernels apply to undo the scaling [f32 8 + F32Mult::k*], the input scales
+// 2^-e_x [f32 16..19] and the block counter of the |x|max pass [u32 20].
 constexpr size_t kF32ScaleBytes = 256;
 constexpr size_t kFwdCounterBytes = 256;   // 16-bit forward workspace: tile counter of the persistent kernel
 struct F32Mult {
@@ -112,14 +113,15 @@ struct F32Mult {
     kDPair = 6      // 2^(e_dO + e_v): dpair = kDPair * dS'
   };
 };
-inline const int* f32_exp_slot(const void* block, int which) { return static_cast<const int*>(block) + 4 + which; }
+// 2^-e_x of tensor `which` (0 q, 1 k, 2 v, 3 dO): what the split kernel multiplies by
+inline const float* f32_in_scale(const void* block, int which) { return static_cast<const float*>(block) + 16 + which; }
 inline const float* f32_mults(const void* block) { return static_cast<const float*>(block) + 8; }
 // memset + |x|max of q, k, v (and dO, may be NULL) + exponents / multipliers; n* = element counts
 int attn_f32_scales(void* block, const void* q, int64_t nq, const void* k, int64_t nk, const void* v,
                     int64_t nv, const void* dO, int64_t ndo, cudaStream_t st);
-// (rows, E) fp32, E in {16, 32, 64} -> (rows, 128) fp16 rows [hi(64) | lo(64)] with x * 2^-(*exp_slot) ~ hi + lo
+// (rows, E) fp32, E in {16, 32, 64} -> (rows, 128) fp16 rows [hi(64) | lo(64)] with x * (*scale_slot) ~ hi + lo
 // (columns >= E of each half are written as zeros)
-int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, int E, const int* exp_slot,
+int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, int E, const float* scale_slot,
                         cudaStream_t st);
 // attn_bwd_f32_sm100.cu -- Float32 (E = 64) backward on the tensor cores (split-bf16 operands)
 size_t attn_f32_bwd_workspace_bytes(int QL, int KL, int QH, int KH, int B);
