@@ -552,3 +552,69 @@ def test_duo_backward_matches_one_cta_per_tile(nnop, causal, E):
                 assert max_abs(got[0], ref[0]) <= 2 ** -7 * max(1.0, ref[0].abs().max().item()), (B, QH, KH, QL, KL)
     finally:
         nnop.set_bwd_pair_mode(0)
+
+
+def test_stateless_abi_graph_replay_and_threads(nnop):
+    """The product ABI keeps no device-side or process-wide state (round 2: the persistent kernels' tile counters
+    live in the caller's workspace).  (1) A forward + backward captured into a CUDA graph replays to the same
+    bits, also when two captured graphs with their own workspaces replay concurrently on two streams.  (2) Two
+    host threads driving different streams at the same time get the results a single thread gets."""
+    import threading
+    B, H, L, E = 8, 16, 1024, 64          # E = 64, deep tile queue: persistent forward and backward
+    mk = lambda seed: tuple(t.cuda() for t in _inputs(B, H, H, L, L, E, torch.bfloat16, seed)[:4])
+    sets = [mk(900), mk(901)]
+    ref = []
+    for q, k, v, dO in sets:
+        o, lse = nnop._flash_attention(q, k, v, causal=True)
+        ref.append((o, lse) + tuple(nnop.grad_flash_attention(dO, o, lse, q, k, v, causal=True)[:3]))
+    torch.cuda.synchronize()
+
+    # (1) graphs
+    graphs, outs, streams = [], [], [torch.cuda.Stream(), torch.cuda.Stream()]
+    for (q, k, v, dO), st in zip(sets, streams):
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            o, lse = nnop._flash_attention(q, k, v, causal=True)          # warm-up on the capture stream
+            nnop.grad_flash_attention(dO, o, lse, q, k, v, causal=True)
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            o, lse = nnop._flash_attention(q, k, v, causal=True)
+            dq, dk, dv, _ = nnop.grad_flash_attention(dO, o, lse, q, k, v, causal=True)
+        graphs.append(g)
+        outs.append((o, lse, dq, dk, dv))
+    for _ in range(3):
+        for g, st in zip(graphs, streams):       # both graphs in flight at once, each on its own stream
+            with torch.cuda.stream(st):
+                g.replay()
+    torch.cuda.synchronize()
+    for got, want in zip(outs, ref):
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        assert torch.equal(got[3], want[3]) and torch.equal(got[4], want[4])
+        assert max_abs(got[2], want[2]) <= 2 ** -7 * max(1.0, want[2].abs().max().item())
+
+    # (2) threads
+    results, errors = [None, None], []
+
+    def work(i):
+        try:
+            st = torch.cuda.Stream()
+            q, k, v, dO = sets[i]
+            with torch.cuda.stream(st):
+                for _ in range(4):
+                    o, lse = nnop._flash_attention(q, k, v, causal=True)
+                    dq, dk, dv, _ = nnop.grad_flash_attention(dO, o, lse, q, k, v, causal=True)
+            st.synchronize()
+            results[i] = (o, lse, dq, dk, dv)
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    for got, want in zip(results, ref):
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        assert torch.equal(got[3], want[3]) and torch.equal(got[4], want[4])
