@@ -1311,8 +1311,17 @@ __global__ void __launch_bounds__(256) absmax_f32_kernel(uint32_t* __restrict__ 
   const float4* in = reinterpret_cast<const float4*>(a.ptr[which]);
   const int64_t n4 = a.n4[which];
   float m = 0.f;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n4;
-       i += static_cast<int64_t>(gridDim.x) * 256) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {   // four independent loads in flight per thread
+    const float4 x0 = in[i], x1 = in[i + stride], x2 = in[i + 2 * stride], x3 = in[i + 3 * stride];
+    const float m0 = fmaxf(fmaxf(fabsf(x0.x), fabsf(x0.y)), fmaxf(fabsf(x0.z), fabsf(x0.w)));
+    const float m1 = fmaxf(fmaxf(fabsf(x1.x), fabsf(x1.y)), fmaxf(fabsf(x1.z), fabsf(x1.w)));
+    const float m2 = fmaxf(fmaxf(fabsf(x2.x), fabsf(x2.y)), fmaxf(fabsf(x2.z), fabsf(x2.w)));
+    const float m3 = fmaxf(fmaxf(fabsf(x3.x), fabsf(x3.y)), fmaxf(fabsf(x3.z), fabsf(x3.w)));
+    m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+  }
+  for (; i < n4; i += stride) {
     const float4 x = in[i];
     m = fmaxf(fmaxf(m, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
   }

@@ -31,5 +31,13 @@ for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 1):
     qr, kr = nn.llama_rope(q, k, cos=cos, sin=sin)
     o, lse = nn._flash_attention(qr, kr, v, causal=True)
     nn.grad_flash_attention(torch.randn_like(o), o, lse, qr, kr, v, causal=True)   # prep / post kernels
+    # the reference's benchmark shape with a pair bias (benchmarks/main.jl:305-386: Float32 E=64 L=2048 H=4 B=4):
+    # layout kernels of the bias (pair -> head-major, dpair back), |x|max pass and fp16 split of the Float32 path
+    g = torch.Generator(device="cuda").manual_seed(0)
+    Bp, Hp, Lp, Ep = 4, 4, 2048, 64
+    qf, kf, vf, dOf = (torch.randn(Bp, Hp, Lp, Ep, device="cuda", generator=g) for _ in range(4))
+    pr = torch.randn(Bp, Lp, Lp, Hp, device="cuda", generator=g)
+    of, lsef = nn._flash_attention(qf, kf, vf, pr, causal=True)
+    nn.grad_flash_attention(dOf, of, lsef, qf, kf, vf, pr, causal=True)
     torch.cuda.synchronize()
 print("ok")
