@@ -95,6 +95,19 @@ dpair_from_head_major_kernel(T* __restrict__ out, const T* __restrict__ in, cons
     const int k = k0 + kk + threadIdx.x;
     keep[kk / 32] = k < KL && (!kpad || kpad[static_cast<int64_t>(b) * KL + k] != 0);
   }
+  // tiles fully inside the arrays and fully ABOVE the diagonal (half of a causal problem): nothing to read,
+  // no index math -- plain zero stores with a hoisted base (they used to take the generic path below, which
+  // spends ~80 % of its issue slots on per-element divisions and predicates)
+  if (all_dead && k0 + kTP <= KL && c0 + kTP <= C) {
+    T* dp = out + static_cast<int64_t>(b) * KL * C + static_cast<int64_t>(k0 + threadIdx.y) * C + c0 + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < kTP / 8; ++i) {
+      dp[0] = T(0);
+      dp[32] = T(0);
+      dp += static_cast<int64_t>(8) * C;
+    }
+    return;
+  }
   // tiles fully inside the arrays and fully below the diagonal: no per-element predicates, hoisted bases
   if (k0 + kTP <= KL && c0 + kTP <= C && (!causal || k0 + kTP - 1 <= c0 / QH)) {
     int c = c0 + threadIdx.y;
@@ -216,6 +229,16 @@ dpair_from_head_major_16x2_kernel(uint16_t* __restrict__ out, const uint16_t* __
   if (kpad) {
     keep0 = keep0 && kpad[static_cast<int64_t>(b) * KL + k] != 0;
     keep1 = keep1 && kpad[static_cast<int64_t>(b) * KL + k + 1] != 0;
+  }
+  if (all_dead && k0 + kTP <= KL && c0 + kTP <= C) {   // interior tile fully above the diagonal: zeros, no reads
+    uint16_t* dp = out + static_cast<int64_t>(b) * KL * C + static_cast<int64_t>(k0 + threadIdx.y) * C + c0 +
+                   2 * threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < kTP / 8; ++i) {
+      *reinterpret_cast<uint32_t*>(dp) = 0u;
+      dp += static_cast<int64_t>(8) * C;
+    }
+    return;
   }
   if (k0 + kTP <= KL && c0 + kTP <= C && (!causal || k0 + kTP - 1 <= c0 / QH)) {
     // interior tile fully below the diagonal: only the key padding mask can kill an entry
