@@ -243,7 +243,9 @@ __device__ __forceinline__ void load_pairs(const T* p, float2 (&out)[VecIO<T>::N
 // flight per CTA while it reduces the current one; w / b stay in registers across rows when the row is
 // short enough (MAXV <= 2), otherwise they are re-read from L1 / L2 per row.
 // ---------------------------------------------------------------------------------------
-template <typename T, int TPR, int MAXV, int OP, bool PERSIST>
+// FULL: the row is exactly TPR * MAXV vectors (emb 4096 bf16, 4096 / 8192 Float32, ...): every "is this vector
+// inside the row" predicate folds away -- these kernels are issue-bound for 16-bit rows.
+template <typename T, int TPR, int MAXV, int OP, bool PERSIST, bool FULL = false>
 __global__ void __launch_bounds__(kThreads)
 rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict__ stat1,
                 const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b,
@@ -257,6 +259,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
   const int t = threadIdx.x % TPR;
   const int sub = threadIdx.x / TPR;
   const int nvec = static_cast<int>(emb / VE);
+  auto in_row = [&](int vi) { return FULL || vi < nvec; };
   const float inv_n = 1.f / static_cast<float>(emb);
   const int64_t n_groups = (n + RPB - 1) / RPB;
 
@@ -273,7 +276,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
   if constexpr (kCacheW) {
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      if (t + i * TPR < nvec) {
+      if (in_row(t + i * TPR)) {
         load_wb(i, wv[i], bv[OP == 2 ? i : 0]);
       } else {
 #pragma unroll
@@ -292,7 +295,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
-        if (vi < nvec) cp_async16(slot(st, i), x + row * emb + static_cast<int64_t>(vi) * VE);
+        if (in_row(vi)) cp_async16(slot(st, i), x + row * emb + static_cast<int64_t>(vi) * VE);
       }
     }
     cp_async_commit();  // always commit so the group count is uniform
@@ -313,7 +316,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
     float2 xv[MAXV][NP];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      if (live && t + i * TPR < nvec) {
+      if (live && in_row(t + i * TPR)) {
         if constexpr (PERSIST)
           unpack_pairs<T>(*reinterpret_cast<const uint4*>(slot(stage, i)), xv[i]);
         else
@@ -350,7 +353,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
-        if (vi < nvec) {
+        if (in_row(vi)) {
 #pragma unroll
           for (int j = 0; j < NP; ++j) xv[i][j] = f2_mul(xv[i][j], inv);
           store_pairs<T>(yr + static_cast<int64_t>(vi) * VE, xv[i]);
@@ -369,7 +372,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
-        if (vi < nvec) {
+        if (in_row(vi)) {
           float2 wl[NP], bl[NP];
           if constexpr (!kCacheW) load_wb(i, wl, bl);
 #pragma unroll
@@ -388,7 +391,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
       float2 ss2 = f2_dup(0.f);
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
-        if (t + i * TPR < nvec) {  // padding vectors hold 0, not mu: keep them out of the variance
+        if (in_row(t + i * TPR)) {  // padding vectors hold 0, not mu: keep them out of the variance
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
             xv[i][j] = f2_add(xv[i][j], nmu);
@@ -406,7 +409,7 @@ rowwise_fwd_vec(T* __restrict__ y, float* __restrict__ stat0, float* __restrict_
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
-        if (vi < nvec) {
+        if (in_row(vi)) {
           float2 wl[NP], bl[NP];
           if constexpr (!kCacheW) load_wb(i, wl, bl);
 #pragma unroll
@@ -480,7 +483,7 @@ rowwise_fwd_generic(T* __restrict__ y, float* __restrict__ stat0, float* __restr
 // ---------------------------------------------------------------------------------------
 // NT = threads per CTA (256 in production; the 512-thread form -- half the columns, accumulators and registers
 // per thread, twice the warps per SM -- is kept for the A/B recorded in launch_bwd: it lost).
-template <typename T, int TPR, int MAXV, int OP, int NT = kThreads>
+template <typename T, int TPR, int MAXV, int OP, int NT = kThreads, bool FULL = false>
 __global__ void __launch_bounds__(NT, (NT == 512 ? 2 : (MAXV <= 2 ? NNOP_ROWWISE_BWD_MINB : 1)))
 rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict__ part1,
                 const T* __restrict__ dy, const T* __restrict__ x_or_y,
@@ -498,6 +501,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
   const int t = threadIdx.x % TPR;
   const int sub = threadIdx.x / TPR;
   const int nvec = static_cast<int>(emb / VE);
+  auto in_row = [&](int vi) { return FULL || vi < nvec; };
   const float inv_n = 1.f / static_cast<float>(emb);
   const int64_t n_groups = (n + RPB - 1) / RPB;
 
@@ -508,7 +512,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int vi = t + i * TPR;
-      if (vi < nvec) {
+      if (in_row(vi)) {
         load_pairs<T>(w + static_cast<int64_t>(vi) * VE, wv[i]);
       } else {
 #pragma unroll
@@ -536,7 +540,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
-        if (vi < nvec) {
+        if (in_row(vi)) {
           cp_async16(slot(st, 0, i), x_or_y + row * emb + static_cast<int64_t>(vi) * VE);
           cp_async16(slot(st, 1, i), dy + row * emb + static_cast<int64_t>(vi) * VE);
         }
@@ -566,7 +570,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int vi = t + i * TPR;
-      if (live && vi < nvec) {
+      if (live && in_row(vi)) {
         unpack_pairs<T>(*reinterpret_cast<const uint4*>(slot(stage, 0, i)), av[i]);
         unpack_pairs<T>(*reinterpret_cast<const uint4*>(slot(stage, 1, i)), dv[i]);
       } else {
@@ -588,7 +592,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
-        if (vi < nvec) {
+        if (in_row(vi)) {
 #pragma unroll
           for (int j = 0; j < NP; ++j) av[i][j] = f2_mul(av[i][j], f2_add(dv[i][j], ns));
           store_pairs<T>(dxr + static_cast<int64_t>(vi) * VE, av[i]);
@@ -607,7 +611,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
-        if (vi < nvec) {
+        if (in_row(vi)) {
           float2 o[NP];
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
@@ -642,7 +646,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int vi = t + i * TPR;
-        if (vi < nvec) {
+        if (in_row(vi)) {
           float2 o[NP];
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
@@ -662,7 +666,7 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int vi = t + i * TPR;
-      if (vi < nvec) {
+      if (in_row(vi)) {
 #pragma unroll
         for (int j = 0; j < NP; j += 2) {
           *reinterpret_cast<float4*>(part0 + prow * emb + static_cast<int64_t>(vi) * VE + 2 * j) =
@@ -848,8 +852,14 @@ int launch_fwd(void* y, float* s0, float* s1, const void* x, const void* w, cons
       kern_p<<<static_cast<unsigned>(cap_p), kThreads, smem, st>>>(yy, s0, s1, xx, ww, bb, emb, n, eps, offset);
     }
   };
-#define NNOP_FWD(TPR_, MAXV_, RPC_) \
-  run(rowwise_fwd_vec<T, TPR_, MAXV_, OP, true>, rowwise_fwd_vec<T, TPR_, MAXV_, OP, false>, RPC_, MAXV_)
+#define NNOP_FWD(TPR_, MAXV_, RPC_)                                                                          \
+  do {                                                                                                       \
+    if (nvec == TPR_ * MAXV_)                                                                                \
+      run(rowwise_fwd_vec<T, TPR_, MAXV_, OP, true, true>, rowwise_fwd_vec<T, TPR_, MAXV_, OP, false, true>, \
+          RPC_, MAXV_);                                                                                      \
+    else                                                                                                     \
+      run(rowwise_fwd_vec<T, TPR_, MAXV_, OP, true>, rowwise_fwd_vec<T, TPR_, MAXV_, OP, false>, RPC_, MAXV_); \
+  } while (0)
   if (al && nvec <= 32 * 8) {
     if (nvec <= 32) NNOP_FWD(32, 1, 8);
     else if (nvec <= 64) NNOP_FWD(32, 2, 8);
@@ -920,7 +930,13 @@ int launch_bwd(void* dx, TW* dw, TW* db, const void* dy, const void* a, const fl
     // 52.4 us at 8192 rows, 404 vs 350 us at 65536.  The kernel is bound by instruction issue (10 packed FP
     // ops per element pair against 6 for RMS norm, which runs at 95 %), not by latency, so more warps only add
     // barrier width.  profiles/r02_perf_rowwise_nt512.txt)
-    if (nvec <= 256) run(rowwise_bwd_vec<T, 256, 1, OP>, 1, 1);
+    // full-row specialisation (no "vector inside the row" predicates): layer norm only -- measured +4 % at C3 and
+    // 89 -> 95 % of copy bandwidth at 65 536 rows there, but -18 % for RMS norm (profiles/r02_perf_rowwise_full.txt)
+    constexpr bool kFullBwd = OP == 2;
+    if (kFullBwd && nvec == 256) run(rowwise_bwd_vec<T, 256, 1, OP, kThreads, kFullBwd>, 1, 1);
+    else if (kFullBwd && nvec == 512) run(rowwise_bwd_vec<T, 256, 2, OP, kThreads, kFullBwd>, 1, 2);
+    else if (kFullBwd && nvec == 1024) run(rowwise_bwd_vec<T, 256, 4, OP, kThreads, kFullBwd>, 1, 4);
+    else if (nvec <= 256) run(rowwise_bwd_vec<T, 256, 1, OP>, 1, 1);
     else if (nvec <= 512) run(rowwise_bwd_vec<T, 256, 2, OP>, 1, 2);
     else if (nvec <= 1024) run(rowwise_bwd_vec<T, 256, 4, OP>, 1, 4);
     else if constexpr (OP == 0) run(rowwise_bwd_vec<T, 256, 8, OP>, 1, 8);
