@@ -1582,7 +1582,8 @@ int attn_sm100_fwd(const AttnParams& a) {
   // automatic choice, from measurement (profiles/r01d_perf_fwd_modes.txt): the persistent kernel wins
   // where the per-tile fixed cost matters -- E = 64 (+15 %) and short sequences (L = 2 048: +6 %) --
   // and is neutral (bench.py regime) to slower (back-to-back launches) on long E = 128 tiles
-  const bool persist_pays = a.E <= 64 || a.QL <= 2048;
+  // (packed batches: sequences of very different lengths -- the dynamic queue balances them; C4 1 038 -> 1 067 TFLOP/s)
+  const bool persist_pays = a.E <= 64 || a.QL <= 2048 || packed;
   if (persist_ok && (mode == 2 || mode >= 100 || (mode == 0 && persist_pays && n_tiles >= 2LL * sm_count()))) {
     const int ctas = mode >= 100 ? (mode - 100 < 1 ? 1 : mode - 100) : sm_count();
     if (a.dtype == NNOP_BF16)
