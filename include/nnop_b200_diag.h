@@ -37,7 +37,8 @@ int nnop_set_bwd_pair_mode(int mode);
  * QL <= 2048) run the persistent kernel (one CTA per SM, dynamic tile queue, Q / K / V of the next
  * tile loaded under the current one, O stored through private staging); 1: always one CTA per q
  * tile; 2: persistent wherever eligible; 100+n: persistent on n CTAs (tests).  O and lse are
- * bit-identical across modes.  (The persistent forward needs the workspace of nnop_flash_attn_fwd_ws /
+ * bit-identical across these modes.  3: experiment -- one CTA per q tile with two softmax warps per 32
+ * query rows (E = 128, dense layout; slower; O within one ulp of the others).  (The persistent forward needs the workspace of nnop_flash_attn_fwd_ws /
  * nnop_flash_attn_varlen_fwd_ws for its tile counter; without one the call runs one CTA per q tile.) */
 int nnop_set_fwd_mode(int mode);
 

@@ -126,8 +126,8 @@ extern "C" int nnop_set_attention_path(int mode) {
 }
 extern "C" int nnop_last_attention_path(void) { return g_last_path; }
 extern "C" int nnop_set_fwd_mode(int mode) {
-  if (mode < 0 || (mode > 2 && mode < 101) || mode > 100 + 65535)
-    return fail(NNOP_ERR_ARG, "forward kernel mode must be 0..2 or 100+n");
+  if (mode < 0 || (mode > 3 && mode < 101) || mode > 100 + 65535)
+    return fail(NNOP_ERR_ARG, "forward kernel mode must be 0..3 or 100+n");
   attn_sm100_set_fwd_mode(mode);
   return NNOP_OK;
 }

@@ -35,6 +35,10 @@ namespace nnop {
 namespace {
 
 constexpr int kFwdThreads = 384;
+// QUAD variant: the producer warpgroup (TMA, MMA, TMEM allocator) and sixteen softmax warps (two per 32 rows of
+// each tile); launched at 96 registers per thread, setmaxnreg moves them to 64 / 104
+constexpr int kFwdQuadThreads = 640;
+constexpr int kFwdQuadXchBytes = 6144;   // row-max exchange [2 tiles][2 parities][2 halves][128] + row-sum exchange [2][2][128]
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
@@ -43,6 +47,10 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #endif
 // every kPolyEvery-th pair of exponentials runs on the FMA pipe instead of the MUFU (0 = none)
 constexpr int kPolyEvery = NNOP_FWD_POLY_EVERY;
+#ifndef NNOP_FWD_QUAD_POLY_EVERY
+#define NNOP_FWD_QUAD_POLY_EVERY 0
+#endif
+constexpr int kQuadPolyEvery = NNOP_FWD_QUAD_POLY_EVERY;   // QUAD variant: same switch
 #ifndef NNOP_FWD_SPLIT_QK
 #define NNOP_FWD_SPLIT_QK 0
 #endif
@@ -107,8 +115,17 @@ struct FwdSmem {
 // (128 query) x (128-byte) box of it is one TMA load; warp 3 streams those boxes through two 16 KB
 // buffers per tile (the K/V ring gives up one stage for them) and the softmax warpgroups fold them
 // into the logits (in log2 units) before the mask / max / exp steps.
-template <typename T, int D, bool SPLIT = false, bool BIAS = false>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+//
+// QUAD = true (16-bit, E = 128, no bias): FOUR softmax warpgroups, two per tile, each thread owning HALF a row
+// (64 key columns).  The per-tile chain S -> softmax -> P -> PV -> QK -> S bounds the step, and a single thread
+// walking 128 logits is most of it (~2 100 of ~3 250 clk); two threads per row halve that.  The two
+// warps that share 32 rows exchange their partial row max through shared memory behind a 64-thread named
+// barrier (the speculative first chunk of exponentials is issued before the barrier, so its latency is
+// hidden), keep partial row sums (added in the epilogue), rescale their own half of O's columns and write
+// their P into the first 32 columns of their OWN half of S (so neither can overwrite logits the other has
+// not read yet; the PV MMA takes its A operand from two 32-column pieces).
+template <typename T, int D, bool SPLIT = false, bool BIAS = false, bool QUAD = false>
+__global__ void __launch_bounds__(QUAD ? kFwdQuadThreads : kFwdThreads, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
                       const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v,
@@ -116,6 +133,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
                       const __grid_constant__ CUtensorMap tm_bias, const FwdParams p) {
   using S = FwdSmem<D, BIAS ? 3 : 4, BIAS ? 65536 : 0>;
   constexpr int kNStage = S::kNStage;
+  static_assert(!QUAD || (D == 128 && !SPLIT && !BIAS), "QUAD: 16-bit E = 128 without a bias");
+  constexpr int kThreads = QUAD ? kFwdQuadThreads : kFwdThreads;
+  constexpr int kAllocWarp = 2;       // TMEM allocator
+  constexpr int kFirstSoftmaxWarp = 4;
   using BT = typename std::conditional<SPLIT, float, T>::type;  // element type of the bias
   constexpr int kBiasCols = 128 / static_cast<int>(sizeof(BT));  // keys per 128-byte box row
   constexpr int kBiasChunks = 128 / kBiasCols;                   // boxes per 128-key block
@@ -172,7 +193,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     // sequences, then all walk the per-thread counts (scratch: the not yet used Q buffer).
     int* scratch = reinterpret_cast<int*>(smem);
     const int e = blockIdx.x;
-    const int per = (p.nseq + kFwdThreads - 1) / kFwdThreads;
+    const int per = (p.nseq + kThreads - 1) / kThreads;
     auto tiles_of = [&](int z) { return (p.cu_q[z + 1] - p.cu_q[z] + 255) >> 8; };
     {
       const int z0 = min(p.nseq, static_cast<int>(threadIdx.x) * per), z1 = min(p.nseq, z0 + per);
@@ -182,13 +203,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     }
     __syncthreads();
     int run = 0, c = 0;
-    for (; c < kFwdThreads; ++c) {
+    for (; c < kThreads; ++c) {
       const int v = scratch[c];
       if (e < run + v) break;
       run += v;
     }
     __syncthreads();   // scratch is the Q buffer from here on
-    if (c == kFwdThreads) return;  // past the last tile of the batch (whole CTA exits together)
+    if (c == kThreads) return;  // past the last tile of the batch (whole CTA exits together)
     int z = c * per, nt = tiles_of(z);
     while (e >= run + nt) {
       run += nt;
@@ -213,7 +234,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     if (threadIdx.x == 0) s_kl_eff = 0;
     __syncthreads();
     int last = 0;
-    for (int kk = threadIdx.x; kk < KL; kk += kFwdThreads)
+    for (int kk = threadIdx.x; kk < KL; kk += kThreads)
       if (kmask[kk]) last = kk + 1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
@@ -252,14 +273,14 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     if constexpr (BIAS) tma_prefetch_desc(&tm_bias);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == kAllocWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    setmaxnreg_dec<88>();  // launch: 384 x 168; warps 0-3 give back 128 x 80 = 10240 registers, exactly what 256 x (208 - 168) takes
+  if (warp < kFirstSoftmaxWarp) {
+    if constexpr (QUAD) setmaxnreg_dec<64>(); else setmaxnreg_dec<88>();  // launch: 384 x 168; warps 0-3 give back 128 x 80 = 10240 registers, exactly what 256 x (208 - 168) takes
     if (warp == 0 && lane == 0 && nblk > 0) {
       // ================================ TMA producer =================================
       mbar_arrive_expect_tx(&q_full[0], S::kTileBytes);
@@ -366,7 +387,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       auto pv_half = [&](int t, int slot, int hf, bool acc) {
         const uint64_t b0 = dv0 + static_cast<uint64_t>(((slot % kNStage) * S::kTileBytes) >> 4);
         const uint32_t d = tm + 256 + t * D;
-        const uint32_t a = tm + t * 128;  // P aliases S columns [0, 64)
+        // P aliases S columns [0, 64); QUAD: keys 64.. sit in the first 32 columns of the second half of S
+        const uint32_t a = tm + t * 128 + ((QUAD && hf) ? 32 : 0);
         if (elect_one()) {
 #pragma unroll
           for (int j = 4 * hf; j < 4 * hf + 4; ++j) {
@@ -439,6 +461,191 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         }
         commit(&kv_empty[vslot % kNStage]);
         if (i + 1 < nblk) commit(&kv_empty[knext % kNStage]);
+      }
+    }
+  } else if constexpr (QUAD) {
+    // ====================== softmax warps, two per 32 rows of a tile =======================
+    setmaxnreg_inc<104>();   // 640 x 96 at launch; the producer warpgroup's 128 x 32 cover 512 x 8
+    const int sw = warp - kFirstSoftmaxWarp;          // 0..15
+    const int t = sw >> 3, hf = (sw >> 2) & 1;         // tile, half of the key columns
+    const int nbt = t ? nb1 : nb0;
+    const int wq = warp & 3;                           // TMEM lane quarter this warp may touch
+    const int row = wq * 32 + lane;
+    const int q_row = q0 + t * 128 + row;
+    const uint32_t pair_bar = 3 + t * 4 + wq;          // named barrier of the two warps that share these rows
+    float* xmax = reinterpret_cast<float*>(smem + ((S::kTotal + 15) & ~15)) + t * 512;   // [parity][half][row]
+    float* xsum = reinterpret_cast<float*>(smem + ((S::kTotal + 15) & ~15)) + 1024 + t * 256;  // [half][row]
+    if (nbt > 0) {
+      const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+      const uint32_t tS = tmem_base + lane_off + t * 128 + hf * 64;       // my 64 logits; my P = its first 32 columns
+      const uint32_t tO = tmem_base + lane_off + 256 + t * D + hf * (D / 2);  // my half of O's columns
+      const float sl2 = p.scale_log2;
+      const uint64_t sl2x2 = pack_f2(sl2, sl2);
+      float m_used = -1e30f;   // reference max, scaled log2 units; identical in both threads of a row
+      float l = 0.f;           // partial row sum (my 64 columns of every block)
+      auto mask_bytes = [&](int blk) -> uint32_t {
+        uint32_t r = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kk = blk * 128 + 4 * lane + j;
+          if (kk < KL && kmask[kk]) r |= 1u << (8 * j);
+        }
+        return r;
+      };
+      uint32_t mb_next = kmask ? mask_bytes(0) : 0u;
+      for (int i = 0; i < nbt; ++i) {
+        const uint32_t mb = mb_next;
+        if (kmask && i + 1 < nbt) mb_next = mask_bytes(i + 1);
+        mbar_wait(&s_full[t], i & 1);
+        tc_fence_after();
+        if ((sw & 7) == 0) FWD_STAMP(i, 5 * t + 0);
+        uint32_t sr[2][32];
+        tmem_ld_x32(tS, sr[0]);
+        tmem_ld_x32(tS + 32, sr[1]);
+        tmem_ld_wait();
+        if ((sw & 7) == 0) FWD_STAMP(i, 5 * t + 1);
+        const int k0 = i * 128;
+        uint32_t kw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (kmask) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) kw[j] = __ballot_sync(0xffffffffu, (mb >> (8 * j)) & 1u);
+        }
+        const bool need_mask = (k0 + 128 > KL) || (p.causal && (k0 + 127 > q0 + t * 128)) ||
+                               ((kw[0] & kw[1] & kw[2] & kw[3]) != 0xffffffffu);
+        if (need_mask) {
+          const int lim = p.causal ? min(KL - 1, q_row) : (KL - 1);  // last visible key
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int kk = hf * 64 + c * 32 + j;
+              if (k0 + kk > lim || !((kw[kk & 3] >> (kk >> 2)) & 1u)) sr[c][j] = 0xff800000u;  // -inf
+            }
+        }
+        // partial row max of my 64 columns -> shared memory for the other half's thread
+        float mx8[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            mx8[j & 3] = fmax3(mx8[j & 3], __uint_as_float(sr[c][2 * j]), __uint_as_float(sr[c][2 * j + 1]));
+        const float mx_mine = fmax3(mx8[0], mx8[1], fmaxf(mx8[2], mx8[3]));
+        xmax[(i & 1) * 256 + hf * 128 + row] = mx_mine;
+        // exp2(S * scale * log2e - m_used) of 16 columns (sub-chunk sc of my 64), packed to 16 bits, summed
+        auto exp_sub = [&](int sc, uint32_t (&pr)[8], uint64_t& sum2) {
+          const uint64_t negm2 = pack_f2(-m_used, -m_used);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = (sc & 1) * 16 + 2 * j;
+            const uint64_t x2 = ffma2(pack_f2(__uint_as_float(sr[sc >> 1][col]), __uint_as_float(sr[sc >> 1][col + 1])),
+                                      sl2x2, negm2);
+            float x0, x1;
+            unpack_f2(x2, x0, x1);
+            float p0, p1;
+            if (kQuadPolyEvery > 0 && (j % (kQuadPolyEvery > 0 ? kQuadPolyEvery : 1)) == kQuadPolyEvery - 1) {
+              exp2_poly2(x0, x1, p0, p1);
+            } else {
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            sum2 = fadd2(sum2, pack_f2(p0, p1));
+            pr[j] = pack2<T>(p0, p1);
+          }
+        };
+        // speculation (see the two-warpgroup kernel): the first sub-chunk is exponentiated against the running
+        // reference max before the barrier, i.e. while the other half's partial max is on its way
+        uint32_t pr0[8];
+        uint64_t sum0 = pack_f2(0.f, 0.f);
+        exp_sub(0, pr0, sum0);
+        named_bar_sync(pair_bar, 64);
+        const float mx = fmaxf(mx_mine, xmax[(i & 1) * 256 + (hf ^ 1) * 128 + row]);
+        const float mx_s = mx * sl2;
+        const bool grow = mx_s > m_used + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, grow)) {   // same rows, same inputs: the partner warp takes the same branch
+          const float m_new = grow ? mx_s : m_used;
+          const float alpha = fast_exp2(m_used - m_new);
+          m_used = m_new;
+          l *= alpha;
+          if (i > 0) {
+#pragma unroll
+            for (int c = 0; c < D / 32; ++c) {   // 16 columns at a time: the 64 logits stay in registers
+              uint32_t orow[16];
+              tmem_ld_x16(tO + c * 16, orow);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) orow[j] = __float_as_uint(__uint_as_float(orow[j]) * alpha);
+              tmem_st_x16(tO + c * 16, orow);
+            }
+            // PV(i) adds into ALL of O's columns as soon as either half of P is announced: both halves of O
+            // must have been rescaled by then
+            tmem_st_wait();
+            tc_fence_before();
+            named_bar_sync(pair_bar, 64);
+          }
+          sum0 = pack_f2(0.f, 0.f);
+          exp_sub(0, pr0, sum0);
+        }
+        if ((sw & 7) == 0) FWD_STAMP(i, 5 * t + 2);
+        tmem_st_x8(tS, pr0);
+        uint64_t sum2 = sum0;
+#pragma unroll
+        for (int sc = 1; sc < 4; ++sc) {
+          uint32_t pr[8];
+          exp_sub(sc, pr, sum2);
+          tmem_st_x8(tS + sc * 8, pr);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_half[2 * t + hf]);
+        if ((sw & 3) == 0) FWD_STAMP(i, 5 * t + 3 + hf);
+        float s0, s1;
+        unpack_f2(sum2, s0, s1);
+        l += s0 + s1;
+      }
+
+      // ---- epilogue: my 64 columns of O / l -> 16-bit -> box `hf` of the swizzled Q_t buffer -> TMA store ----
+      mbar_wait(&o_full[t], 0);
+      tc_fence_after();
+      xsum[hf * 128 + row] = l;
+      named_bar_sync(pair_bar, 64);
+      l += xsum[(hf ^ 1) * 128 + row];
+      const float inv_l = l > 0.f ? 1.f / l : 0.f;
+      uint8_t* stage = sQ + t * S::kTileBytes + hf * S::kBoxBytes;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t orow[32];
+        tmem_ld_x32(tO + c * 32, orow);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 v;
+          v.x = pack2<T>(__uint_as_float(orow[8 * u + 0]) * inv_l, __uint_as_float(orow[8 * u + 1]) * inv_l);
+          v.y = pack2<T>(__uint_as_float(orow[8 * u + 2]) * inv_l, __uint_as_float(orow[8 * u + 3]) * inv_l);
+          v.z = pack2<T>(__uint_as_float(orow[8 * u + 4]) * inv_l, __uint_as_float(orow[8 * u + 5]) * inv_l);
+          v.w = pack2<T>(__uint_as_float(orow[8 * u + 6]) * inv_l, __uint_as_float(orow[8 * u + 7]) * inv_l);
+          const int cin = c * 4 + u;  // 16-byte chunk within the 128-byte box row
+          *reinterpret_cast<uint4*>(stage + row * 128 + ((cin ^ (row & 7)) << 4)) = v;
+        }
+      }
+      if (hf == 0 && q_row < QL)
+        p.lse[static_cast<int64_t>(bh_q) * QL + q_row] = l > 0.f ? (m_used + fast_log2(l)) * kLn2 : -INFINITY;
+      fence_proxy_async_smem();
+      named_bar_sync(1 + t, 256);
+      if ((sw & 7) == 0 && lane == 0) {
+#pragma unroll
+        for (int bx = 0; bx < S::kNBox; ++bx)
+          tma_store_3d(&tm_o, sQ + t * S::kTileBytes + bx * S::kBoxBytes, bx * 64, q_off + q0 + t * 128, bh_q);
+        bulk_commit();
+        bulk_wait_read<0>();
+      }
+    } else if (hf == 0 && (t == 0 || act1)) {
+      // no visible keys at all (KL == 0): the output rows are 0 and lse = -inf
+      if (q_row < QL) {
+        const int64_t ri = static_cast<int64_t>(bh_q) * QL + q_row;
+        uint4* orow = reinterpret_cast<uint4*>(static_cast<char*>(p.o_ptr) + ri * p.o_row_bytes);
+        for (int c = 0; c < p.o_row_bytes / 16; ++c) orow[c] = make_uint4(0u, 0u, 0u, 0u);
+        p.lse[ri] = -INFINITY;
       }
     }
   } else {
@@ -729,7 +936,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
   // ---- teardown -------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == kAllocWarp) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -1401,7 +1608,7 @@ int launch_fwd_f32(const AttnParams& a) {
   return NNOP_OK;
 }
 
-template <typename T, int D, bool BIAS = false>
+template <typename T, int D, bool BIAS = false, bool QUAD = false>
 int launch_fwd(const AttnParams& a) {
   using S = FwdSmem<D, BIAS ? 3 : 4, BIAS ? 65536 : 0>;
   alignas(64) CUtensorMap tq, tk, tv, to;
@@ -1420,8 +1627,9 @@ int launch_fwd(const AttnParams& a) {
   alignas(64) CUtensorMap tb = to;  // unused without a bias
   if constexpr (BIAS)
     if (int rc = make_tmap_3d(&tb, a.pair_t, a.dtype, a.KLp, a.QL, bhq, 64, 128)) return rc;
-  auto kern = attn_fwd_sm100_kernel<T, D, false, BIAS>;
-  NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynBytes));
+  auto kern = attn_fwd_sm100_kernel<T, D, false, BIAS, QUAD>;
+  constexpr int kSmemBytes = S::kDynBytes + (QUAD ? 16 + kFwdQuadXchBytes : 0);
+  NNOP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   FwdParams fp;
   fp.lse = a.lse;
   fp.QL = a.QL; fp.KL = a.KL; fp.QH = a.QH; fp.KH = a.KH; fp.causal = a.causal;
@@ -1441,7 +1649,7 @@ int launch_fwd(const AttnParams& a) {
   }
   dim3 grid(packed ? static_cast<unsigned>(a.total_q / 256 + a.nseq) : (a.QL + 255) / 256, a.QH, packed ? 1 : a.B);
   timing_begin(0, a.stream);
-  kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, tb, fp);
+  kern<<<grid, QUAD ? kFwdQuadThreads : kFwdThreads, kSmemBytes, a.stream>>>(tq, tk, tv, to, tb, fp);
   timing_end(0, a.stream);
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
@@ -1590,6 +1798,9 @@ int attn_sm100_fwd(const AttnParams& a) {
       return a.E == 128 ? launch_fwd_persist<__nv_bfloat16, 128>(a, ctas) : launch_fwd_persist<__nv_bfloat16, 64>(a, ctas);
     return a.E == 128 ? launch_fwd_persist<__half, 128>(a, ctas) : launch_fwd_persist<__half, 64>(a, ctas);
   }
+  // 3 = two softmax warps per 32 rows (QUAD; E = 128, dense layout)
+  if (mode == 3 && a.E == 128 && !packed)
+    return a.dtype == NNOP_BF16 ? launch_fwd<__nv_bfloat16, 128, false, true>(a) : launch_fwd<__half, 128, false, true>(a);
   if (a.dtype == NNOP_BF16)
     return a.E == 128 ? launch_fwd<__nv_bfloat16, 128>(a) : launch_fwd<__nv_bfloat16, 64>(a);
   return a.E == 128 ? launch_fwd<__half, 128>(a) : launch_fwd<__half, 64>(a);

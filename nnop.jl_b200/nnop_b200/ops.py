@@ -74,7 +74,7 @@ def set_bwd_pair_mode(mode: int) -> None:
 
 def set_fwd_mode(mode: int) -> None:
     """Forward kernel variant on the tcgen05 path: 0 automatic (persistent kernel for deep tile queues),
-    1 one CTA per q tile, 2 persistent, 100+n persistent on n CTAs."""
+    1 one CTA per q tile, 2 persistent, 100+n persistent on n CTAs, 3 the two-softmax-warps-per-row experiment."""
     check(lib.nnop_set_fwd_mode(int(mode)))
 
 

@@ -479,6 +479,36 @@ def test_persistent_forward_matches_one_cta_per_tile(nnop, causal, E):
         nnop.set_fwd_mode(0)
 
 
+@pytest.mark.parametrize("causal", [False, True])
+def test_quad_forward_matches_default_kernel(nnop, causal):
+    """nnop_set_fwd_mode(3), the experiment with two softmax warps per 32 query rows (half a row per thread,
+    partial row max / row sum exchanged through shared memory): same P bit for bit, only the
+    row sum is added in a different order -- O within one ulp of T, lse within fp32 rounding -- incl. ragged
+    sizes, GQA and a key padding mask."""
+    try:
+        for trial, (B, QH, KH, QL, KL, mask) in enumerate([(2, 4, 4, 1024, 1024, False), (1, 4, 2, 300, 517, False),
+                                                           (3, 2, 2, 255, 1024, True), (1, 2, 1, 129, 64, False),
+                                                           (2, 2, 2, 1000, 1000, True), (1, 1, 1, 1, 1, False)]):
+            if causal and QL != KL:
+                continue
+            dtype = torch.bfloat16 if trial % 2 == 0 else torch.float16
+            q, k, v, _, _, m = _inputs(B, QH, KH, QL, KL, 128, dtype, 700 + trial, mask=mask)
+            qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
+            md = m.cuda() if m is not None else None
+            nnop.set_fwd_mode(1)
+            o_ref, lse_ref = nnop._flash_attention(qd, kd, vd, causal=causal, kpad_mask=md)
+            nnop.set_fwd_mode(3)
+            o, lse = nnop._flash_attention(qd, kd, vd, causal=causal, kpad_mask=md)
+            assert nnop.last_attention_path() == 1
+            ulp = 2.0 ** (-8 if dtype == torch.bfloat16 else -11)
+            assert max_abs(o, o_ref) <= ulp * max(1.0, o_ref.float().abs().max().item()), (B, QH, KH, QL, KL)
+            fin = torch.isfinite(lse_ref)
+            assert torch.equal(torch.isfinite(lse), fin)
+            assert max_abs(lse[fin], lse_ref[fin]) <= 1e-5 * max(1.0, lse_ref[fin].abs().max().item())
+    finally:
+        nnop.set_fwd_mode(0)
+
+
 @pytest.mark.parametrize("dtype,E", [(torch.float32, 64), (torch.bfloat16, 128)])
 def test_backward_reuses_forward_pair_copy(nnop, dtype, E):
     """The head-major copy of `pair` the forward leaves in its workspace can be handed to the backward
