@@ -64,8 +64,12 @@ constexpr bool kSplitPV = NNOP_FWD_SPLIT_PV != 0;  // start PV on keys 0..63 whi
 // development aid: pipeline timeline of CTA (0,0,0), 16 clock64 stamps per kv step
 __device__ long long g_fwd_trace[256 * 16];
 #define FWD_STAMP(i, k) do { if (tr) g_fwd_trace[(i) * 16 + (k)] = clock64(); } while (0)
+// NNOP_FWD_TRACE=2: the four warps of tile 0's softmax warpgroup instead (warp w: stamps 4w .. 4w+3 = logits in
+// registers, max decided, first / second half of P announced): how far apart do the warps of one group run?
+#define FWD_TRACE_WARPS (NNOP_FWD_TRACE == 2)
 #else
 #define FWD_STAMP(i, k) do { } while (0)
+#define FWD_TRACE_WARPS 0
 #endif
 
 struct FwdParams {
@@ -434,15 +438,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
             qk_half(t, knext, 1);
           }
           mbar_wait(&p_half[2 * t], i & 1);
-          if (t == 0) FWD_STAMP(i, 14);
+          if (t == 0 && !FWD_TRACE_WARPS) FWD_STAMP(i, 14);
           slot_wait(vslot);
           tc_fence_after();
-          FWD_STAMP(i, 10 + 2 * t);
+          if (!FWD_TRACE_WARPS) FWD_STAMP(i, 10 + 2 * t);
           pv_half(t, vslot, 0, i > 0);
           if (kSplitPV) {
             mbar_wait(&p_half[2 * t + 1], i & 1);
             tc_fence_after();
-            if (t == 0) FWD_STAMP(i, 15);
+            if (t == 0 && !FWD_TRACE_WARPS) FWD_STAMP(i, 15);
           }
           pv_half(t, vslot, 1, true);
           if (has_next) {
@@ -457,7 +461,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           } else {
             commit(&o_full[t]);
           }
-          FWD_STAMP(i, 11 + 2 * t);
+          if (!FWD_TRACE_WARPS) FWD_STAMP(i, 11 + 2 * t);
         }
         commit(&kv_empty[vslot % kNStage]);
         if (i + 1 < nblk) commit(&kv_empty[knext % kNStage]);
@@ -685,12 +689,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         if (kmask && i + 1 < nbt) mb_next = mask_bytes(i + 1);
         mbar_wait(&s_full[t], i & 1);
         tc_fence_after();
-        if (wq == 0) FWD_STAMP(i, 5 * t + 0);
+        if (wq == 0 && !FWD_TRACE_WARPS) FWD_STAMP(i, 5 * t + 0);
         uint32_t sr[4][32];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, sr[c]);
         tmem_ld_wait();
-        if (wq == 0) FWD_STAMP(i, 5 * t + 1);
+        if (FWD_TRACE_WARPS ? t == 0 : wq == 0) FWD_STAMP(i, FWD_TRACE_WARPS ? 4 * wq : 5 * t + 1);
         if (kSplitQK) {
           tc_fence_before();
           __syncwarp();
@@ -812,7 +816,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           }
           exp_chunk(0, pf);
         }
-        if (wq == 0) FWD_STAMP(i, 5 * t + 2);
+        if (FWD_TRACE_WARPS ? t == 0 : wq == 0) FWD_STAMP(i, FWD_TRACE_WARPS ? 4 * wq + 1 : 5 * t + 2);
         uint64_t sum2 = pack_f2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -836,7 +840,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_half[2 * t + (kSplitPV ? (c >> 1) : 0)]);
-            if (wq == 0) FWD_STAMP(i, 5 * t + 3 + (c >> 1));
+            if (FWD_TRACE_WARPS ? t == 0 : wq == 0) FWD_STAMP(i, FWD_TRACE_WARPS ? 4 * wq + 2 + (c >> 1) : 5 * t + 3 + (c >> 1));
           }
         }
         float s0, s1;
