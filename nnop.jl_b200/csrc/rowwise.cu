@@ -479,7 +479,7 @@ rowwise_fwd_generic(T* __restrict__ y, float* __restrict__ stat0, float* __restr
 
 // ---------------------------------------------------------------------------------------
 // backward kernels (vector path).  Persistent grid; CTA g handles row groups g, g+G, ...
-// partial layout: part0[g][emb] (dw), part1[g][emb] (db, layer norm only), fp32.
+// partial layout: part0[g][emb] (dw), part1[g][emb] (db, layer norm only), fp32, one row per CTA g.
 // ---------------------------------------------------------------------------------------
 // NT = threads per CTA (256 in production; the 512-thread form -- half the columns, accumulators and registers
 // per thread, twice the warps per SM -- is kept for the A/B recorded in launch_bwd: it lost).
@@ -660,8 +660,40 @@ rowwise_bwd_vec(T* __restrict__ dx, float* __restrict__ part0, float* __restrict
     }
   }
 
-  if constexpr (OP != 0) {
-    // one partial row per (CTA, sub-row): index blockIdx.x * RPB + sub
+  if constexpr (OP != 0 && TPR == 32) {
+    // warp-per-row form: the CTA's RPB warps first add their accumulators in shared memory (the prefetch ring,
+    // idle by now), so the CTA writes ONE partial row instead of RPB (r02a: 1 024 rows of emb 1 024 wrote 1 024
+    // partial rows -- twice the bytes of the input -- for the second kernel to read back)
+    constexpr int EP = 32 * MAXV * VE;   // padded row length in floats
+    cp_async_wait<0>();
+    __syncthreads();
+    float* rows = reinterpret_cast<float*>(ring);   // [dw | db][sub][EP]
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = t + i * TPR;
+#pragma unroll
+      for (int j = 0; j < NP; j += 2) {
+        *reinterpret_cast<float4*>(rows + sub * EP + vi * VE + 2 * j) =
+            make_float4(acc0[i][j].x, acc0[i][j].y, acc0[i][j + 1].x, acc0[i][j + 1].y);
+        if (OP == 2)
+          *reinterpret_cast<float4*>(rows + (RPB + sub) * EP + vi * VE + 2 * j) =
+              make_float4(acc1[i][j].x, acc1[i][j].y, acc1[i][j + 1].x, acc1[i][j + 1].y);
+      }
+    }
+    __syncthreads();
+    for (int c4 = threadIdx.x; c4 < (OP == 2 ? 2 : 1) * (EP / 4); c4 += NT) {
+      const int which = c4 / (EP / 4), col = (c4 - which * (EP / 4)) * 4;
+      if (col >= emb) continue;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < RPB; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(rows + (which * RPB + r) * EP + col);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      *reinterpret_cast<float4*>((which ? part1 : part0) + static_cast<int64_t>(blockIdx.x) * emb + col) = a;
+    }
+  } else if constexpr (OP != 0) {
+    // one partial row per CTA: index blockIdx.x
     const int64_t prow = static_cast<int64_t>(blockIdx.x) * RPB + sub;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
@@ -744,38 +776,57 @@ rowwise_bwd_generic(T* __restrict__ dx, float* __restrict__ part0, float* __rest
   }
 }
 
-// out{0,1}[e] = sum_g part{0,1}[g][e]; blockDim (32, 32), grid (ceil(emb/32), 1 or 2): blockIdx.y picks
-// dw / db, the 32 thread rows walk the partial rows with four independent sums each (the r01 kernel --
-// 8 thread rows, one dependent chain of n_part / 8 loads -- took 8.5-11 us for 5 MB: latency, not bytes)
+// out{0,1}[e] = sum_g part{0,1}[g][e]; blockDim (8, 32) = 8 float4 column groups x 32 row walkers, grid
+// (ceil(emb/32), 1 or 2): blockIdx.y picks dw / db.  The kernel runs behind a 40 us operation on data that sits
+// in L2, so what it costs is (i) dependent L2 round trips and (ii) waves: r01 walked one chain of n_part / 8 loads
+// (8.5-11 us); r02a had 1 024-thread CTAs, two per SM -- layer norm at emb 8 192 needed 512 of them, two waves, and
+// cost 9 us of a 49 us backward.  Now 256-thread CTAs (all resident at once), every walker issues all of its
+// (up to kBatch) 16-byte loads before the first add, and a warp reads four full 128-byte row segments.
 template <typename TO>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 reduce_partials(TO* __restrict__ out0, TO* __restrict__ out1, const float* __restrict__ part0,
                 const float* __restrict__ part1, int64_t n_part, int64_t emb) {
-  __shared__ float sm[32][33];
+  constexpr int kBatch = 10;
+  __shared__ float4 sm[32][9];
   const float* part = blockIdx.y ? part1 : part0;
   TO* out = blockIdx.y ? out1 : out0;
-  const int64_t e = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x;
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x * 4;   // emb % 4 == 0 (vector paths) or scalar tail below
   // launched with programmatic stream serialisation: the CTAs are resident while the backward kernel drains
   // and only wait here for its memory to be visible (takes the launch latency off a 40 us operation)
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  if (e < emb) {
-    int64_t g = threadIdx.y;
-    for (; g + 96 < n_part; g += 128) {
-      s0 += part[g * emb + e];
-      s1 += part[(g + 32) * emb + e];
-      s2 += part[(g + 64) * emb + e];
-      s3 += part[(g + 96) * emb + e];
-    }
-    for (; g < n_part; g += 32) s0 += part[g * emb + e];
-  }
-  sm[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
-  __syncthreads();
-  if (threadIdx.y == 0 && e < emb) {
-    float t = 0.f;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool vec = (emb & 3) == 0;
+  if (vec && e < emb) {
+    for (int64_t g0 = threadIdx.y; g0 < n_part; g0 += 32 * kBatch) {
+      float4 v[kBatch];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) t += sm[i][threadIdx.x];
-    out[e] = from_f32<TO>(t);
+      for (int k = 0; k < kBatch; ++k) {
+        const int64_t g = g0 + 32 * k;
+        v[k] = g < n_part ? __ldcg(reinterpret_cast<const float4*>(part + g * emb + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
+    }
+  } else if (!vec) {
+    // (generic kernels with emb not a multiple of 4: scalar columns, same walk)
+    float* sp = &s.x;
+    for (int c = 0; c < 4; ++c)
+      if (e + c < emb)
+        for (int64_t g = threadIdx.y; g < n_part; g += 32) sp[c] += part[g * emb + e + c];
+  }
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float4 v = sm[i][threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (e + c < emb) out[e + c] = from_f32<TO>(tv[c]);
   }
 }
 
@@ -917,7 +968,7 @@ int launch_bwd(void* dx, TW* dw, TW* db, const void* dy, const void* a, const fl
     const int64_t groups = (n + rows_per_cta - 1) / rows_per_cta;
     const int64_t cap = static_cast<int64_t>(sm_count()) * occ;
     grid = static_cast<int>(groups < cap ? groups : cap);
-    n_part = static_cast<int64_t>(grid) * rows_per_cta;
+    n_part = grid;   // one partial row per CTA (the warp-per-row kernels add their sub-rows in shared memory)
     kern<<<grid, nt, smem, st>>>(dxx, p0, p1, dyy, aa, s0, s1, ww, emb, n, offset);
   };
   if (plan.mode == 1) {
@@ -945,13 +996,13 @@ int launch_bwd(void* dx, TW* dw, TW* db, const void* dy, const void* a, const fl
   }
   NNOP_LAUNCH_CHECK();
   if (OP != 0) {
-    // every (CTA, sub-row) writes its partial row (zeros if it never saw a live row)
+    // every CTA writes its partial row (zeros if it never saw a live row)
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.gridDim = dim3(static_cast<unsigned>((emb + 31) / 32), OP == 2 ? 2 : 1);
-    cfg.blockDim = dim3(32, 32);
+    cfg.blockDim = dim3(8, 32);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cfg.attrs = attr;
