@@ -84,8 +84,8 @@ int nnop_flash_attn_fwd(void* o, float* lse, const void* q, const void* k, const
 /* Forward with an optional caller-owned workspace.  With a workspace of at least
  * nnop_flash_attn_fwd_workspace_bytes(...) bytes (256-byte aligned), 16-bit problems whose tile queue is deep
  * and short-tiled enough may run the persistent forward kernel (its tile counter lives in the workspace;
- * O and lse are bit-identical either way), and Float32 problems with E = 64
- * run on the tensor cores: q, k, v are split into two fp16 terms each (x ~ hi + lo,
+ * O and lse are bit-identical either way), and Float32 problems with E in {16, 32, 64} (E = 128 without `pair`)
+ * run on the tensor cores: q, k, v are scaled by a power of two and split into two fp16 terms each (x ~ hi + lo,
  * 22 significant bits), S = Qh Kh^T + Qh Kl^T + Ql Kh^T and O = (Ph + Pl)(Vh + Vl) accumulate in fp32;
  * max abs error vs an fp64 evaluation stays below 1e-4.  Without it (or for other shapes) the call
  * is identical to nnop_flash_attn_fwd.  The size query returns 0 where no workspace is used.
@@ -96,7 +96,9 @@ int nnop_flash_attn_fwd(void* o, float* lse, const void* q, const void* k, const
  * library then keeps a head-major copy of pair there (its layout has the head as the fastest axis,
  * which no tile load can fetch).  Same rule for nnop_flash_attn_bwd with backward = 1 (copy of pair
  * plus the staging area dpair is produced in): total = round_up(bwd_workspace_bytes, 256) +
- * pair_workspace_bytes(..., 1).  With a smaller workspace `pair` is served by the SIMT kernels. */
+ * pair_workspace_bytes(..., 1).  With a smaller workspace `pair` is served by the SIMT kernels.
+ * (16-bit E = 256 runs its forward on the tensor cores without any workspace; its backward, like that of Float32
+ * E = 128, and every `pair` call at those widths are served by the SIMT kernels.) */
 size_t nnop_flash_attn_pair_workspace_bytes(int dtype, int QL, int KL, int QH, int B, int backward);
 size_t nnop_flash_attn_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B);
 int nnop_flash_attn_fwd_ws(void* o, float* lse, const void* q, const void* k, const void* v,

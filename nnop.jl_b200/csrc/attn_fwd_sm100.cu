@@ -98,8 +98,9 @@ struct FwdSmem {
   static constexpr int kTileBytes = 128 * D * 2;   // one Q tile / K block / V block
   static constexpr int kBoxBytes = 128 * 64 * 2;   // one 64-column TMA box (16 KB)
   static constexpr int kNBox = D / 64;
+  static constexpr int kQTiles = D == 256 ? 1 : 2;   // E = 256: one 128-row q tile per CTA (64 KB tiles)
   static constexpr int kQOff = 0;
-  static constexpr int kKVOff = 2 * kTileBytes;
+  static constexpr int kKVOff = kQTiles * kTileBytes;
   static constexpr int kBiasOff = kKVOff + kNStage * kTileBytes;  // [2 tiles][2 buffers] x 16 KB
   static constexpr int kBarOff = kBiasOff + BIASB;
   static constexpr int kNumBars = 2 + 2 * kNStage + 10 + 8;
@@ -135,8 +136,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
                       const __grid_constant__ CUtensorMap tm_v,
                       const __grid_constant__ CUtensorMap tm_o,
                       const __grid_constant__ CUtensorMap tm_bias, const FwdParams p) {
-  using S = FwdSmem<D, BIAS ? 3 : 4, BIAS ? 65536 : 0>;
+  // D = 256 (16-bit E = 256): ONE 128-row q tile per CTA, K / V blocks of 64 KB through a two-slot ring (192 KB of
+  // shared memory), S at TMEM columns 0..127 and the 256-column O at 256..511; the second softmax warpgroup idles.
+  // No ping-pong, so the tensor pipe waits for every softmax -- still tens of times the SIMT kernel.
+  constexpr bool SINGLE = D == 256;
+  // SINGLE + SPLIT = Float32 E = 128: rows [hi 128 | lo 128]
+  static_assert(!SINGLE || (!BIAS && !QUAD), "256-wide rows: forward without a bias only");
+  using S = FwdSmem<D, SINGLE ? 2 : (BIAS ? 3 : 4), BIAS ? 65536 : 0>;
   constexpr int kNStage = S::kNStage;
+  constexpr int kCtaRows = SINGLE ? 128 : 256;
   static_assert(!QUAD || (D == 128 && !SPLIT && !BIAS), "QUAD: 16-bit E = 128 without a bias");
   constexpr int kThreads = QUAD ? kFwdQuadThreads : kFwdThreads;
   constexpr int kAllocWarp = 2;       // TMEM allocator
@@ -226,7 +234,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     KL = p.cu_k[z + 1] - k_off;
     b = 0;
   }
-  const int q0 = qt * 256;
+  const int q0 = qt * kCtaRows;
   const int bh_q = b * p.QH + h;
   const int bh_kv = b * p.KH + h / (p.QH / p.KH);
   // key padding mask (src/attention.jl:73-79): keys past the last attended one are never loaded
@@ -246,7 +254,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
     __syncthreads();
     KL = s_kl_eff;
   }
-  const bool act1 = q0 + 128 < QL;
+  const bool act1 = !SINGLE && q0 + 128 < QL;
   const int nb0 = ((p.causal ? min(KL, q0 + 128) : KL) + 127) >> 7;
   const int nb1 = act1 ? (((p.causal ? min(KL, q0 + 256) : KL) + 127) >> 7) : 0;
   const int nblk = act1 ? nb1 : nb0;
@@ -356,13 +364,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         const uint32_t d = tm + t * 128;
         if (elect_one()) {
           if constexpr (SPLIT) {
-            // box 0 = hi terms, box 1 = lo terms: hi*hi, hi*lo, lo*hi (lo*lo is below fp32 rounding)
+            // first half of the boxes = hi terms, second half = lo terms: hi*hi, hi*lo, lo*hi (lo*lo is below fp32
+            // rounding); D / 32 k-steps of 16 per part (E = D / 2)
+            constexpr int kLo = (S::kNBox / 2) * S::kBoxBytes;
 #pragma unroll
             for (int part = 0; part < 3; ++part)
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                const uint32_t aoff = ((part == 2 ? S::kBoxBytes : 0) + k4 * 32) >> 4;
-                const uint32_t boff = ((part == 1 ? S::kBoxBytes : 0) + k4 * 32) >> 4;
+              for (int k4 = 0; k4 < D / 32; ++k4) {
+                const uint32_t koff = (k4 >> 2) * S::kBoxBytes + (k4 & 3) * 32;
+                const uint32_t aoff = ((part == 2 ? kLo : 0) + koff) >> 4;
+                const uint32_t boff = ((part == 1 ? kLo : 0) + koff) >> 4;
                 umma_ss(d, a0 + aoff, b0 + boff, idesc_qk, (part | k4) ? 1u : 0u);
               }
           } else {
@@ -855,13 +866,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       uint8_t* stage = sQ + t * S::kTileBytes;
       if constexpr (SPLIT) {
         inv_l *= __ldg(p.f32_mult + F32Mult::kO);   // O = 2^e_v * P V'
-        // O'[:, 0:64] = P Vh, O'[:, 64:128] = P Vl: add them, normalise, stage as fp32 (two boxes of
+        // O'[:, 0:D/2] = P Vh, O'[:, D/2:D] = P Vl: add them, normalise, stage as fp32 (boxes of
         // 32 floats x 128 rows, same 128-byte swizzle) for the fp32 TMA store
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < D / 64; ++c) {
           uint32_t ohi[32], olo[32];
           tmem_ld_x32(tO + c * 32, ohi);
-          tmem_ld_x32(tO + 64 + c * 32, olo);
+          tmem_ld_x32(tO + D / 2 + c * 32, olo);
           tmem_ld_wait();
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -1478,7 +1489,7 @@ attn_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tm_q,
 // percent.  The power of two is exact; the kernels undo it with the multipliers below.
 __global__ void __launch_bounds__(256)
 split_f32_kernel(__half* __restrict__ out, const float* __restrict__ in, int64_t n4,
-                 const float* __restrict__ scale_slot, int per_row) {
+                 const float* __restrict__ scale_slot, int per_row, int half4) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;  // one float4 per thread
   if (i >= n4) return;
   const float sc = scale_slot ? __ldg(scale_slot) : 1.f;   // 2^-e_x: an exact power of two
@@ -1491,17 +1502,18 @@ split_f32_kernel(__half* __restrict__ out, const float* __restrict__ in, int64_t
   const uint32_t h0 = pack2<__half>(x.x, x.y), h1 = pack2<__half>(x.z, x.w);
   const uint32_t l0 = pack2<__half>(x.x - unpack_lo<__half>(h0), x.y - unpack_hi<__half>(h0));
   const uint32_t l1 = pack2<__half>(x.z - unpack_lo<__half>(h1), x.w - unpack_hi<__half>(h1));
-  uint2* o = reinterpret_cast<uint2*>(out + row * 128);
+  // half4 = width of each half in float4 units: 16 (rows [hi 64 | lo 64]) or 32 (E = 128: [hi 128 | lo 128])
+  uint2* o = reinterpret_cast<uint2*>(out + row * (8 * half4));
   o[c4] = make_uint2(h0, h1);
-  o[16 + c4] = make_uint2(l0, l1);
-  for (int z = c4 + per_row; z < 16; z += per_row) o[z] = o[16 + z] = make_uint2(0u, 0u);
+  o[half4 + c4] = make_uint2(l0, l1);
+  for (int z = c4 + per_row; z < half4; z += per_row) o[z] = o[half4 + z] = make_uint2(0u, 0u);
 }
 
 int launch_split(__half* out, const void* in, int64_t rows, int E, const float* scale_slot, cudaStream_t st) {
   const int64_t n4 = rows * (E / 4);
   if (n4 == 0) return NNOP_OK;
   split_f32_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(out, static_cast<const float*>(in), n4,
-                                                                           scale_slot, E / 4);
+                                                                           scale_slot, E / 4, E > 64 ? 32 : 16);
   NNOP_LAUNCH_CHECK();
   return NNOP_OK;
 }
@@ -1570,16 +1582,16 @@ __global__ void __launch_bounds__(256) absmax_f32_kernel(uint32_t* __restrict__ 
 }
 
 // Float32, E = 64: split q, k, v into [hi | lo] bf16 rows in the workspace, then the SPLIT kernel
-template <bool BIAS>
+template <bool BIAS, int D = 128>
 int launch_fwd_f32(const AttnParams& a) {
   using T = __half;
-  constexpr int D = 128;
-  using S = FwdSmem<D, BIAS ? 3 : 4, BIAS ? 65536 : 0>;
+  using S = FwdSmem<D, D == 256 ? 2 : (BIAS ? 3 : 4), BIAS ? 65536 : 0>;
+  constexpr int kCtaRows = D == 256 ? 128 : 256;
   const int64_t rq = static_cast<int64_t>(a.B) * a.QH * a.QL, rk = static_cast<int64_t>(a.B) * a.KH * a.KL;
   T* qs = static_cast<T*>(a.fwd_ws);
-  T* ks = qs + rq * 128;
-  T* vs = ks + rk * 128;
-  void* blk = vs + rk * 128;   // scale block (256-byte aligned: every copy is a multiple of 256 bytes)
+  T* ks = qs + rq * D;
+  T* vs = ks + rk * D;
+  void* blk = vs + rk * D;   // scale block (256-byte aligned: every copy is a multiple of 256 bytes)
   if (int rc = attn_f32_scales(blk, a.q, rq * a.E, a.k, rk * a.E, a.v, rk * a.E, nullptr, 0, a.stream)) return rc;
   if (int rc = launch_split(qs, a.q, rq, a.E, f32_in_scale(blk, 0), a.stream)) return rc;
   if (int rc = launch_split(ks, a.k, rk, a.E, f32_in_scale(blk, 1), a.stream)) return rc;
@@ -1604,7 +1616,7 @@ int launch_fwd_f32(const AttnParams& a) {
   fp.o_row_bytes = a.E * static_cast<int>(sizeof(float));
   fp.lpt_group = 0;
   fp.kpad = a.kpad;
-  dim3 grid((a.QL + 255) / 256, a.QH, a.B);
+  dim3 grid((a.QL + kCtaRows - 1) / kCtaRows, a.QH, a.B);
   timing_begin(0, a.stream);
   kern<<<grid, kFwdThreads, S::kDynBytes, a.stream>>>(tq, tk, tv, to, tb, fp);
   timing_end(0, a.stream);
@@ -1614,7 +1626,8 @@ int launch_fwd_f32(const AttnParams& a) {
 
 template <typename T, int D, bool BIAS = false, bool QUAD = false>
 int launch_fwd(const AttnParams& a) {
-  using S = FwdSmem<D, BIAS ? 3 : 4, BIAS ? 65536 : 0>;
+  using S = FwdSmem<D, D == 256 ? 2 : (BIAS ? 3 : 4), BIAS ? 65536 : 0>;
+  constexpr int kCtaRows = D == 256 ? 128 : 256;
   alignas(64) CUtensorMap tq, tk, tv, to;
   const bool packed = a.cu_q != nullptr;
   // packed mode: the tensors are (QH, total_q, E) / (KH, total_k, E); a.QL / a.KL hold the maxima
@@ -1651,7 +1664,8 @@ int launch_fwd(const AttnParams& a) {
     fp.lpt_group = env >= 0 ? env : static_cast<int>(48.0 * 1024 * 1024 / (kv_bytes > 1 ? kv_bytes : 1));
     if (fp.lpt_group > a.QH * a.B) fp.lpt_group = a.QH * a.B;
   }
-  dim3 grid(packed ? static_cast<unsigned>(a.total_q / 256 + a.nseq) : (a.QL + 255) / 256, a.QH, packed ? 1 : a.B);
+  dim3 grid(packed ? static_cast<unsigned>(a.total_q / 256 + a.nseq) : (a.QL + kCtaRows - 1) / kCtaRows, a.QH,
+            packed ? 1 : a.B);
   timing_begin(0, a.stream);
   kern<<<grid, QUAD ? kFwdQuadThreads : kFwdThreads, kSmemBytes, a.stream>>>(tq, tk, tv, to, tb, fp);
   timing_end(0, a.stream);
@@ -1724,12 +1738,16 @@ extern "C" int nnop_debug_fwd_trace(long long* host_out, int n) {
 
 bool attn_sm100_supported(const AttnParams& a, bool backward) {
   if (backward && !attn_sm100_bwd_available()) return false;
-  const bool f32_split = a.dtype == NNOP_F32 && (a.E == 16 || a.E == 32 || a.E == 64) && !backward &&
-                         a.fwd_ws != nullptr && !a.cu_q;
+  // Float32 forward: E <= 64 on the two-tile split kernel (also with a bias), E = 128 on the one-tile form (no bias)
+  const bool f32_split = a.dtype == NNOP_F32 && !backward && a.fwd_ws != nullptr && !a.cu_q &&
+                         (a.E == 16 || a.E == 32 || a.E == 64 || (a.E == 128 && a.pair == nullptr));
   if (a.dtype != NNOP_F16 && a.dtype != NNOP_BF16 && !f32_split) return false;
   if (a.E != 64 && a.E != 128) {
     // 16 / 32: dense 16-bit problems only (the packed kernels address partial tiles with plain pointers)
-    if ((a.E != 16 && a.E != 32) || a.cu_q != nullptr) return false;
+    // 256: dense 16-bit FORWARD without a bias (one q tile per CTA); its backward stays on the SIMT kernels --
+    // dK and dV alone would fill all 512 TMEM columns
+    const bool e256 = a.E == 256 && !backward && a.dtype != NNOP_F32 && a.pair == nullptr;
+    if ((a.E != 16 && a.E != 32 && !e256) || a.cu_q != nullptr) return false;
   }
   // the additive bias needs its head-major copy (and, backward, a dpair staging area) in the
   // workspace (nnop_flash_attn_pair_workspace_bytes); without it the generic path serves it
@@ -1771,19 +1789,21 @@ int attn_f32_scales(void* block, const void* q, int64_t nq, const void* k, int64
 size_t attn_sm100_fwd_workspace_bytes(int dtype, int E, int QL, int KL, int QH, int KH, int B) {
   // 16-bit: the persistent forward's tile counter; Float32 E = 64: the [hi | lo] copies + scale block
   if (dtype != NNOP_F32) return (E == 16 || E == 32 || E == 64 || E == 128) ? kFwdCounterBytes : 0;
-  if (E != 16 && E != 32 && E != 64) return 0;
-  return (static_cast<size_t>(B) * QH * QL + 2 * static_cast<size_t>(B) * KH * KL) * 128 * 2 + kF32ScaleBytes;
+  if (E != 16 && E != 32 && E != 64 && E != 128) return 0;
+  const size_t row = E == 128 ? 256 : 128;   // [hi | lo] fp16 elements per row
+  return (static_cast<size_t>(B) * QH * QL + 2 * static_cast<size_t>(B) * KH * KL) * row * 2 + kF32ScaleBytes;
 }
 
 int attn_sm100_fwd(const AttnParams& a) {
   if (a.pair) {
     if (int rc = attn_pair_to_head_major(a)) return rc;
-    if (a.dtype == NNOP_F32) return launch_fwd_f32<true>(a);
+    if (a.dtype == NNOP_F32) return launch_fwd_f32<true>(a);   // (E <= 64: attn_sm100_supported)
     if (a.dtype == NNOP_BF16)
       return a.E == 128 ? launch_fwd<__nv_bfloat16, 128, true>(a) : launch_fwd<__nv_bfloat16, 64, true>(a);
     return a.E == 128 ? launch_fwd<__half, 128, true>(a) : launch_fwd<__half, 64, true>(a);
   }
-  if (a.dtype == NNOP_F32) return launch_fwd_f32<false>(a);
+  if (a.dtype == NNOP_F32) return a.E == 128 ? launch_fwd_f32<false, 256>(a) : launch_fwd_f32<false>(a);
+  if (a.E == 256) return a.dtype == NNOP_BF16 ? launch_fwd<__nv_bfloat16, 256>(a) : launch_fwd<__half, 256>(a);
   // forward variant (nnop_set_fwd_mode / NNOP_FWD_MODE): 0 automatic, 1 one CTA per q tile, 2 persistent,
   // 100+n persistent on n CTAs
   const int mode = fwd_mode();

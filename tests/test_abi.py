@@ -74,5 +74,7 @@ def test_workspace_queries_need_no_gpu(nnop):
     # the [hi | lo] fp16 copies of q, k, v plus the 256-byte scale block, Float32 of any other E nothing
     assert lib.nnop_flash_attn_fwd_workspace_bytes(2, 128, 1000, 1000, 8, 2, 2) == 256
     assert lib.nnop_flash_attn_fwd_workspace_bytes(0, 64, 1000, 1000, 8, 2, 2) == (2 * 8 * 1000 + 2 * 2 * 2 * 1000) * 256 + 256
-    assert lib.nnop_flash_attn_fwd_workspace_bytes(0, 128, 1000, 1000, 8, 2, 2) == 0
+    # Float32 E = 128: [hi 128 | lo 128] fp16 copies for the one-tile split forward; E = 256: SIMT, no workspace
+    assert lib.nnop_flash_attn_fwd_workspace_bytes(0, 128, 1000, 1000, 8, 2, 2) == (2 * 8 * 1000 + 2 * 2 * 2 * 1000) * 512 + 256
+    assert lib.nnop_flash_attn_fwd_workspace_bytes(0, 256, 1000, 1000, 8, 2, 2) == 0
     assert lib.nnop_flash_attn_varlen_fwd_workspace_bytes(2, 128, 3, 1000, 8) == 256

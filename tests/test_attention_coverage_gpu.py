@@ -18,9 +18,13 @@ from test_attention_gpu import F32_TOL, H16_TOL, _check, _inputs
 pytestmark = pytest.mark.gpu
 
 
-def _expected_path(dtype, E):
-    """1 = tcgen05 kernels: 16-bit E in {16, 32, 64, 128}, Float32 E in {16, 32, 64}; everything else SIMT."""
-    return int(E <= (64 if dtype == torch.float32 else 128))
+def _expected_path(dtype, E, pair=False):
+    """Forward kernel family.  1 = tcgen05: 16-bit E in {16, 32, 64, 128} and Float32 E in {16, 32, 64} (also with
+    `pair`), 16-bit E = 256 and Float32 E = 128 without `pair` (one q tile per CTA; their backward is SIMT);
+    everything else SIMT."""
+    if dtype == torch.float32:
+        return int(E <= 64 or (E == 128 and not pair))
+    return int(E <= 128 or (E == 256 and not pair))
 
 
 @pytest.mark.parametrize("forced_simt", [False, True])
@@ -30,14 +34,17 @@ def _expected_path(dtype, E):
                                      (torch.float32, 128), (torch.float32, 256)])
 def test_small_and_large_E_dtype_grid(nnop, dtype, E, causal, forced_simt):
     """Every (dtype, E) outside the round-1 tensor-core set.  16-bit E in {16, 32} now run the E = 64 tcgen05
-    kernels (TMA zero-pads the narrower rows) and are ALSO checked on the SIMT kernels they used to take
-    (`forced_simt`); E = 256 and Float32 E >= 128 are served by the SIMT kernels only.  Shapes follow the
+    kernels (TMA zero-pads the narrower rows); 16-bit E = 256 and Float32 E = 128 run their FORWARD on the
+    one-q-tile-per-CTA tcgen05 kernel (backward: SIMT).  All of them are ALSO checked on the SIMT kernels they
+    used to take (`forced_simt`); Float32 E = 256 is served by the SIMT kernels only.  Shapes follow the
     reference grids (test/attention_tests.jl:13-18, test/gqa_attention_tests.jl:8-12): ragged and
     tile-multiple L, QL != KL when not causal, GQA 4/1 and 6/2, then pair + kpad_mask."""
     tol = F32_TOL if dtype == torch.float32 else H16_TOL
     path = 0 if forced_simt else _expected_path(dtype, E)
     if forced_simt and _expected_path(dtype, E) == 0:
         pytest.skip("already covered: this (dtype, E) only has the SIMT path")
+    if forced_simt and E >= 128 and causal:
+        pytest.skip("E >= 128 on the SIMT forward: the non-causal pass covers it (keeps the slow runs short)")
     shapes = [(2, 2, 2, 255, 255), (1, 4, 1, 257, 257), (1, 6, 2, 512, 512), (2, 2, 2, 256, 511), (1, 2, 1, 1, 1),
               (1, 2, 2, 130, 3)]
     if E == 256:   # keep the E = 256 SIMT runs short
@@ -54,9 +61,58 @@ def test_small_and_large_E_dtype_grid(nnop, dtype, E, causal, forced_simt):
             except AssertionError as e:
                 raise AssertionError(f"{dtype} E={E} shape {(B, QH, KH, QL, KL)}: {e}") from e
         q, k, v, dO, pr, m = _inputs(2, 4, 2, 255, 255, E, dtype, 5 + E, pair=True, mask=True)
-        _check(nnop, q, k, v, dO, pr, m, causal, tol, expect_path=path)
+        _check(nnop, q, k, v, dO, pr, m, causal, tol, expect_path=0 if forced_simt else _expected_path(dtype, E, pair=True))
     finally:
         nnop.set_attention_path(0)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("dtype,E", [(torch.bfloat16, 256), (torch.float16, 256), (torch.float32, 128)])
+def test_one_tile_forward_long_rows_and_speed(nnop, dtype, E, causal):
+    """16-bit E = 256 / Float32 E = 128 forward on the tcgen05 kernel with ONE q tile per CTA (rows of 512 bytes:
+    [hi | lo] fp16 terms for Float32): several kv blocks per tile, ragged ends, GQA, key padding mask, against the
+    fp64 oracle; autograd through the public wrapper (tcgen05 forward + SIMT backward); >= 10x the SIMT forward."""
+    tol = F32_TOL if dtype == torch.float32 else H16_TOL
+    for (B, QH, KH, QL, KL, mask) in [(1, 4, 2, 1000, 1000, True), (2, 2, 2, 640, 640, False), (1, 2, 1, 300, 900, False)]:
+        if causal and QL != KL:
+            continue
+        q, k, v, dO, _, m = _inputs(B, QH, KH, QL, KL, E, dtype, 900 + QL, mask=mask)
+        qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
+        md = m.cuda() if m is not None else None
+        o, lse = nnop._flash_attention(qd, kd, vd, causal=causal, kpad_mask=md)
+        assert nnop.last_attention_path() == 1
+        o_ref, lse_ref = O.naive_attention(q.double(), k.double(), v.double(), None, causal=causal, kpad_mask=m, return_lse=True)
+        assert max_abs(o, o_ref) < tol and max_abs(lse, lse_ref) < max(tol, 1e-4), (B, QH, KH, QL, KL)
+        qa, ka, va = (t.clone().requires_grad_(True) for t in (qd, kd, vd))
+        nnop.flash_attention(qa, ka, va, causal=causal, kpad_mask=md).backward(dO.cuda())
+        o_arg = o.double().cpu() if tol > 1e-3 else None
+        rq, rk, rv, _ = O.naive_attention_bwd(dO.double(), q.double(), k.double(), v.double(), None, causal=causal,
+                                              kpad_mask=m, o=o_arg)
+        assert kernel_err(qa.grad, rq) < tol and kernel_err(ka.grad, rk) < tol and kernel_err(va.grad, rv) < tol
+    # speed against the SIMT forward (what these shapes ran on before)
+    q, k, v, _, _, _ = _inputs(2, 8, 8, 2048, 2048, E, dtype, 17)
+    qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
+
+    def ms(n):
+        for _ in range(2):
+            nnop._flash_attention(qd, kd, vd, causal=causal)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            nnop._flash_attention(qd, kd, vd, causal=causal)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    try:
+        t_tc = ms(5)
+        assert nnop.last_attention_path() == 1
+        nnop.set_attention_path(1)
+        t_simt = ms(2)
+        assert nnop.last_attention_path() == 0
+    finally:
+        nnop.set_attention_path(0)
+    assert t_simt >= 10 * t_tc, (t_simt, t_tc)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
