@@ -1840,40 +1840,55 @@ attn_bwd_prep_kernel(float* __restrict__ deltap, float* __restrict__ lse2p,
   }
 }
 
-// prep for packed sequences: grid (row groups of the longest padded sequence, QH, nseq)
+// prep for packed sequences: grid (128-row blocks of the padded statistics, QH).  Statistics block s belongs to the
+// sequence z with the largest packed_stat_row(cu_q[z], z) <= 128 s (every sequence is padded to whole blocks, so a
+// block never straddles two; blocks in the gaps between sequences are never read).  (r02a launched (row groups of
+// the LONGEST sequence, QH, nseq) CTAs: on config C4 -- 64 lengths between 128 and 16 384 -- 1.7 of 2.1 million CTAs
+// found nothing to do, 0.9 ms of a 31 ms backward.)
 template <typename T, int D>
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_packed_kernel(float* __restrict__ deltap, float* __restrict__ lse2p,
                             float* __restrict__ dq_accum, const T* __restrict__ dO,
                             const T* __restrict__ o, const float* __restrict__ lse,
-                            const int* __restrict__ cu_q, int64_t total_q, int64_t QLp) {
+                            const int* __restrict__ cu_q, int nseq, int64_t total_q, int64_t QLp) {
   constexpr int LPR = D / 8;
-  const int z = blockIdx.z, h = blockIdx.y;
+  constexpr int kRows = 256 / LPR;
+  const int sblk = blockIdx.x, h = blockIdx.y;
+  int lo = 0, hi = nseq;   // largest z with (cu_q[z] >> 7) + z <= sblk
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((cu_q[mid] >> 7) + mid <= sblk) lo = mid; else hi = mid;
+  }
+  const int z = lo;
   const int q_off = cu_q[z];
   const int QL = cu_q[z + 1] - q_off;
-  const int r = blockIdx.x * (256 / LPR) + threadIdx.x / LPR;  // row within the padded sequence
+  const int r0 = (sblk - ((q_off >> 7) + z)) << 7;   // first row of this block within the sequence
+  if (r0 >= ((QL + 127) & ~127)) return;             // gap block (whole CTA)
   const int li = threadIdx.x % LPR;
-  if (r >= ((QL + 127) & ~127)) return;  // whole row groups exit together
-  float acc = 0.f;
-  if (r < QL) {
-    const int64_t off = (static_cast<int64_t>(h) * total_q + q_off + r) * D + li * 8;
-    const uint4 a = *reinterpret_cast<const uint4*>(dO + off);
-    const uint4 c = *reinterpret_cast<const uint4*>(o + off);
-    const T* ah = reinterpret_cast<const T*>(&a);
-    const T* ch = reinterpret_cast<const T*>(&c);
+#pragma unroll 2
+  for (int it = 0; it < 128 / kRows; ++it) {
+    const int r = r0 + it * kRows + threadIdx.x / LPR;
+    float acc = 0.f;
+    if (r < QL) {
+      const int64_t off = (static_cast<int64_t>(h) * total_q + q_off + r) * D + li * 8;
+      const uint4 a = *reinterpret_cast<const uint4*>(dO + off);
+      const uint4 c = *reinterpret_cast<const uint4*>(o + off);
+      const T* ah = reinterpret_cast<const T*>(&a);
+      const T* ch = reinterpret_cast<const T*>(&c);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc = fmaf(to_f32<T>(ah[e]), to_f32<T>(ch[e]), acc);
-    float4* zp = reinterpret_cast<float4*>(dq_accum + off);
-    zp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-    zp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+      for (int e = 0; e < 8; ++e) acc = fmaf(to_f32<T>(ah[e]), to_f32<T>(ch[e]), acc);
+      float4* zp = reinterpret_cast<float4*>(dq_accum + off);
+      zp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      zp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
-  for (int sft = 1; sft < LPR; sft <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
-  if (li == 0) {
-    const int64_t pr = static_cast<int64_t>(h) * QLp + packed_stat_row(q_off, z) + r;
-    deltap[pr] = r < QL ? acc : 0.f;
-    const float l = r < QL ? lse[static_cast<int64_t>(h) * total_q + q_off + r] : INFINITY;
-    lse2p[pr] = l == -INFINITY ? INFINITY : l * kLog2e;
+    for (int sft = 1; sft < LPR; sft <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+    if (li == 0) {
+      const int64_t pr = static_cast<int64_t>(h) * QLp + (static_cast<int64_t>(sblk) << 7) + (r - r0);
+      deltap[pr] = r < QL ? acc : 0.f;
+      const float l = r < QL ? lse[static_cast<int64_t>(h) * total_q + q_off + r] : INFINITY;
+      lse2p[pr] = l == -INFINITY ? INFINITY : l * kLog2e;
+    }
   }
 }
 
@@ -1953,10 +1968,9 @@ int launch_bwd(const AttnParams& a) {
   int* tile_pre = tile_counter + 64;
 
   if (packed) {
-    constexpr int kRows = 256 / (D / 8);
-    dim3 pg((((a.QL + 127) & ~127) + kRows - 1) / kRows, a.QH, a.nseq);
+    dim3 pg(static_cast<unsigned>(QLp / 128), a.QH);
     attn_bwd_prep_packed_kernel<T, D><<<pg, 256, 0, a.stream>>>(
-        deltap, lse2p, dqa, static_cast<const T*>(a.dO), static_cast<const T*>(a.o), a.lse, a.cu_q,
+        deltap, lse2p, dqa, static_cast<const T*>(a.dO), static_cast<const T*>(a.o), a.lse, a.cu_q, a.nseq,
         a.total_q, QLp);
     NNOP_LAUNCH_CHECK();
   } else {
