@@ -591,12 +591,18 @@ int attn_f32_bwd(const AttnParams& a) {
         static_cast<const float*>(a.o), a.lse, a.QL, QLp, n_rows_p, f32_mults(blk), a.E);
     NNOP_LAUNCH_CHECK();
   }
-  NNOP_CUDA_CHECK(cudaMemsetAsync(a.dk, 0, static_cast<size_t>(BHk) * a.KL * E * sizeof(float), a.stream));
-  NNOP_CUDA_CHECK(cudaMemsetAsync(a.dv, 0, static_cast<size_t>(BHk) * a.KL * E * sizeof(float), a.stream));
-  if (int rc = attn_split_f32_rows(qs, a.q, BH * a.QL, E, f32_in_scale(blk, 0), a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(dos, a.dO, BH * a.QL, E, f32_in_scale(blk, 3), a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(ks, a.k, BHk * a.KL, E, f32_in_scale(blk, 1), a.stream)) return rc;
-  if (int rc = attn_split_f32_rows(vs, a.v, BHk * a.KL, E, f32_in_scale(blk, 2), a.stream)) return rc;
+  {
+    // q, dO, k, v -> [hi | lo] fp16 rows and the zeroing of the dk / dv accumulators: one launch (six 5-10 us nodes
+    // before; at the reference's README shape they were ~6 % of the backward)
+    F32StageJobs jobs;
+    jobs.out[0] = qs; jobs.in[0] = a.q; jobs.rows[0] = BH * a.QL; jobs.scale[0] = f32_in_scale(blk, 0);
+    jobs.out[1] = dos; jobs.in[1] = a.dO; jobs.rows[1] = BH * a.QL; jobs.scale[1] = f32_in_scale(blk, 3);
+    jobs.out[2] = ks; jobs.in[2] = a.k; jobs.rows[2] = BHk * a.KL; jobs.scale[2] = f32_in_scale(blk, 1);
+    jobs.out[3] = vs; jobs.in[3] = a.v; jobs.rows[3] = BHk * a.KL; jobs.scale[3] = f32_in_scale(blk, 2);
+    jobs.zero[0] = a.dk; jobs.zero_floats[0] = BHk * a.KL * E;
+    jobs.zero[1] = a.dv; jobs.zero_floats[1] = BHk * a.KL * E;
+    if (int rc = attn_stage_f32(jobs, E, a.stream)) return rc;
+  }
   alignas(64) CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdq;
   const uint64_t bhq = static_cast<uint64_t>(BH), bhk = static_cast<uint64_t>(BHk);
   if (int rc = make_tmap_3d(&tq, qs, NNOP_F16, 128, a.QL, bhq, 64, 128)) return rc;

@@ -1509,6 +1509,37 @@ split_f32_kernel(__half* __restrict__ out, const float* __restrict__ in, int64_t
   for (int z = c4 + per_row; z < half4; z += per_row) o[z] = o[half4 + z] = make_uint2(0u, 0u);
 }
 
+// split_f32_kernel for up to four tensors and two zero-fills in one launch: blockIdx.y = job
+struct StageArgs {
+  __half* out[4];
+  const float* in[4];
+  int64_t n4[4];
+  const float* scale[4];
+  float4* zero[2];
+  int64_t zn4[2];
+  int per_row, half4;
+};
+__global__ void __launch_bounds__(256) f32_stage_kernel(const StageArgs a) {
+  const int job = blockIdx.y;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;  // one float4 per thread
+  if (job >= 4) {
+    if (i < a.zn4[job - 4]) a.zero[job - 4][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  if (i >= a.n4[job]) return;
+  const float sc = a.scale[job] ? __ldg(a.scale[job]) : 1.f;
+  float4 x = reinterpret_cast<const float4*>(a.in[job])[i];
+  x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
+  const int64_t row = i / a.per_row;
+  const int c4 = static_cast<int>(i % a.per_row);
+  const uint32_t h0 = pack2<__half>(x.x, x.y), h1 = pack2<__half>(x.z, x.w);
+  const uint32_t l0 = pack2<__half>(x.x - unpack_lo<__half>(h0), x.y - unpack_hi<__half>(h0));
+  const uint32_t l1 = pack2<__half>(x.z - unpack_lo<__half>(h1), x.w - unpack_hi<__half>(h1));
+  uint2* o = reinterpret_cast<uint2*>(a.out[job] + row * (8 * a.half4));
+  o[c4] = make_uint2(h0, h1);
+  o[a.half4 + c4] = make_uint2(l0, l1);
+  for (int z = c4 + a.per_row; z < a.half4; z += a.per_row) o[z] = o[a.half4 + z] = make_uint2(0u, 0u);
+}
 int launch_split(__half* out, const void* in, int64_t rows, int E, const float* scale_slot, cudaStream_t st) {
   const int64_t n4 = rows * (E / 4);
   if (n4 == 0) return NNOP_OK;
@@ -1593,9 +1624,13 @@ int launch_fwd_f32(const AttnParams& a) {
   T* vs = ks + rk * D;
   void* blk = vs + rk * D;   // scale block (256-byte aligned: every copy is a multiple of 256 bytes)
   if (int rc = attn_f32_scales(blk, a.q, rq * a.E, a.k, rk * a.E, a.v, rk * a.E, nullptr, 0, a.stream)) return rc;
-  if (int rc = launch_split(qs, a.q, rq, a.E, f32_in_scale(blk, 0), a.stream)) return rc;
-  if (int rc = launch_split(ks, a.k, rk, a.E, f32_in_scale(blk, 1), a.stream)) return rc;
-  if (int rc = launch_split(vs, a.v, rk, a.E, f32_in_scale(blk, 2), a.stream)) return rc;
+  {
+    F32StageJobs jobs;   // q, k, v -> [hi | lo] in one launch
+    jobs.out[0] = qs; jobs.in[0] = a.q; jobs.rows[0] = rq; jobs.scale[0] = f32_in_scale(blk, 0);
+    jobs.out[1] = ks; jobs.in[1] = a.k; jobs.rows[1] = rk; jobs.scale[1] = f32_in_scale(blk, 1);
+    jobs.out[2] = vs; jobs.in[2] = a.v; jobs.rows[2] = rk; jobs.scale[2] = f32_in_scale(blk, 2);
+    if (int rc = attn_stage_f32(jobs, a.E, a.stream)) return rc;
+  }
   alignas(64) CUtensorMap tq, tk, tv, to;
   const uint64_t bhq = static_cast<uint64_t>(a.B) * a.QH, bhk = static_cast<uint64_t>(a.B) * a.KH;
   if (int rc = make_tmap_3d(&tq, qs, NNOP_F16, D, a.QL, bhq, 64, 128)) return rc;
@@ -1764,6 +1799,32 @@ bool attn_sm100_supported(const AttnParams& a, bool backward) {
 int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, int E, const float* scale_slot,
                         cudaStream_t st) {
   return launch_split(static_cast<__half*>(out_bf16x2), in_f32, rows, E, scale_slot, st);
+}
+
+int attn_stage_f32(const F32StageJobs& jobs, int E, cudaStream_t st) {
+  StageArgs a;
+  int64_t most = 0;
+  int last = -1;
+  for (int j = 0; j < 4; ++j) {
+    a.out[j] = static_cast<__half*>(jobs.out[j]);
+    a.in[j] = static_cast<const float*>(jobs.in[j]);
+    a.n4[j] = jobs.out[j] ? jobs.rows[j] * (E / 4) : 0;
+    a.scale[j] = jobs.scale[j];
+    if (a.n4[j] > 0) last = j;
+    if (a.n4[j] > most) most = a.n4[j];
+  }
+  for (int j = 0; j < 2; ++j) {
+    a.zero[j] = static_cast<float4*>(jobs.zero[j]);
+    a.zn4[j] = jobs.zero[j] ? jobs.zero_floats[j] / 4 : 0;
+    if (a.zn4[j] > 0) last = 4 + j;
+    if (a.zn4[j] > most) most = a.zn4[j];
+  }
+  if (last < 0) return NNOP_OK;
+  a.per_row = E / 4;
+  a.half4 = E > 64 ? 32 : 16;
+  f32_stage_kernel<<<dim3(static_cast<unsigned>((most + 255) / 256), last + 1), 256, 0, st>>>(a);
+  NNOP_LAUNCH_CHECK();
+  return NNOP_OK;
 }
 
 int attn_f32_scales(void* block, const void* q, int64_t nq, const void* k, int64_t nk, const void* v,

@@ -123,6 +123,17 @@ int attn_f32_scales(void* block, const void* q, int64_t nq, const void* k, int64
 // (columns >= E of each half are written as zeros)
 int attn_split_f32_rows(void* out_bf16x2, const void* in_f32, int64_t rows, int E, const float* scale_slot,
                         cudaStream_t st);
+// The same for up to four tensors, plus up to two fp32 regions to zero (the backward's dk / dv accumulators), in ONE
+// launch: at the reference's README shape the Float32 calls are a dozen 5-10 us nodes around a 0.2-0.7 ms kernel.
+struct F32StageJobs {
+  void* out[4] = {nullptr, nullptr, nullptr, nullptr};          // (rows, 2 * half width) fp16
+  const void* in[4] = {nullptr, nullptr, nullptr, nullptr};     // (rows, E) fp32
+  int64_t rows[4] = {0, 0, 0, 0};
+  const float* scale[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* zero[2] = {nullptr, nullptr};                           // 16-byte aligned fp32 regions ...
+  int64_t zero_floats[2] = {0, 0};                              // ... of this many floats (multiples of 4)
+};
+int attn_stage_f32(const F32StageJobs& jobs, int E, cudaStream_t st);
 // attn_bwd_f32_sm100.cu -- Float32 (E = 64) backward on the tensor cores (split-bf16 operands)
 size_t attn_f32_bwd_workspace_bytes(int QL, int KL, int QH, int KH, int B);
 int attn_f32_bwd(const AttnParams& p);
