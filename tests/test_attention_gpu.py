@@ -11,7 +11,7 @@ import math
 import pytest
 import torch
 
-from helpers import kernel_err, load_golden, max_abs, reference_isapprox
+from helpers import kernel_err, load_golden, max_abs, reference_isapprox, ulp_T
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -333,6 +333,38 @@ def test_full_size_properties_config_c2(nnop):
     assert kernel_err(dq[b:b + 1, h:h + 1], rq) < H16_TOL
     assert kernel_err(dk[b:b + 1, h:h + 1], rk) < H16_TOL
     assert kernel_err(dv[b:b + 1, h:h + 1], rv) < H16_TOL
+
+
+@pytest.mark.parametrize("B,QH,KH", [(8, 32, 32), (2, 32, 8)], ids=["C2", "C3-gqa"])
+def test_config_c2_every_slab_against_torch_sdpa(nnop, B, QH, KH):
+    """BASELINE config C2 (and C3: GQA 32 / 8, two batch elements) at its full shape, EVERY (b, h) slab, O and all three gradients, against an independent
+    GPU implementation (torch's scaled_dot_product_attention + autograd, one batch element at a time).  The oracle
+    stays the judge of accuracy (one slab above, the small grids elsewhere); this catches what a single slab cannot:
+    a tile or head that goes wrong only at some (b, h, block) of the full grid.  Both sides round to bf16 with
+    different summation orders, so the bound is BASELINE's 2e-2 plus two bf16 ulps of the element."""
+    import torch.nn.functional as F
+    L, E = 8192, 128
+    g = torch.Generator(device="cuda").manual_seed(1)
+    rnd = lambda h: torch.randn(B, h, L, E, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+    q, k, v, dO = rnd(QH), rnd(KH), rnd(KH), rnd(QH)
+    o, lse = nnop._flash_attention(q, k, v, causal=True)
+    assert nnop.last_attention_path() == 1
+    dq, dk, dv, _ = nnop.grad_flash_attention(dO, o, lse, q, k, v, causal=True)
+    assert nnop.last_attention_path() == 1
+
+    def close(got, ref, what, b):
+        d = (got.float() - ref.float()).abs()
+        bound = H16_TOL + 2 * ulp_T(ref, torch.bfloat16).float()
+        bad = d > bound
+        assert not bad.any(), f"{what}, batch element {b}: {int(bad.sum())} elements off, worst {d.max().item():.4f}"
+    for b in range(B):
+        qb, kb, vb = (t[b:b + 1].clone().requires_grad_(True) for t in (q, k, v))
+        ob = F.scaled_dot_product_attention(qb, kb, vb, is_causal=True, enable_gqa=QH != KH)
+        gq, gk, gv = torch.autograd.grad(ob, (qb, kb, vb), dO[b:b + 1])
+        close(o[b:b + 1], ob.detach(), "o", b)
+        close(dq[b:b + 1], gq, "dq", b)
+        close(dk[b:b + 1], gk, "dk", b)
+        close(dv[b:b + 1], gv, "dv", b)
 
 
 @pytest.mark.parametrize("causal", [False, True])
