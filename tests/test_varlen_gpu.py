@@ -136,6 +136,18 @@ def test_varlen_config4_shape_properties(nnop):
         s_dv = dv[:, a:b].float().sum(1)
         s_do = dO[:, a:b].float().sum(1)
         assert (s_dv - s_do).abs().max().item() < 2e-2 * max(1.0, s_do.abs().max().item())
+    # every sequence, O and all three gradients, against an independent GPU implementation (torch SDPA + autograd on
+    # the sequence's own slice): catches a sequence / tile of the full packed grid going wrong; bound 2e-2 + 2 ulps
+    import torch.nn.functional as F
+    from helpers import ulp_T
+    for z in range(64):
+        a, b = int(cu[z]), int(cu[z + 1])
+        qz, kz, vz = (t[None, :, a:b].clone().requires_grad_(True) for t in (q, k, v))
+        oz = F.scaled_dot_product_attention(qz, kz, vz, is_causal=True)
+        gq, gk, gv = torch.autograd.grad(oz, (qz, kz, vz), dO[None, :, a:b])
+        for got, ref, what in ((o, oz.detach(), "o"), (dq, gq, "dq"), (dk, gk, "dk"), (dv, gv, "dv")):
+            d = (got[:, a:b].float() - ref[0].float()).abs()
+            assert not (d > TOL + 2 * ulp_T(ref[0], torch.bfloat16).float()).any(), (what, z, lens[z], d.max().item())
     # one short sequence against the oracle
     z = min(range(64), key=lambda i: lens[i])
     a, b = int(cu[z]), int(cu[z + 1])
