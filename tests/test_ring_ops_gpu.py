@@ -156,6 +156,34 @@ def test_p2p_ring_virtual_ranks_on_one_gpu(nnop, W, causal):
     _p2p_case(nnop, W, [0] * W, (2, 2, 2, 192 * W, 64), torch.float16, causal)
 
 
+def test_p2p_ring_config_c5_full_shape_virtual_ranks(nnop):
+    """BASELINE config C5 at its full shape (bf16 causal, B = 1, H = 32, L = 131 072, E = 128, 8 ranks in zig-zag
+    order) through nnop_ring_attn_fwd / _bwd with the 8 ranks living on ONE GPU, against the dense kernels on the
+    unsharded tensors (themselves checked against the oracle at C2 / C3 shape): O, lse and all three gradients.
+    A one-GPU box can hold the whole problem (~25 GB); the schedule, landing buffers, merges and gradient pushes
+    are the ones the 8-GPU run uses.  Bound: 2e-2 + 2 bf16 ulps (two bf16 results with different summation orders)."""
+    from helpers import ulp_T
+    W, B, H, L, E = 8, 1, 32, 131072, 128
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q, k, v, dO = (torch.randn(B, H, L, E, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+                   for _ in range(4))
+    o, lse = nnop._flash_attention(q, k, v, causal=True)
+    dq, dk, dv, _ = nnop.grad_flash_attention(dO, o, lse, q, k, v, causal=True)
+    qs, ks, vs, dOs = ([nnop.zigzag_shard(t, r, W).contiguous() for r in range(W)] for t in (q, k, v, dO))
+    os_, lses = nnop.p2p_ring_attention_forward(qs, ks, vs, causal=True)
+    dqs, dks, dvs = nnop.p2p_ring_attention_backward(dOs, os_, lses, qs, ks, vs, causal=True)
+    torch.cuda.synchronize()
+    del qs, ks, vs, dOs
+    un = lambda ps: nnop.zigzag_unshard(ps)
+    for got, ref, what in ((un(os_), o, "o"), (un(dqs), dq, "dq"), (un(dks), dk, "dk"), (un(dvs), dv, "dv")):
+        d = (got.float() - ref.float()).abs()
+        bad = d > 2e-2 + 2 * ulp_T(ref, torch.bfloat16).float()
+        assert not bad.any(), f"{what}: {int(bad.sum())} elements off, worst {d.max().item():.4f}"
+        del d, bad, got
+    l2 = un([l.unsqueeze(-1) for l in lses]).squeeze(-1)
+    assert (l2 - lse).abs().max().item() < 1e-3
+
+
 def test_p2p_ring_float32_and_errors(nnop):
     _p2p_case(nnop, 2, [0, 0], (1, 2, 1, 256, 32), torch.float32, True, tol=1e-4)
     q = torch.randn(1, 2, 255, 64, device="cuda", dtype=torch.bfloat16)
