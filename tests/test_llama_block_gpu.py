@@ -55,3 +55,52 @@ def test_llama3_attention_block_fwd_bwd(nnop, L):
     for name, a, b in zip(("dx", "dw_norm", "dwq", "dwk", "dwv"), grads, rgrads):
         rel = (a.double().cpu() - b).norm().item() / max(b.norm().item(), 1e-12)
         assert rel < 2e-2, (name, rel)         # reference-style norm-wise check (isapprox, rtol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 2e-2), (torch.float32, 2e-5)])
+def test_config_c3_rowwise_ops_full_shape(nnop, dtype, tol):
+    """BASELINE config C3 at its full size, one batch element: rms_norm / layer_norm over hidden 4096 on
+    L = 8192 rows (forward and backward), llama_rope on q (32 heads) / k (8 heads) of E = 128 at L = 8192 (forward
+    and pullback), online_softmax at the reference's benchmark shape (8192 x 1024, benchmarks/main.jl:279-300):
+    every element against the fp64 oracle.  These are the shapes `bench.py`'s `secondary` block times."""
+    hidden, L, QH, KH, E = 4096, 8192, 32, 8, 128
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(L, hidden, generator=g).to(dtype)
+    dy = torch.randn(L, hidden, generator=g).to(dtype)
+    w = (1.0 + 0.1 * torch.randn(hidden, generator=g)).to(dtype)
+    b = torch.rand(hidden, generator=g).to(dtype)
+    xd, dyd, wd, bd = x.cuda(), dy.cuda(), w.cuda(), b.cuda()
+    X, DY, W, Bb = x.double(), dy.double(), w.double(), b.double()
+    y, rstd = nnop._rms_norm(xd, wd)
+    assert max_abs(y, O.naive_rms_norm(X, W)) < tol
+    dx, dw = nnop.grad_rms_norm(dyd, rstd, xd, wd)
+    rx, rw = O.naive_rms_norm_bwd(DY, X, W)
+    assert max_abs(dx, rx) < tol
+    assert max_abs(dw, rw) < 1e-3 * max(1.0, rw.abs().max().item())      # dw stays Float32: 8192 fp32 adds per column
+    y, mean, rstd = nnop._layer_norm(xd, wd, bd)
+    assert max_abs(y, O.naive_layer_norm(X, W, Bb)) < tol
+    dx, dw, db = nnop.grad_layer_norm(dyd, mean, rstd, xd, wd, bd)
+    rx, rw, rb = O.naive_layer_norm_bwd(DY, X, W, Bb)
+    assert max_abs(dx, rx) < tol
+    wtol = 2e-2 if dtype == torch.bfloat16 else 1e-3                      # dw / db are returned in T
+    assert max_abs(dw, rw) < wtol * max(1.0, rw.abs().max().item())
+    assert max_abs(db, rb) < wtol * max(1.0, rb.abs().max().item())
+    del xd, dyd, X, DY, rx, y, dx
+    # RoPE
+    q = torch.randn(1, QH, L, E, generator=g).to(dtype)
+    k = torch.randn(1, KH, L, E, generator=g).to(dtype)
+    pos = torch.arange(L, dtype=torch.float32).view(1, L)
+    cos, sin = nnop.LlamaRotaryEmbedding(E)(pos)
+    q1, k1 = nnop.llama_rope(q.cuda(), k.cuda(), cos=cos.cuda(), sin=sin.cuda())
+    q2, k2 = O.naive_llama_rope(q.double(), k.double(), cos=cos.double(), sin=sin.double())
+    assert max_abs(q1, q2) < 4 * tol and max_abs(k1, k2) < 4 * tol
+    qb, kb = nnop.grad_llama_rope(q.cuda(), k.cuda(), cos=cos.cuda(), sin=sin.cuda())
+    q3, k3 = O.naive_llama_rope(q.double(), k.double(), cos=cos.double(), sin=sin.double(), bwd=True)
+    assert max_abs(qb, q3) < 4 * tol and max_abs(kb, k3) < 4 * tol
+    # softmax, reference benchmark shape
+    xs = torch.randn(1024, 8192, generator=g).to(dtype)
+    ds = torch.randn(1024, 8192, generator=g).to(dtype)
+    s = nnop.online_softmax(xs.cuda())
+    assert max_abs(s, O.naive_softmax(xs.double())) < (2e-3 if dtype == torch.bfloat16 else 1e-6)
+    gs = nnop.grad_online_softmax(ds.cuda(), s)
+    assert max_abs(gs, O.naive_softmax_bwd(ds.double(), s.double().cpu())) < tol
