@@ -320,9 +320,26 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
                       q_off + q0 + 128, bh_q);
       }
       load_kv(&tm_v, 0);
+      if constexpr (SINGLE) {
+        // K lives in slot 0 and V in slot 1 (uses counted per slot).  QK(i+1) completes before PV(i-1) does, so
+        // K(i+2) can be fetched before V(i+1): issue the loads in the order their slots come free
+        auto load_to = [&](const CUtensorMap* tm, int st, int blk) {
+          mbar_wait(&kv_empty[st], (blk & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[st], S::kTileBytes);
+#pragma unroll
+          for (int bx = 0; bx < S::kNBox; ++bx)
+            tma_load_3d(sKV + st * S::kTileBytes + bx * S::kBoxBytes, tm, &kv_full[st], bx * 64, k_off + blk * 128, bh_kv);
+        };
+        if (nblk > 1) load_to(&tm_k, 0, 1);
+        for (int i = 1; i < nblk; ++i) {
+          if (i + 1 < nblk) load_to(&tm_k, 0, i + 1);
+          load_to(&tm_v, 1, i);
+        }
+      } else {
       for (int i = 1; i < nblk; ++i) {
         load_kv(&tm_k, i);
         load_kv(&tm_v, i);
+      }
       }
     } else if (BIAS && warp == 3 && lane == 0 && nblk > 0) {
       // ================================ bias producer ================================
@@ -358,8 +375,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       };
       // descriptor address field is (byte address >> 4): advancing an operand = adding bytes/16.
       // (Building descriptors inside the asm block, as the backward does, measured 5% slower here.)
+      // (SINGLE: `t` names the S buffer -- there is one q tile and the logits are double-buffered)
       auto qk = [&](int t, int slot) {
-        const uint64_t a0 = dq0 + static_cast<uint64_t>((t * S::kTileBytes) >> 4);
+        const uint64_t a0 = dq0 + static_cast<uint64_t>(((SINGLE ? 0 : t) * S::kTileBytes) >> 4);
         const uint64_t b0 = dk0 + static_cast<uint64_t>(((slot % kNStage) * S::kTileBytes) >> 4);
         const uint32_t d = tm + t * 128;
         if (elect_one()) {
@@ -401,7 +419,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       // O_t += P_t[:, 64*hf .. 64*hf+64) V[64*hf .. 64*hf+64, :]
       auto pv_half = [&](int t, int slot, int hf, bool acc) {
         const uint64_t b0 = dv0 + static_cast<uint64_t>(((slot % kNStage) * S::kTileBytes) >> 4);
-        const uint32_t d = tm + 256 + t * D;
+        const uint32_t d = tm + 256 + (SINGLE ? 0 : t * D);
         // P aliases S columns [0, 64); QUAD: keys 64.. sit in the first 32 columns of the second half of S
         const uint32_t a = tm + t * 128 + ((QUAD && hf) ? 32 : 0);
         if (elect_one()) {
@@ -416,6 +434,44 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       auto commit = [&](uint64_t* bar) {
         if (elect_one()) tc_commit(bar);
       };
+      if constexpr (SINGLE) {
+        // One q tile, TWO S buffers (TMEM columns 0..127 / 128..255): QK(i+1) is issued before PV(i), so the
+        // tensor pipe computes the next block's logits while the softmax warpgroup works on the current one --
+        // the overlap the two-tile kernels get from their second tile.  K always sits in ring slot 0, V in
+        // slot 1.  In-order execution keeps QK(i+1) (which overwrites P(i-1)) behind PV(i-1).  o_full[1]
+        // completes a phase per PV: the softmax warpgroup waits on it before it rescales O.
+        mbar_wait(&q_full[0], 0);
+        slot_wait(0);
+        tc_fence_after();
+        qk(0, 0);
+        commit(&s_full[0]);
+        commit(&kv_empty[0]);
+        FWD_STAMP(0, 10);
+        for (int i = 0; i < nblk; ++i) {
+          const int bsel = i & 1, vslot = 2 * i + 1, knext = 2 * i + 2;
+          if (i + 1 < nblk) {
+            slot_wait(knext);
+            tc_fence_after();
+            FWD_STAMP(i, 11);
+            qk(bsel ^ 1, knext);
+            commit(&s_full[bsel ^ 1]);
+            commit(&kv_empty[knext % kNStage]);
+          }
+          mbar_wait(&p_half[2 * bsel], (i >> 1) & 1);
+          FWD_STAMP(i, 12);
+          slot_wait(vslot);
+          tc_fence_after();
+          FWD_STAMP(i, 13);
+          pv_half(bsel, vslot, 0, i > 0);
+          mbar_wait(&p_half[2 * bsel + 1], (i >> 1) & 1);
+          tc_fence_after();
+          pv_half(bsel, vslot, 1, true);
+          commit(&kv_empty[vslot % kNStage]);
+          commit(&o_full[1]);
+          if (i + 1 == nblk) commit(&o_full[0]);
+          FWD_STAMP(i, 14);
+        }
+      } else {
       mbar_wait(&q_full[0], 0);
       slot_wait(0);
       tc_fence_after();
@@ -476,6 +532,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
         }
         commit(&kv_empty[vslot % kNStage]);
         if (i + 1 < nblk) commit(&kv_empty[knext % kNStage]);
+      }
       }
     }
   } else if constexpr (QUAD) {
@@ -673,7 +730,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       const int row = wq * 32 + lane;
       const int q_row = q0 + t * 128 + row;
       const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
-      const uint32_t tS = tmem_base + lane_off + t * 128;
+      const uint32_t tS0 = tmem_base + lane_off + t * 128;
       const uint32_t tO = tmem_base + lane_off + 256 + t * D;
       // with a bias the logits are moved to log2 units as they are folded, so the rest runs unscaled
       // Float32 (SPLIT): q', k' are the caller's q, k times exact powers of two (scale block); the logit scale
@@ -698,7 +755,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
       for (int i = 0; i < nbt; ++i) {
         const uint32_t mb = mb_next;
         if (kmask && i + 1 < nbt) mb_next = mask_bytes(i + 1);
-        mbar_wait(&s_full[t], i & 1);
+        // SINGLE: the logits alternate between two TMEM buffers (block i -> buffer i & 1, a phase every other block)
+        const int bsel = SINGLE ? (i & 1) : t;
+        const uint32_t bph = SINGLE ? ((i >> 1) & 1) : (i & 1);
+        const uint32_t tS = SINGLE ? tS0 + bsel * 128 : tS0;
+        mbar_wait(&s_full[bsel], bph);
         tc_fence_after();
         if (wq == 0 && !FWD_TRACE_WARPS) FWD_STAMP(i, 5 * t + 0);
         uint32_t sr[4][32];
@@ -815,6 +876,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
           m_used = m_new;
           l *= alpha;
           if (i > 0) {
+            if constexpr (SINGLE) {   // S(i) was issued ahead of PV(i-1): O is only stable once that PV has completed
+              mbar_wait(&o_full[1], (i - 1) & 1);
+              tc_fence_after();
+            }
 #pragma unroll
             for (int c = 0; c < D / 32; ++c) {
               uint32_t orow[32];
@@ -850,7 +915,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q,
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_half[2 * t + (kSplitPV ? (c >> 1) : 0)]);
+            if (lane == 0) mbar_arrive(&p_half[2 * bsel + (kSplitPV ? (c >> 1) : 0)]);
             if (FWD_TRACE_WARPS ? t == 0 : wq == 0) FWD_STAMP(i, FWD_TRACE_WARPS ? 4 * wq + 2 + (c >> 1) : 5 * t + 3 + (c >> 1));
           }
         }

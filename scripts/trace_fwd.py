@@ -6,7 +6,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else "trace"
 os.environ["NNOP_B200_LIB"] = str(ROOT / "nnop.jl_b200" / "lib" / "variants" / f"libnnop_b200_{name}.so")
 sys.path.insert(0, str(ROOT / "nnop.jl_b200"))
 import torch, nnop_b200 as nn
-B, H, L, E = 2, 74, 8192, 128
+E = int(os.environ.get("TRACE_E", "128"))   # 256: the one-tile kernel (stamps 11..14 = K ready, P seen, V ready, block issued)
+B, H, L = 2, 74, 8192
 q, k, v = (torch.randn(B, H, L, E, device="cuda", dtype=torch.bfloat16) for _ in range(3))
 for _ in range(3):
     nn._flash_attention(q, k, v, causal=True)
