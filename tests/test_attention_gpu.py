@@ -263,7 +263,7 @@ def _zero_masked_check(nnop, q, k, v, dO, m, causal):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("E", [128, 64])
+@pytest.mark.parametrize("E", [128, 64, 256])   # 256: the one-q-tile-per-CTA forward (its backward is SIMT)
 @pytest.mark.parametrize("causal", [False, True])
 def test_tcgen05_kpad_mask(nnop, dtype, E, causal):
     """kpad_mask on the tensor-core path: the reference's own pattern (test/attention_tests.jl:27-28,
