@@ -307,7 +307,7 @@ def run_ours(args, rank, local_rank, world):
                 "kernel_ms": kern_ms, "algorithmic_flops_per_launch": f_bwd}
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # the CPU baseline is timed at N = 1 only (rank 0's host cores)
         threads = os.cpu_count() or 1
         sb, sh, reps = 1, 1, 0
         t_cpu, t_start = 0.0, time.perf_counter()
